@@ -1,0 +1,211 @@
+"""ctypes binding of the C-ABI CUDA library (``include/wfagpu.h``).
+
+The library is the only compute path of this package: if ``libwfagpu.so`` is missing or no
+B200 is visible, calls raise -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwfagpu.so")
+
+CONFIG_FIELDS = [
+    "distance", "scope", "span",
+    "pattern_begin_free", "pattern_end_free", "text_begin_free", "text_end_free",
+    "heuristic", "min_wavefront_length", "max_distance_threshold",
+    "steps_between_cutoffs", "xdrop",
+    "match", "mismatch", "gap_opening1", "gap_extension1", "gap_opening2", "gap_extension2",
+    "max_steps", "reserved",
+]
+
+
+class Config(C.Structure):
+    """``wfagpu_config_t``"""
+    _fields_ = [(f, C.c_int32) for f in CONFIG_FIELDS]
+
+
+class BatchStats(C.Structure):
+    """``wfagpu_batch_stats_t``"""
+    _fields_ = [(f, C.c_int64) for f in (
+        "n_pairs", "kernel_launches", "packed_bytes", "h2d_bytes", "d2h_bytes", "cells",
+        "history_bytes", "retried_pairs")]
+
+
+OK, EINVAL, ECUDA, ENOMEM, ENODEVICE, EUNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+
+class WfaGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"wfagpu error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load ``libwfagpu.so`` (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m pywfa_b200.build` "
+            "(pywfa_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, cp = C.c_void_p, C.c_int64, C.c_char_p
+    cfgp = vp          # any structure with wfagpu_config_t's layout, passed by address
+    L.wfagpu_config_default.argtypes = [cfgp]
+    L.wfagpu_config_default.restype = None
+    L.wfagpu_config_check.argtypes = [cfgp, i64, i64, cp, C.c_size_t]
+    L.wfagpu_config_check.restype = C.c_int
+    L.wfagpu_device_count.argtypes = []
+    L.wfagpu_device_count.restype = C.c_int
+    L.wfagpu_create.argtypes = [C.POINTER(vp), C.c_int, cp, C.c_size_t]
+    L.wfagpu_create.restype = C.c_int
+    L.wfagpu_destroy.argtypes = [vp]
+    L.wfagpu_destroy.restype = None
+    L.wfagpu_last_error.argtypes = [vp]
+    L.wfagpu_last_error.restype = cp
+    L.wfagpu_strerror.argtypes = [C.c_int]
+    L.wfagpu_strerror.restype = cp
+    seq_args = [vp, vp, vp, vp, vp, i64]          # seq, p_off, p_len, t_off, t_len, n
+    out_args = [vp, vp, vp, vp, C.POINTER(vp)]    # score, status, locs, cig_off, cig_runs
+    L.wfagpu_align_batch.argtypes = [vp, cfgp] + seq_args + out_args
+    L.wfagpu_align_batch.restype = C.c_int
+    L.wfagpu_batch_prepare.argtypes = [vp, cfgp] + seq_args + [C.POINTER(vp)]
+    L.wfagpu_batch_prepare.restype = C.c_int
+    L.wfagpu_batch_run.argtypes = [vp, vp, vp]
+    L.wfagpu_batch_run.restype = C.c_int
+    L.wfagpu_batch_fetch.argtypes = [vp, vp] + out_args
+    L.wfagpu_batch_fetch.restype = C.c_int
+    L.wfagpu_batch_free.argtypes = [vp, vp]
+    L.wfagpu_batch_free.restype = None
+    L.wfagpu_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
+    L.wfagpu_batch_get_stats.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One ``wfagpu_ctx`` (= one CUDA device)."""
+
+    def __init__(self, device: int = 0):
+        L = lib()
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = L.wfagpu_create(C.byref(h), device, err, len(err))
+        if rc != OK:
+            raise WfaGpuError(rc, err.value.decode() or L.wfagpu_strerror(rc).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().wfagpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != OK:
+            raise WfaGpuError(rc, lib().wfagpu_last_error(self._h).decode())
+
+    @staticmethod
+    def _inputs(seq, p_off, p_len, t_off, t_len):
+        seq = np.ascontiguousarray(seq, np.uint8)
+        p_off = np.ascontiguousarray(p_off, np.int64)
+        t_off = np.ascontiguousarray(t_off, np.int64)
+        p_len = np.ascontiguousarray(p_len, np.int32)
+        t_len = np.ascontiguousarray(t_len, np.int32)
+        n = len(p_len)
+        if not (len(p_off) == len(t_off) == len(t_len) == n):
+            raise ValueError("offset/length arrays differ in length")
+        if n:
+            if (p_off < 0).any() or (t_off < 0).any() or int((p_off + p_len).max()) > len(seq) \
+                    or int((t_off + t_len).max()) > len(seq):
+                raise ValueError("a pair lies outside the sequence buffer")
+        return seq, p_off, p_len, t_off, t_len, n
+
+    def align_batch(self, cfg: Config, seq, p_off, p_len, t_off, t_len):
+        """``wfagpu_align_batch`` on host arrays; returns a dict of numpy arrays."""
+        seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len)
+        score = np.empty(n, np.int32)
+        status = np.empty(n, np.int32)
+        locs = np.empty((n, 4), np.int32)
+        cig_off = np.empty(n + 1, np.int64)
+        runs_p = C.c_void_p()
+        rc = lib().wfagpu_align_batch(self._h, C.addressof(cfg), _ptr(seq), _ptr(p_off), _ptr(p_len),
+                                      _ptr(t_off), _ptr(t_len), n, _ptr(score), _ptr(status),
+                                      _ptr(locs), _ptr(cig_off), C.byref(runs_p))
+        self._check(rc)
+        total = int(cig_off[n])
+        if total:
+            runs = np.ctypeslib.as_array(C.cast(runs_p, C.POINTER(C.c_uint32)), shape=(total,)).copy()
+        else:
+            runs = np.zeros(0, np.uint32)
+        return dict(score=score, status=status, locs=locs, cig_off=cig_off, runs=runs)
+
+    def prepare(self, cfg: Config, seq, p_off, p_len, t_off, t_len) -> "Batch":
+        seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len)
+        h = C.c_void_p()
+        rc = lib().wfagpu_batch_prepare(self._h, C.addressof(cfg), _ptr(seq), _ptr(p_off), _ptr(p_len),
+                                        _ptr(t_off), _ptr(t_len), n, C.byref(h))
+        self._check(rc)
+        return Batch(self, h, n)
+
+
+class Batch:
+    """A packed, HBM-resident batch (``wfagpu_batch``): ``run`` launches kernels only."""
+
+    def __init__(self, ctx: Context, h, n: int):
+        self.ctx, self._h, self.n = ctx, h, n
+
+    def run(self, stream=None):
+        self.ctx._check(lib().wfagpu_batch_run(self.ctx._h, self._h, C.c_void_p(stream) if stream else None))
+
+    def fetch(self, cigars: bool = True):
+        n = self.n
+        score = np.empty(n, np.int32)
+        status = np.empty(n, np.int32)
+        locs = np.empty((n, 4), np.int32)
+        cig_off = np.empty(n + 1, np.int64)
+        runs_p = C.c_void_p()
+        rc = lib().wfagpu_batch_fetch(self.ctx._h, self._h, _ptr(score), _ptr(status), _ptr(locs),
+                                      _ptr(cig_off), C.byref(runs_p) if cigars else None)
+        self.ctx._check(rc)
+        total = int(cig_off[n])
+        if cigars and total:
+            runs = np.ctypeslib.as_array(C.cast(runs_p, C.POINTER(C.c_uint32)), shape=(total,)).copy()
+        else:
+            runs = np.zeros(0, np.uint32)
+        return dict(score=score, status=status, locs=locs, cig_off=cig_off, runs=runs)
+
+    def stats(self) -> dict:
+        s = BatchStats()
+        lib().wfagpu_batch_get_stats(self._h, C.byref(s))
+        return {f: int(getattr(s, f)) for f, _ in BatchStats._fields_}
+
+    def free(self):
+        if self._h:
+            lib().wfagpu_batch_free(self.ctx._h, self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,75 @@
+"""In-tree build of the C-ABI CUDA library ``pywfa_b200/libwfagpu.so`` (sm_100a only).
+
+``python -m pywfa_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles without a GPU.
+The built ``.so`` stays in-tree (git-ignored) so that it travels with the repository snapshot.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libwfagpu.so")
+OBJ = os.path.join(HERE, "csrc", "build")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-Wno-deprecated-gpu-targets"]
+CXX_FLAGS = ["-O3", "-march=x86-64-v3", "-std=c++17", "-fPIC", "-Wall"]
+
+
+def _cuda_home() -> str:
+    for c in (os.environ.get("CUDA_HOME"), "/usr/local/cuda"):
+        if c and os.path.exists(os.path.join(c, "bin", "nvcc")):
+            return c
+    nv = shutil.which("nvcc")
+    if nv:
+        return os.path.dirname(os.path.dirname(nv))
+    raise RuntimeError("nvcc not found")
+
+
+def _stale(target: str, deps) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    cuda = _cuda_home()
+    nvcc = os.path.join(cuda, "bin", "nvcc")
+    os.makedirs(OBJ, exist_ok=True)
+    headers = [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(HERE, "..", "include", "wfagpu.h"))
+    jobs = [
+        ("wfa_kernels.cu", [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])),
+        ("wfagpu_api.cpp", ["g++"] + CXX_FLAGS + ["-I" + os.path.join(cuda, "include")]),
+        ("pack.cpp", ["g++"] + CXX_FLAGS),
+    ]
+    objs, procs = [], []
+    for src, cmd in jobs:
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            procs.append((src, subprocess.Popen(cmd + ["-c", s, "-o", o], stdout=subprocess.PIPE,
+                                                stderr=subprocess.STDOUT, text=True)))
+    rebuilt = bool(procs)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"compiling {src} failed:\n{out}")
+        if verbose and out:
+            print(out)
+    if rebuilt or not os.path.exists(OUT):
+        r = subprocess.run([nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-lpthread"],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"linking libwfagpu.so failed:\n{r.stdout}")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,28 @@
+/* pack.h -- host-side batch layout + 2-bit packing (internal, C++ linkage). */
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wfagpu {
+
+struct PairMetaHost {   /* must match wfagpu::PairMeta (wfa_core.cuh) */
+  int64_t woff;
+  int32_t plen, tlen;
+};
+
+/* Pack one sequence (ASCII, any case) into 2-bit words; false if a non-ACGT byte was seen. */
+bool pack_sequence(const uint8_t* s, int len, uint32_t* out);
+
+/* Word offsets of every pair (pattern words, then text words); returns the total word count. */
+int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, PairMetaHost* meta,
+                     int32_t* max_plen, int32_t* max_tlen);
+
+/* Pack all pairs (multi-threaded).  Returns -1, or the index of the first pair holding a
+ * byte outside ACGT/acgt. */
+int64_t pack_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
+                   const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint);
+
+void parallel_copy(void* dst, const void* src, size_t bytes);
+int pack_threads(int64_t n_items, int64_t bytes);
+
+}  // namespace wfagpu

@@ -1,0 +1,622 @@
+/*
+ * wfa_core.cuh -- the wavefront-alignment hot path for one read pair, written for a
+ * cooperating thread group (a warp, or a whole CTA) on sm_100a.
+ *
+ * This is a from-scratch B200 design of the path that pywfa drives in WFA2-lib
+ * (reference citations: W/ = pywfa/WFA2_lib/ in the reference checkout):
+ *
+ *   - the gap-affine / gap-affine-2p recurrence (W/wavefront/wavefront_compute_affine.c:44-86,
+ *     wavefront_compute_affine2p.c:45-106) and the exact-match extension
+ *     (W/wavefront/wavefront_extend_kernels.c:64-163) are FUSED: the lane that produces
+ *     M[s][k] extends it at once, 16 bases per step, by XOR-ing two funnel-shifted 32-bit
+ *     words of the 2-bit packed sequences and counting the agreeing low bit pairs;
+ *   - the offset wavefronts live in a ring of max_score_scope slots (M) and e+1 slots
+ *     (I1/D1/I2/D2) in shared memory (or in an L2-resident HBM arena for very wide
+ *     wavefronts); "outside [lo,hi] reads as NULL" (W/wavefront/wavefront_compute.c:490-567)
+ *     is a range check at load time instead of NULL padding;
+ *   - trim_ends (W/wavefront/wavefront_compute.c:571-605), end-to-end / ends-free termination
+ *     (W/wavefront/wavefront_termination.c:37-162) and the WF-adaptive / X-drop cut-offs
+ *     (W/wavefront/wavefront_heuristic.c:257-383,509-567) are min-reductions over the group;
+ *   - scope=full spills one (pre-extension M offset, origin code) record per cell to a
+ *     per-group HBM arena with coalesced stores; the backtrace
+ *     (W/wavefront/wavefront_backtrace.c:320-529) then follows the recorded origin codes,
+ *     which hold the winner of the reference's (offset<<4 | type) max and one ext/open bit
+ *     per gap component, and emits run-length encoded CIGAR words directly.
+ *
+ * The file is also compiled as plain host C++ with a one-thread group by tests/emu/ (test
+ * infrastructure for the CPU-only CI; never part of the product library).
+ */
+#pragma once
+#include <stdint.h>
+#include <limits.h>
+
+#ifdef __CUDACC__
+#define WFA_DEV __device__ __forceinline__
+#define WFA_DEV_NOINLINE __device__ __noinline__
+#else
+#define WFA_DEV inline
+#define WFA_DEV_NOINLINE inline
+#endif
+
+namespace wfagpu {
+
+constexpr int OFFNULL = INT32_MIN / 2;      /* W/wavefront/wavefront_offset.h:44 */
+constexpr int KNONE = INT_MAX;
+
+enum { CM = 0, CI1 = 1, CD1 = 2, CI2 = 3, CD2 = 4 };
+/* backtrace_type priorities, W/wavefront/wavefront_backtrace.c:49-59 */
+enum { BT_NONE = 0, BT_I1_OPEN = 1, BT_I1_EXT = 2, BT_I2_OPEN = 3, BT_I2_EXT = 4, BT_D1_OPEN = 5,
+       BT_D1_EXT = 6, BT_D2_OPEN = 7, BT_D2_EXT = 8, BT_M = 9 };
+
+/* per-pair outcome of one tier */
+enum { PAIR_DONE = 0, PAIR_OVERFLOW = 1 };
+
+/* status codes, W/wavefront/wfa.h:46-55 */
+constexpr int ST_COMPLETED = 0, ST_PARTIAL = 1, ST_MAX_STEPS = -100, ST_OOM = -200;
+
+constexpr int META_INTS = 12;   /* flags, clo, (lo,hi) x 5 components */
+constexpr int FLAG_EXISTS = 1;  /* M wavefront allocated at this score   */
+WFA_DEV int comp_bit(int c) { return 2 << c; }
+
+/* SAM op codes (pywfa/align.pyx:11-14) */
+constexpr uint32_t OP_M = 0, OP_I = 1, OP_D = 2, OP_X = 8;
+
+struct PairMeta {      /* 16 bytes, one per pair, in HBM */
+  int64_t woff;        /* first 32-bit word of the packed pattern; text words follow it */
+  int32_t plen, tlen;
+};
+
+struct KParams {
+  /* normalised penalties (W/wavefront/wavefront_penalties.c:95-173) */
+  int x, o1, e1, o2, e2, match;
+  int max_scope;                 /* W/wavefront/wavefront_components.c:81-124 */
+  int rm, r1, r2;                /* ring slots: M, I1/D1, I2/D2 */
+  int endsfree;                  /* span */
+  int pbf, pef, tbf, tef;
+  int heuristic, min_wf_len, max_dist_thr, steps_between, xdrop;
+  int max_steps;                 /* INT_MAX = unlimited */
+  /* user (un-normalised) penalties are not needed on the device: maxtrim only ever
+   * sees an empty CIGAR on this path. */
+  /* tier capacities */
+  int wcap;                      /* max wavefront width (diagonals) per ring slot */
+  int seq_words_cap;             /* words of smem for both packed sequences (0: read HBM) */
+  long long hcap;                /* history cells per group */
+  int scap;                      /* history score-table entries per group */
+  int runcap;                    /* CIGAR run staging words per group */
+  /* batch */
+  const PairMeta* pairs;
+  const uint32_t* words;
+  const int* worklist;           /* pair ids, or nullptr = identity */
+  const int* n_work;             /* device pointer to the number of work items */
+  int* work_counter;
+  int* retry_list; int* retry_count;
+  /* results (SoA) */
+  int* score; int* status; int* locs; int* nruns; long long* runs_base;
+  /* scope=full scratch */
+  int* hist_m0; uint8_t* hist_code; int2* hmeta; uint32_t* runs_stage;
+  uint32_t* runs_tmp; unsigned long long* runs_cursor; unsigned long long runs_tmp_cap;
+  /* global ring arena for the widest tier (ints per group = ring_ints) */
+  int* gring; long long gring_ints;
+  unsigned long long* cells_total;
+};
+
+/* pointers a group works with for the current pair */
+struct GroupMem {
+  const uint32_t* pw; const uint32_t* tw;   /* packed sequences, readable one word past the end */
+  int* ring[5];
+  int* meta;
+  int* h_m0; uint8_t* h_code; int2* hmeta; uint32_t* runs_stage;
+};
+
+struct PairResult {
+  int score, status;
+  int locs[4];
+  int nruns;
+  long long cells;
+};
+
+/* ------------------------------------------------------------------------------------ */
+#ifdef __CUDACC__
+WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
+WFA_DEV int first_set(uint32_t x) { return __ffs((int)x) - 1; }
+#else
+WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
+  const uint64_t v = ((uint64_t)hi << 32) | lo;
+  return (uint32_t)(v >> (sh & 31));
+}
+WFA_DEV int first_set(uint32_t x) { return __builtin_ctz(x); }
+#endif
+WFA_DEV int imax(int a, int b) { return a > b ? a : b; }
+WFA_DEV int imin(int a, int b) { return a < b ? a : b; }
+
+/* 16 bases starting at base index i (base j of a word sits in bits 2j..2j+1) */
+WFA_DEV uint32_t fetch16(const uint32_t* w, int i) {
+  const int j = i >> 4;
+  return funnel_r(w[j], w[j + 1], (i & 15) << 1);
+}
+
+/*
+ * Exact-match extension of one diagonal (what wavefront_extend_matches_kernel_blockwise,
+ * W/wavefront/wavefront_extend_kernels.c:64-88, does 8 bytes at a time with sentinels):
+ * here 16 bases per XOR, clamped to the sequence ends instead of sentinels.
+ */
+WFA_DEV int extend_offset(const uint32_t* pw, const uint32_t* tw, int plen, int tlen, int k, int off) {
+  int v = off - k, h = off;
+  const int rem = imin(plen - v, tlen - h);
+  int n = 0;
+  while (n < rem) {
+    const uint32_t x = fetch16(pw, v + n) ^ fetch16(tw, h + n);
+    if (x) { n += first_set(x) >> 1; break; }
+    n += 16;
+  }
+  return off + imin(n, rem);
+}
+
+WFA_DEV bool in_bounds(int k, int off, int plen, int tlen) {
+  return (uint32_t)off <= (uint32_t)tlen && (uint32_t)(off - k) <= (uint32_t)plen;
+}
+
+/* wavefront_compute_classic_score, W/wavefront/wavefront_compute.c:108-120 with
+ * WF_SCORE_TO_SW_SCORE (wavefront_penalties.h:73): int32 wrap-around, C truncating division */
+WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
+  const int swg_match = -match;
+  if (swg_match == 0) return -wf_score;
+  const int32_t sum = (int32_t)((uint32_t)plen + (uint32_t)tlen);
+  const int32_t prod = (int32_t)((uint32_t)swg_match * (uint32_t)sum);
+  return (int32_t)((uint32_t)prod - (uint32_t)wf_score) / 2;
+}
+
+/* one source wavefront component as the recurrence reads it */
+struct Src {
+  const int* slot;   /* ring slot base */
+  int clo;           /* diagonal stored at slot[0] */
+  int lo, hi;        /* valid range; lo > hi = null */
+};
+WFA_DEV int rd(const Src& s, int k) {
+  return (k >= s.lo && k <= s.hi) ? s.slot[k - s.clo] : OFFNULL;
+}
+
+WFA_DEV int wrap_sub(int cur, int d, int n) { int t = cur - d; return t < 0 ? t + n : t; }
+
+/* ---- CIGAR run emitter (rank 0 only); runs are produced end -> start --------------- */
+struct RunEmitter {
+  uint32_t* stage; int cap; int n; uint32_t op; int len;
+  WFA_DEV void init(uint32_t* s, int c) { stage = s; cap = c; n = 0; op = 0xffu; len = 0; }
+  WFA_DEV void flush() { if (len > 0 && n < cap) stage[n] = ((uint32_t)len << 4) | op; if (len > 0) ++n; len = 0; }
+  WFA_DEV void push(uint32_t o, int cnt) {
+    if (cnt <= 0) return;
+    if (o == op) { len += cnt; return; }
+    flush(); op = o; len = cnt;
+  }
+};
+
+/*
+ * Backtrace over the recorded history (W/wavefront/wavefront_backtrace.c:320-529).  One
+ * thread.  At an M cell the origin code gives the winning source type and the stored
+ * pre-extension offset gives the length of the match run; inside a gap only the ext/open
+ * bit of that component is needed.  Runs are written end -> start into `em`.
+ */
+template <bool TWO_P>
+WFA_DEV void backtrace(const KParams& P, const GroupMem& gm, int plen, int tlen,
+                       int a_score, int a_k, int a_off, RunEmitter& em) {
+  int mt = CM, score = a_score, k = a_k;
+  int off = a_off;
+  int h = a_off, v = a_off - a_k;
+  if (v < plen) em.push(OP_D, plen - v);
+  if (h < tlen) em.push(OP_I, tlen - h);
+  while (v > 0 && h > 0 && score > 0) {
+    const int2 hm = gm.hmeta[score];
+    const long long idx = (long long)hm.x + (k - hm.y);
+    const int code = gm.h_code[idx];
+    int type;
+    if (mt == CM) {
+      type = code & 15;
+      if (type == BT_NONE) break;
+      const int m0 = gm.h_m0[idx];
+      em.push(OP_M, off - m0);
+      off = m0;
+      v = off - k; h = off;
+      if (v <= 0 || h <= 0) break;
+    } else if (mt == CI1) type = (code & 0x10) ? BT_I1_EXT : BT_I1_OPEN;
+    else if (mt == CD1) type = (code & 0x20) ? BT_D1_EXT : BT_D1_OPEN;
+    else if (mt == CI2) type = (code & 0x40) ? BT_I2_EXT : BT_I2_OPEN;
+    else type = (code & 0x80) ? BT_D2_EXT : BT_D2_OPEN;
+    switch (type) {
+      case BT_M: score -= P.x; mt = CM; break;
+      case BT_I1_OPEN: score -= P.o1 + P.e1; mt = CM; break;
+      case BT_I1_EXT: score -= P.e1; mt = CI1; break;
+      case BT_I2_OPEN: score -= P.o2 + P.e2; mt = CM; break;
+      case BT_I2_EXT: score -= P.e2; mt = CI2; break;
+      case BT_D1_OPEN: score -= P.o1 + P.e1; mt = CM; break;
+      case BT_D1_EXT: score -= P.e1; mt = CD1; break;
+      case BT_D2_OPEN: score -= P.o2 + P.e2; mt = CM; break;
+      default: score -= P.e2; mt = CD2; break;
+    }
+    if (type == BT_M) { em.push(OP_X, 1); --off; }
+    else if (type <= BT_I2_EXT) { em.push(OP_I, 1); --k; --off; }
+    else { em.push(OP_D, 1); ++k; }
+    v = off - k; h = off;
+  }
+  if (mt == CM) {
+    if (v > 0 && h > 0) {
+      const int n = imin(v, h);
+      em.push(OP_M, n);
+      v -= n; h -= n;
+    }
+    em.push(OP_D, v);
+    em.push(OP_I, h);
+  }
+  em.flush();
+}
+
+/* `locations` of pywfa (pywfa/align.pyx:788-833) from the staged (reversed) runs */
+WFA_DEV void locations_from_stage(const uint32_t* stage, int n, int plen, int tlen, int* locs) {
+  locs[0] = locs[1] = locs[2] = locs[3] = 0;
+  if (n == 0 || plen == 0 || tlen == 0) return;
+  int ps = 0, ts = 0;
+  for (int i = n - 1; i >= 0; --i) {          /* CIGAR order = reverse staging order */
+    const uint32_t w = stage[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
+    if (op == OP_M) break;
+    if (op == OP_D) ps += ln; else if (op == OP_X) { ps += ln; ts += ln; } else ts += ln;
+  }
+  int pe = plen, te = tlen;
+  for (int i = 0; i < n; ++i) {
+    const uint32_t w = stage[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
+    if (op == OP_M) break;
+    if (op == OP_D) pe -= ln; else if (op == OP_X) { pe -= ln; te -= ln; } else te -= ln;
+  }
+  locs[0] = ps; locs[1] = pe; locs[2] = ts; locs[3] = te;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/*
+ * Align one pair with the thread group `g`.  G provides: rank, size, sync(),
+ * template<int N> allmin(int (&v)[N]).
+ * Returns PAIR_DONE (res filled; for scope=full the reversed runs are in gm.runs_stage)
+ * or PAIR_OVERFLOW (a tier capacity was exceeded; retry on a larger tier).
+ */
+template <class G, bool TWO_P, bool FULL>
+WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int tlen, PairResult& res) {
+  const int NC = TWO_P ? 5 : 3;
+  const int wcap = P.wcap;
+  int* const meta = gm.meta;
+  const int ak = tlen - plen;
+
+  int s = 0, cur = 0, c1 = 0, c2 = 0;
+  int num_null = 0;
+  int steps_wait = P.steps_between;          /* W/wavefront/wavefront_heuristic.c:114-121 */
+  int max_sw = 0; bool sw_init = false;
+  long long cells = 0;
+  long long cell_off = 0;
+  /* state of the current score's wavefront, uniform across the group */
+  bool cur_exists;
+  int clo[5], chi[5];
+  int term_k;
+  int end_k = KNONE, end_off = OFFNULL;
+  int status;                                 /* 0 running, 1 end reached, 2 unreachable, 3 max steps */
+
+  /* ---- score 0: wavefront_aligner_init_wf_m, W/wavefront/wavefront_aligner.c:251-310 ---- */
+  {
+    const bool ef = P.endsfree && P.match == 0;
+    const int lo = ef ? -P.pbf : 0, hi = ef ? P.tbf : 0;
+    if (hi - lo + 1 > wcap) return PAIR_OVERFLOW;
+    int t = KNONE;
+    int* const mslot = gm.ring[CM];
+    for (int k = lo + g.rank; k <= hi; k += g.size) {
+      const int off0 = k > 0 ? k : 0;
+      const int off = extend_offset(gm.pw, gm.tw, plen, tlen, k, off0);
+      mslot[k - lo] = off;
+      bool term;
+      if (P.endsfree) {
+        const int hh = off, vv = off - k;
+        term = (hh >= tlen && plen - vv <= P.pef) || (vv >= plen && tlen - hh <= P.tef);
+      } else term = (k == ak && off >= tlen);
+      if (term) t = imin(t, k);
+    }
+    int r[1] = {t};
+    g.template allmin<1>(r);
+    term_k = r[0];
+    for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
+    clo[CM] = lo; chi[CM] = hi;
+    cur_exists = true;
+    if (g.rank == 0) {
+      meta[0] = FLAG_EXISTS | comp_bit(CM);
+      meta[1] = lo;
+      meta[2] = lo; meta[3] = hi;
+      for (int c = 1; c < 5; ++c) { meta[2 + 2 * c] = 1; meta[3 + 2 * c] = -1; }
+    }
+    g.sync();
+  }
+
+  for (;;) {
+    /* ---- after-extend step of score s (extend.c:90-125 / :263-297) ---- */
+    if (!cur_exists) {
+      if (num_null > P.max_scope) { status = 2; break; }          /* extend.c:99-106 */
+    } else {
+      const int cur_clo = meta[cur * META_INTS + 1];
+      if (term_k != KNONE) {
+        end_k = term_k;
+        end_off = gm.ring[CM][cur * wcap + (term_k - cur_clo)];
+        status = 1;
+        cells += imax(0, chi[CM] - clo[CM] + 1);
+        break;
+      }
+      if (P.heuristic != 0 && clo[CM] <= chi[CM]) {
+        /* wavefront_heuristic_cufoff, heuristic.c:509-567 */
+        --steps_wait;
+        const int lo_base = clo[CM], hi_base = chi[CM];
+        const int* const mslot = gm.ring[CM] + cur * wcap;
+        if (steps_wait <= 0) {
+          if (P.heuristic == 1) {
+            /* wavefront_heuristic_wfadaptive, heuristic.c:257-293 */
+            if (hi_base - lo_base + 1 >= P.min_wf_len) {
+              int dm = INT_MAX;
+              for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
+                const int f = mslot[k - cur_clo];
+                const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
+                dm = imin(dm, d);
+              }
+              int r1[1] = {dm};
+              g.template allmin<1>(r1);
+              const int min_d = imin(imax(plen, tlen), r1[0]);
+              int kf = INT_MAX, kl = INT_MIN;
+              for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
+                const int f = mslot[k - cur_clo];
+                const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
+                if (d - min_d <= P.max_dist_thr) { kf = imin(kf, k); kl = imax(kl, k); }
+              }
+              int r2[2] = {kf, kl == INT_MIN ? INT_MAX : -kl};
+              g.template allmin<2>(r2);
+              kf = r2[0]; kl = (r2[1] == INT_MAX) ? INT_MIN : -r2[1];
+              const int top_limit = imin(ak, hi_base);
+              const int nlo = (kf < top_limit) ? kf : imax(lo_base, top_limit);
+              const int bottom = imax(ak, nlo);
+              const int nhi = (kl > bottom) ? kl : imin(hi_base, bottom);
+              clo[CM] = nlo; chi[CM] = nhi;
+              steps_wait = P.steps_between;
+            }
+          } else {
+            /* wavefront_heuristic_xdrop, heuristic.c:329-383 (+ sw scores :297-328) */
+            const int swg = (P.match != 0) ? -P.match : -1;
+            int cmax = INT_MIN, kf = INT_MAX, kl = INT_MIN;
+            for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
+              const int f = mslot[k - cur_clo];
+              if (f < 0) continue;
+              const int sw = (swg * (2 * f - k) - s) / 2;
+              cmax = imax(cmax, sw);
+              if (sw_init && max_sw - sw < P.xdrop) { kf = imin(kf, k); kl = imax(kl, k); }
+            }
+            int r3[3] = {cmax == INT_MIN ? INT_MAX : -cmax, kf, kl == INT_MIN ? INT_MAX : -kl};
+            g.template allmin<3>(r3);
+            cmax = (r3[0] == INT_MAX) ? INT_MIN : -r3[0];
+            kf = r3[1]; kl = (r3[2] == INT_MAX) ? INT_MIN : -r3[2];
+            if (sw_init) {
+              const int nlo = (kf == INT_MAX) ? hi_base + 1 : kf;
+              const int nhi = (kl >= nlo) ? kl : imin(nlo - 1, hi_base);
+              clo[CM] = nlo; chi[CM] = nhi;
+              if (cmax > max_sw) max_sw = cmax;
+            } else { max_sw = cmax; sw_init = true; }
+            steps_wait = P.steps_between;
+          }
+        }
+        if (clo[CM] != lo_base || chi[CM] != hi_base) {
+          /* wf_heuristic_equate, heuristic.c:161-172 */
+          for (int c = 1; c < NC; ++c) {
+            if (clo[c] > chi[c]) continue;
+            if (clo[CM] > clo[c]) clo[c] = clo[CM];
+            if (chi[CM] < chi[c]) chi[c] = chi[CM];
+          }
+          if (g.rank == 0) {
+            int fl = FLAG_EXISTS;
+            for (int c = 0; c < NC; ++c) {
+              const bool nn = clo[c] <= chi[c];
+              if (nn) fl |= comp_bit(c);
+              meta[cur * META_INTS + 2 + 2 * c] = nn ? clo[c] : 1;
+              meta[cur * META_INTS + 3 + 2 * c] = nn ? chi[c] : -1;
+            }
+            meta[cur * META_INTS] = fl;
+          }
+          g.sync();
+        }
+      }
+      cells += imax(0, chi[CM] - clo[CM] + 1);
+    }
+
+    /* ---- compute score s+1 (compute_affine.c:229-260 / compute_affine2p.c:334-368) ---- */
+    ++s;
+    if (++cur == P.rm) cur = 0;
+    if (++c1 == P.r1) c1 = 0;
+    if (TWO_P) { if (++c2 == P.r2) c2 = 0; }
+    {
+      const int sx = s - P.x, so1 = s - P.o1 - P.e1, se1 = s - P.e1;
+      const int slx = wrap_sub(cur, P.x, P.rm), slo1 = wrap_sub(cur, P.o1 + P.e1, P.rm),
+                sle1 = wrap_sub(cur, P.e1, P.rm);
+      const int fx = sx >= 0 ? meta[slx * META_INTS] : 0;
+      const int fo1 = so1 >= 0 ? meta[slo1 * META_INTS] : 0;
+      const int fe1 = se1 >= 0 ? meta[sle1 * META_INTS] : 0;
+      int slo2 = 0, sle2 = 0, fo2 = 0, fe2 = 0;
+      if (TWO_P) {
+        const int so2 = s - P.o2 - P.e2, se2 = s - P.e2;
+        slo2 = wrap_sub(cur, P.o2 + P.e2, P.rm); sle2 = wrap_sub(cur, P.e2, P.rm);
+        fo2 = so2 >= 0 ? meta[slo2 * META_INTS] : 0;
+        fe2 = se2 >= 0 ? meta[sle2 * META_INTS] : 0;
+      }
+      const bool n_mx = !(fx & comp_bit(CM)), n_mo1 = !(fo1 & comp_bit(CM));
+      const bool n_i1 = !(fe1 & comp_bit(CI1)), n_d1 = !(fe1 & comp_bit(CD1));
+      const bool n_mo2 = TWO_P ? !(fo2 & comp_bit(CM)) : true;
+      const bool n_i2 = TWO_P ? !(fe2 & comp_bit(CI2)) : true;
+      const bool n_d2 = TWO_P ? !(fe2 & comp_bit(CD2)) : true;
+      if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
+        /* null step: allocate_output_null, compute.c:374-400 */
+        ++num_null;
+        cur_exists = false;
+        for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
+        term_k = KNONE;
+        if (g.rank == 0) meta[cur * META_INTS] = 0;
+        g.sync();
+      } else {
+        num_null = 0;
+        Src sMx, sMo1, sI1, sD1, sMo2, sI2, sD2;
+#define WFA_SRC(S, isnull, slotidx, ring_, ringslot, comp)                              \
+        if (isnull) { S.slot = gm.ring[ring_]; S.clo = 0; S.lo = 1; S.hi = -1; }          \
+        else { S.slot = gm.ring[ring_] + (ringslot) * wcap; S.clo = meta[(slotidx) * META_INTS + 1]; \
+               S.lo = meta[(slotidx) * META_INTS + 2 + 2 * (comp)];                        \
+               S.hi = meta[(slotidx) * META_INTS + 3 + 2 * (comp)]; }
+        WFA_SRC(sMx, n_mx, slx, CM, slx, CM)
+        WFA_SRC(sMo1, n_mo1, slo1, CM, slo1, CM)
+        const int r1src = wrap_sub(c1, P.e1, P.r1);
+        WFA_SRC(sI1, n_i1, sle1, CI1, r1src, CI1)
+        WFA_SRC(sD1, n_d1, sle1, CD1, r1src, CD1)
+        if (TWO_P) {
+          WFA_SRC(sMo2, n_mo2, slo2, CM, slo2, CM)
+          const int r2src = wrap_sub(c2, P.e2, P.r2);
+          WFA_SRC(sI2, n_i2, sle2, CI2, r2src, CI2)
+          WFA_SRC(sD2, n_d2, sle2, CD2, r2src, CD2)
+        }
+#undef WFA_SRC
+        /* wavefront_compute_limits_input, compute.c:40-86 (null inputs carry lo=1, hi=-1) */
+        int lo = sMx.lo, hi = sMx.hi;
+        lo = imin(lo, sMo1.lo - 1); hi = imax(hi, sMo1.hi + 1);
+        lo = imin(lo, sI1.lo + 1); hi = imax(hi, sI1.hi + 1);
+        lo = imin(lo, sD1.lo - 1); hi = imax(hi, sD1.hi - 1);
+        if (TWO_P) {
+          lo = imin(lo, sMo2.lo - 1); hi = imax(hi, sMo2.hi + 1);
+          lo = imin(lo, sI2.lo + 1); hi = imax(hi, sI2.hi + 1);
+          lo = imin(lo, sD2.lo - 1); hi = imax(hi, sD2.hi - 1);
+        }
+        const int width = hi - lo + 1;
+        if (width > wcap) return PAIR_OVERFLOW;
+        if (FULL) { if (s >= P.scap || cell_off + width > P.hcap) return PAIR_OVERFLOW; }
+        /* allocate_output, compute.c:401-486 */
+        const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
+        const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
+        int* const oM = gm.ring[CM] + cur * wcap;
+        int* const oI1 = gm.ring[CI1] + c1 * wcap;
+        int* const oD1 = gm.ring[CD1] + c1 * wcap;
+        int* const oI2 = TWO_P ? gm.ring[CI2] + c2 * wcap : nullptr;
+        int* const oD2 = TWO_P ? gm.ring[CD2] + c2 * wcap : nullptr;
+        /* reductions: [2c] = first in-bounds k, [2c+1] = -(last in-bounds k), [2*NC] = term */
+        int red[2 * 5 + 1];
+        for (int i = 0; i < 2 * 5 + 1; ++i) red[i] = INT_MAX;
+        for (int k = lo + g.rank; k <= hi; k += g.size) {
+          const int i1o = rd(sMo1, k - 1), i1e = rd(sI1, k - 1);
+          const int d1o = rd(sMo1, k + 1), d1e = rd(sD1, k + 1);
+          const int mis = rd(sMx, k) + 1;
+          const int ins1 = imax(i1o, i1e) + 1, del1 = imax(d1o, d1e);
+          int ins = ins1, del = del1;
+          int i2o = OFFNULL, i2e = OFFNULL, d2o = OFFNULL, d2e = OFFNULL, ins2 = OFFNULL, del2 = OFFNULL;
+          if (TWO_P) {
+            i2o = rd(sMo2, k - 1); i2e = rd(sI2, k - 1);
+            d2o = rd(sMo2, k + 1); d2e = rd(sD2, k + 1);
+            ins2 = imax(i2o, i2e) + 1; del2 = imax(d2o, d2e);
+            ins = imax(ins1, ins2); del = imax(del1, del2);
+          }
+          int mx = imax(del, imax(mis, ins));
+          const bool m_in = in_bounds(k, mx, plen, tlen);
+          if (!m_in) mx = OFFNULL;
+          const int i = k - lo;
+          if (has_i1) { oI1[i] = ins1; if (in_bounds(k, ins1, plen, tlen)) { red[2] = imin(red[2], k); red[3] = imin(red[3], -k); } }
+          if (has_d1) { oD1[i] = del1; if (in_bounds(k, del1, plen, tlen)) { red[4] = imin(red[4], k); red[5] = imin(red[5], -k); } }
+          if (TWO_P) {
+            if (has_i2) { oI2[i] = ins2; if (in_bounds(k, ins2, plen, tlen)) { red[6] = imin(red[6], k); red[7] = imin(red[7], -k); } }
+            if (has_d2) { oD2[i] = del2; if (in_bounds(k, del2, plen, tlen)) { red[8] = imin(red[8], k); red[9] = imin(red[9], -k); } }
+          }
+          if (FULL) {
+            /* origin code: winner of max over (offset<<4 | type), backtrace.c:366-389 */
+            const int x1 = (i1e >= i1o) ? 1 : 0, y1 = (d1e >= d1o) ? 1 : 0;
+            int best = (imax(mis, -1) << 4) | BT_M;
+            best = imax(best, (imax(ins1, -1) << 4) | (BT_I1_OPEN + x1));
+            best = imax(best, (imax(del1, -1) << 4) | (BT_D1_OPEN + y1));
+            int code = (x1 << 4) | (y1 << 5);
+            if (TWO_P) {
+              const int x2 = (i2e >= i2o) ? 1 : 0, y2 = (d2e >= d2o) ? 1 : 0;
+              best = imax(best, (imax(ins2, -1) << 4) | (BT_I2_OPEN + x2));
+              best = imax(best, (imax(del2, -1) << 4) | (BT_D2_OPEN + y2));
+              code |= (x2 << 6) | (y2 << 7);
+            }
+            code |= (best >= 0) ? (best & 15) : 0;
+            gm.h_m0[cell_off + i] = mx;
+            gm.h_code[cell_off + i] = (uint8_t)code;
+          }
+          if (m_in) {
+            red[0] = imin(red[0], k); red[1] = imin(red[1], -k);
+            mx = extend_offset(gm.pw, gm.tw, plen, tlen, k, mx);
+            bool term;
+            if (P.endsfree) {
+              const int hh = mx, vv = mx - k;
+              term = (hh >= tlen && plen - vv <= P.pef) || (vv >= plen && tlen - hh <= P.tef);
+            } else term = (k == ak && mx >= tlen);
+            if (term) red[2 * 5] = imin(red[2 * 5], k);
+          }
+          oM[i] = mx;
+        }
+        if (TWO_P) g.template allmin<11>(red);
+        else {
+          int r7[7] = {red[0], red[1], red[2], red[3], red[4], red[5], red[10]};
+          g.template allmin<7>(r7);
+          red[0] = r7[0]; red[1] = r7[1]; red[2] = r7[2]; red[3] = r7[3]; red[4] = r7[4]; red[5] = r7[5];
+          red[10] = r7[6];
+        }
+        term_k = red[10];
+        /* trim_ends, compute.c:571-605: [first in-bounds, last in-bounds], else null */
+        const bool has[5] = {true, has_i1, has_d1, has_i2, has_d2};
+        for (int c = 0; c < 5; ++c) {
+          if (c < NC && has[c] && red[2 * c] != INT_MAX) { clo[c] = red[2 * c]; chi[c] = -red[2 * c + 1]; }
+          else { clo[c] = 1; chi[c] = -1; }
+        }
+        cur_exists = true;
+        if (g.rank == 0) {
+          int fl = FLAG_EXISTS;
+          for (int c = 0; c < NC; ++c) {
+            if (clo[c] <= chi[c]) fl |= comp_bit(c);
+            meta[cur * META_INTS + 2 + 2 * c] = clo[c];
+            meta[cur * META_INTS + 3 + 2 * c] = chi[c];
+          }
+          meta[cur * META_INTS] = fl;
+          meta[cur * META_INTS + 1] = lo;
+          if (FULL) gm.hmeta[s] = make_int2((int)cell_off, lo);
+        }
+        if (FULL) cell_off += width;
+        g.sync();
+      }
+    }
+    if (s >= P.max_steps) {                         /* unialign.c:98-109 */
+      status = 3;
+      cells += imax(0, chi[CM] - clo[CM] + 1);
+      break;
+    }
+  }
+
+  /* ---- wavefront_unialign_terminate, unialign.c:147-237 ---- */
+  res.cells = cells;
+  res.nruns = 0;
+  res.locs[0] = res.locs[1] = res.locs[2] = res.locs[3] = 0;
+  if (status == 3) {
+    res.score = -P.max_steps; res.status = ST_MAX_STEPS;
+  } else if (!FULL) {
+    if (status == 1) { res.score = classic_score(P.match, plen, tlen, s); res.status = ST_COMPLETED; }
+    else {
+      /* end position was never assigned: end_v = NULL - DIAGONAL_NULL with int32 wrap */
+      const int32_t end_v = (int32_t)((uint32_t)OFFNULL - (uint32_t)INT_MAX);
+      res.score = classic_score(P.match, end_v, OFFNULL, s); res.status = ST_PARTIAL;
+    }
+  } else {
+    if (status == 1) {
+      if (g.rank == 0) {
+        RunEmitter em; em.init(gm.runs_stage, P.runcap);
+        backtrace<TWO_P>(P, gm, plen, tlen, s, end_k, end_off, em);
+        res.nruns = em.n;
+        locations_from_stage(gm.runs_stage, imin(em.n, P.runcap), plen, tlen, res.locs);
+      }
+      res.score = classic_score(P.match, end_off - end_k, end_off, s);
+      res.status = ST_COMPLETED;
+    } else {
+      /* dropped: no end position -> empty CIGAR; maxtrim on an empty CIGAR clears the
+       * score (W/alignment/cigar.c:473-528) */
+      res.score = INT32_MIN; res.status = ST_PARTIAL;
+    }
+  }
+  return PAIR_DONE;
+}
+
+}  // namespace wfagpu

@@ -1,0 +1,330 @@
+/*
+ * wfa_kernels.cu -- sm_100a kernels of the batched wavefront aligner.
+ *
+ *   wfa_align_kernel<TWO_P, FULL, MODE>   persistent kernel; every thread group pulls read
+ *       pairs from a device work queue and runs wfagpu::align_pair (wfa_core.cuh) on them.
+ *       MODE 0: warp-per-pair, wavefront ring + packed sequences in shared memory
+ *       MODE 1: block-per-pair, ring in shared memory
+ *       MODE 2: block-per-pair, ring in an L2-resident HBM arena (very wide wavefronts)
+ *   cigar_count_kernel / cigar_scan_kernel / cigar_gather_kernel   order the per-pair CIGAR
+ *       runs into the caller's layout (cig_off[n+1] + contiguous run words).
+ *
+ * Replaces, for the batch, the reference's per-pair loop wavefront_unialign
+ * (W/wavefront/wavefront_unialign.c:241-273) and everything it calls.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <type_traits>
+
+#include "wfa_core.cuh"
+#include "wfa_launch.h"
+
+namespace wfagpu {
+
+constexpr int MAX_RED = 11;
+
+/* ---- thread groups ------------------------------------------------------------------ */
+struct WarpGroup {
+  int rank, size;
+  __device__ __forceinline__ void sync() { __syncwarp(); }
+  template <int N>
+  __device__ __forceinline__ void allmin(int (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = __reduce_min_sync(0xffffffffu, v[i]);
+  }
+  __device__ __forceinline__ int bcast(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+  __device__ __forceinline__ long long bcastll(long long v) { return __shfl_sync(0xffffffffu, v, 0); }
+};
+
+struct BlockGroup {
+  int rank, size;
+  int* red;        /* 2 * MAX_RED * 32 ints of shared memory */
+  int parity;
+  __device__ __forceinline__ void sync() { __syncthreads(); }
+  template <int N>
+  __device__ __forceinline__ void allmin(int (&v)[N]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int* buf = red + parity * (MAX_RED * 32);
+    parity ^= 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int r = __reduce_min_sync(0xffffffffu, v[i]);
+      if (lane == 0) buf[i * 32 + warp] = r;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int t = (lane < nw) ? buf[i * 32 + lane] : INT_MAX;
+      v[i] = __reduce_min_sync(0xffffffffu, t);
+    }
+  }
+  __device__ __forceinline__ int bcast(int v) {
+    int* buf = red + parity * (MAX_RED * 32);
+    parity ^= 1;
+    if (rank == 0) buf[0] = v;
+    __syncthreads();
+    return buf[0];
+  }
+  __device__ __forceinline__ long long bcastll(long long v) {
+    const int lo = bcast((int)(v & 0xffffffffll));
+    const int hi = bcast((int)(v >> 32));
+    return ((long long)hi << 32) | (unsigned int)lo;
+  }
+};
+
+/* ---- the persistent alignment kernel ------------------------------------------------- */
+template <bool TWO_P, bool FULL, int MODE>
+__global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) int smem[];
+  constexpr bool BLOCK = (MODE != 0);
+  using G = typename std::conditional<BLOCK, BlockGroup, WarpGroup>::type;
+
+  const int NS = P.rm + 2 * P.r1 + (TWO_P ? 2 * P.r2 : 0);
+  const int ring_ints = (MODE == 2) ? 0 : NS * P.wcap;
+  const int group_ints = P.seq_words_cap + ring_ints + P.rm * META_INTS;
+
+  G g;
+  int group_id;
+  int* base;
+  if (BLOCK) {
+    g.rank = threadIdx.x; g.size = blockDim.x;
+    group_id = blockIdx.x;
+    base = smem;
+  } else {
+    g.rank = threadIdx.x & 31; g.size = 32;
+    const int wpb = blockDim.x >> 5;
+    group_id = blockIdx.x * wpb + (threadIdx.x >> 5);
+    base = smem + (threadIdx.x >> 5) * group_ints;
+  }
+  if constexpr (BLOCK) { g.red = smem + group_ints; g.parity = 0; }
+
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base);
+  int* ringbase = (MODE == 2) ? (P.gring + (long long)group_id * P.gring_ints) : (base + P.seq_words_cap);
+  GroupMem gm;
+  gm.ring[CM] = ringbase;
+  gm.ring[CI1] = gm.ring[CM] + P.rm * P.wcap;
+  gm.ring[CD1] = gm.ring[CI1] + P.r1 * P.wcap;
+  gm.ring[CI2] = gm.ring[CD1] + P.r1 * P.wcap;
+  gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * P.wcap : 0);
+  gm.meta = base + P.seq_words_cap + ring_ints;
+  if (FULL) {
+    gm.h_m0 = P.hist_m0 + (long long)group_id * P.hcap;
+    gm.h_code = P.hist_code + (long long)group_id * P.hcap;
+    gm.hmeta = P.hmeta + (long long)group_id * P.scap;
+    gm.runs_stage = P.runs_stage + (long long)group_id * P.runcap;
+  } else {
+    gm.h_m0 = nullptr; gm.h_code = nullptr; gm.hmeta = nullptr; gm.runs_stage = nullptr;
+  }
+
+  const int n_work = *P.n_work;
+  long long cells_acc = 0;
+
+  for (;;) {
+    int w = 0;
+    if (g.rank == 0) w = atomicAdd(P.work_counter, 1);
+    w = g.bcast(w);
+    if (w >= n_work) break;
+    const int pid = P.worklist ? P.worklist[w] : w;
+    const PairMeta pm = P.pairs[pid];
+    const int plen = pm.plen, tlen = pm.tlen;
+    const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+    int rc;
+    PairResult res;
+    if (P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) {
+      rc = PAIR_OVERFLOW;
+    } else {
+      const uint32_t* gw = P.words + pm.woff;
+      if (P.seq_words_cap > 0) {
+        /* stage the 2-bit packed pair in shared memory (coalesced word loads) */
+        uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
+        for (int i = g.rank; i < pwn; i += g.size) sp[i] = gw[i];
+        for (int i = g.rank; i < twn; i += g.size) st[i] = gw[pwn + i];
+        if (g.rank == 0) { sp[pwn] = 0; st[twn] = 0; }
+        gm.pw = sp; gm.tw = st;
+      } else {
+        gm.pw = gw; gm.tw = gw + pwn;      /* device buffer carries one pad word */
+      }
+      g.sync();
+      rc = align_pair<G, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+    }
+    if (rc == PAIR_OVERFLOW) {
+      if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
+    } else {
+      cells_acc += res.cells;
+      if (FULL) {
+        int nr = g.bcast(res.nruns);
+        long long rbase = 0;
+        int st = res.status;
+        if (nr > 0) {
+          if (g.rank == 0) rbase = (long long)atomicAdd(P.runs_cursor, (unsigned long long)nr);
+          rbase = g.bcastll(rbase);
+          if (nr > P.runcap || (unsigned long long)(rbase + nr) > P.runs_tmp_cap) { st = ST_OOM; nr = 0; }
+          for (int i = g.rank; i < nr; i += g.size) P.runs_tmp[rbase + i] = gm.runs_stage[nr - 1 - i];
+        }
+        if (g.rank == 0) {
+          P.score[pid] = res.score; P.status[pid] = st;
+          int4 l = make_int4(res.locs[0], res.locs[1], res.locs[2], res.locs[3]);
+          if (nr == 0) l = make_int4(0, 0, 0, 0);
+          reinterpret_cast<int4*>(P.locs)[pid] = l;
+          P.nruns[pid] = nr; P.runs_base[pid] = rbase;
+        }
+      } else if (g.rank == 0) {
+        P.score[pid] = res.score; P.status[pid] = res.status;
+      }
+    }
+    g.sync();
+  }
+  if (g.rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
+}
+
+/* ---- CIGAR ordering ------------------------------------------------------------------ */
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void cigar_count_kernel(const int* __restrict__ nruns, long long n, long long* __restrict__ tile_sums) {
+  __shared__ long long wsum[SCAN_THREADS / 32];
+  const long long t0 = (long long)blockIdx.x * SCAN_TILE;
+  long long acc = 0;
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    const long long i = t0 + j * SCAN_THREADS + threadIdx.x;
+    if (i < n) acc += nruns[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long s = 0;
+    for (int i = 0; i < SCAN_THREADS / 32; ++i) s += wsum[i];
+    tile_sums[blockIdx.x] = s;
+  }
+}
+
+/* single block: exclusive scan of the tile sums in place; total -> tile_sums[ntiles] */
+__global__ void cigar_scan_kernel(long long* tile_sums, int ntiles) {
+  __shared__ long long carry;
+  __shared__ long long wtot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < ntiles; b += blockDim.x) {
+    const int i = b + threadIdx.x;
+    const long long v = (i < ntiles) ? tile_sums[i] : 0;
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
+    const long long excl = carry + woff + inc - v;
+    if (i < ntiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+
+/* per tile: exclusive offsets of every pair, then copy that pair's runs into place */
+__global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long long* __restrict__ runs_base,
+                                    long long n, const long long* __restrict__ tile_sums,
+                                    const uint32_t* __restrict__ runs_tmp,
+                                    long long* __restrict__ cig_off, uint32_t* __restrict__ runs_out) {
+  __shared__ long long wtot[SCAN_THREADS / 32];
+  __shared__ long long carry_s;
+  const long long t0 = (long long)blockIdx.x * SCAN_TILE;
+  if (threadIdx.x == 0) carry_s = tile_sums[blockIdx.x];
+  __syncthreads();
+  for (int j = 0; j < SCAN_ITEMS; ++j) {
+    const long long i = t0 + j * SCAN_THREADS + threadIdx.x;
+    const int v = (i < n) ? nruns[i] : 0;
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
+    const long long excl = carry_s + woff + inc - v;
+    if (i < n) {
+      cig_off[i] = excl;
+      const long long src = runs_base[i];
+      for (int r = 0; r < v; ++r) runs_out[excl + r] = runs_tmp[src + r];
+    }
+    __syncthreads();
+    if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cig_off[n] = tile_sums[gridDim.x];
+}
+
+/* ---- launch wrappers (C++ linkage, used by wfagpu_api.cpp) -------------------------- */
+template <bool TWO_P, bool FULL, int MODE>
+static cudaError_t launch_one(const KParams& P, int grid, int block, size_t smem, cudaStream_t st) {
+  auto kern = wfa_align_kernel<TWO_P, FULL, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, block, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <bool TWO_P, bool FULL, int MODE>
+static int occupancy_one(int block, size_t smem) {
+  auto kern = wfa_align_kernel<TWO_P, FULL, MODE>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem) != cudaSuccess) return 0;
+  return nb;
+}
+
+#define WFA_DISPATCH(FN, ...)                                                   \
+  do {                                                                          \
+    const int key = (two_p ? 1 : 0) | (full ? 2 : 0) | (mode << 2);             \
+    switch (key) {                                                              \
+      case 0: return FN<false, false, 0>(__VA_ARGS__);                          \
+      case 1: return FN<true, false, 0>(__VA_ARGS__);                           \
+      case 2: return FN<false, true, 0>(__VA_ARGS__);                           \
+      case 3: return FN<true, true, 0>(__VA_ARGS__);                            \
+      case 4: return FN<false, false, 1>(__VA_ARGS__);                          \
+      case 5: return FN<true, false, 1>(__VA_ARGS__);                           \
+      case 6: return FN<false, true, 1>(__VA_ARGS__);                           \
+      case 7: return FN<true, true, 1>(__VA_ARGS__);                            \
+      case 8: return FN<false, false, 2>(__VA_ARGS__);                          \
+      case 9: return FN<true, false, 2>(__VA_ARGS__);                           \
+      case 10: return FN<false, true, 2>(__VA_ARGS__);                          \
+      default: return FN<true, true, 2>(__VA_ARGS__);                           \
+    }                                                                           \
+  } while (0)
+
+cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, int grid, int block,
+                         size_t smem, cudaStream_t st) {
+  WFA_DISPATCH(launch_one, P, grid, block, smem, st);
+}
+
+int align_occupancy(bool two_p, bool full, int mode, int block, size_t smem) {
+  WFA_DISPATCH(occupancy_one, block, smem);
+}
+
+size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }
+
+cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,
+                               long long* tile_sums, const uint32_t* runs_tmp, long long* cig_off,
+                               uint32_t* runs_out, cudaStream_t st) {
+  const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  if (runs_out == nullptr) {   /* phase 1: counts + scan (total lands in tile_sums[ntiles]) */
+    cigar_count_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nruns, n, tile_sums);
+    cigar_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
+  } else {
+    cigar_gather_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nruns, runs_base, n, tile_sums, runs_tmp, cig_off, runs_out);
+  }
+  return cudaGetLastError();
+}
+
+int cigar_order_tiles(long long n) { return (int)((n + SCAN_TILE - 1) / SCAN_TILE); }
+
+}  // namespace wfagpu

@@ -1,0 +1,24 @@
+/* wfa_launch.h -- host-callable launch wrappers of wfa_kernels.cu (internal, C++ linkage). */
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace wfagpu {
+
+struct KParams;
+
+/* mode 0: warp-per-pair (smem ring), 1: block-per-pair (smem ring), 2: block-per-pair (HBM ring) */
+cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, int grid, int block,
+                         size_t smem, cudaStream_t st);
+int align_occupancy(bool two_p, bool full, int mode, int block, size_t smem);
+size_t block_reduce_smem_bytes();
+
+/* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
+ * last one); otherwise gather into cig_off[n+1] / runs_out. */
+cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,
+                               long long* tile_sums, const uint32_t* runs_tmp, long long* cig_off,
+                               uint32_t* runs_out, cudaStream_t st);
+int cigar_order_tiles(long long n);
+
+}  // namespace wfagpu

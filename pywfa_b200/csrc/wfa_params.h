@@ -1,0 +1,43 @@
+/* wfa_params.h -- configuration POD -> kernel parameters (internal; shared with tests/emu). */
+#pragma once
+#include <limits.h>
+
+#include <algorithm>
+
+#include "../../include/wfagpu.h"
+#include "wfa_core.cuh"
+
+namespace wfagpu {
+
+/* Normalised penalties (W/wavefront/wavefront_penalties.c:95-173: Eizenga's transform when
+ * match < 0), ring geometry (max_score_scope, W/wavefront/wavefront_components.c:81-124) and
+ * the alignment form / heuristic fields of wavefront_aligner_attr_t. */
+inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
+  const bool two_p = c.distance == WFAGPU_DISTANCE_AFFINE2P;
+  if (c.match < 0) {
+    k.match = c.match;
+    k.x = 2 * c.mismatch - 2 * c.match;
+    k.o1 = 2 * c.gap_opening1; k.e1 = 2 * c.gap_extension1 - c.match;
+    k.o2 = 2 * c.gap_opening2; k.e2 = 2 * c.gap_extension2 - c.match;
+  } else {
+    k.match = 0; k.x = c.mismatch;
+    k.o1 = c.gap_opening1; k.e1 = c.gap_extension1;
+    k.o2 = c.gap_opening2; k.e2 = c.gap_extension2;
+  }
+  int scope_indel = k.o1 + k.e1;
+  if (two_p) scope_indel = std::max(scope_indel, k.o2 + k.e2);
+  k.max_scope = std::max(scope_indel, k.x) + 1;
+  k.rm = k.max_scope;
+  k.r1 = k.e1 + 1;
+  k.r2 = two_p ? k.e2 + 1 : 1;
+  if (!two_p) { k.o2 = 0; k.e2 = 1; }
+  k.endsfree = c.span == WFAGPU_SPAN_ENDSFREE;
+  k.pbf = c.pattern_begin_free; k.pef = c.pattern_end_free;
+  k.tbf = c.text_begin_free; k.tef = c.text_end_free;
+  k.heuristic = c.heuristic;
+  k.min_wf_len = c.min_wavefront_length; k.max_dist_thr = c.max_distance_threshold;
+  k.steps_between = c.steps_between_cutoffs; k.xdrop = c.xdrop;
+  k.max_steps = c.max_steps <= 0 ? INT_MAX : c.max_steps;
+}
+
+}  // namespace wfagpu

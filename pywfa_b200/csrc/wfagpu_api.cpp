@@ -1,0 +1,586 @@
+/*
+ * wfagpu_api.cpp -- the C ABI of include/wfagpu.h: configuration checks, per-device context,
+ * batch packing / upload, the tiered kernel schedule and result download.
+ *
+ * Host-side counterpart of what pywfa/align.pyx does around wavefront_align
+ * (pywfa/align.pyx:309-443) and of WFA2-lib's aligner lifecycle
+ * (W/wavefront/wavefront_aligner.c:387-463), restructured for batches: one configuration POD,
+ * one packed upload, kernels, one download.  There is no CPU alignment path in this library.
+ */
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/wfagpu.h"
+#include "pack.h"
+#include "wfa_core.cuh"
+#include "wfa_launch.h"
+#include "wfa_params.h"
+
+using namespace wfagpu;
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr; size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = std::max<size_t>((bytes * 5 / 4 + 4095) & ~(size_t)4095, 4096);
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DevCounters {       /* one per batch, in HBM */
+  int work[4];
+  int retry[4];
+  int nwork0;
+  int pad;
+  unsigned long long runs_cursor;
+  unsigned long long cells_total;
+};
+
+struct Tier {
+  int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
+  int threads = 128;
+  int groups_per_block = 4;
+  int wcap = 64;
+  int seq_words_cap = 0;
+  size_t smem = 0;
+  int blocks_per_sm = 1;
+  long long hcap = 0;
+  int scap = 0;
+};
+
+}  // namespace
+
+struct wfagpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sms = 0;
+  int smem_optin = 0;
+  std::string err;
+  /* pinned staging (grow-only) */
+  PinBuf pin_words, pin_meta, pin_runs, pin_small;
+  /* per-run scratch shared by all batches of this context (grow-only) */
+  DevBuf hist_m0, hist_code, hmeta, runs_stage, gring;
+};
+
+struct wfagpu_batch {
+  wfagpu_config_t cfg;
+  int64_t n = 0;
+  int32_t maxp = 0, maxt = 0;
+  int64_t total_words = 0;
+  bool two_p = false, full = false;
+  KParams kp;
+  std::vector<Tier> tiers;
+  DevBuf pairs, words, score, status, locs, nruns, runs_base, runs_tmp, retry_a, retry_b, counters,
+      cig_off, tile_sums, runs_out;
+  unsigned long long runs_tmp_cap = 0;
+  long long total_runs = 0;
+  bool ran = false;
+  wfagpu_batch_stats_t stats;
+};
+
+namespace {
+
+int fail(wfagpu_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+void set_err(char* err, size_t errlen, const char* fmt, ...) {
+  if (!err || !errlen) return;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err, errlen, fmt, ap);
+  va_end(ap);
+}
+
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFAGPU_ENOMEM : WFAGPU_ECUDA,      \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+long long score_bound(const KParams& k, long long p, long long t) {
+  /* any alignment bounds the optimum: min(p,t) mismatches plus one gap */
+  const long long d = p > t ? p - t : t - p;
+  long long b = (long long)k.x * std::min(p, t) + (d ? k.o1 + (long long)k.e1 * d : 0);
+  const long long gaps = (p ? k.o1 + (long long)k.e1 * p : 0) + (t ? k.o1 + (long long)k.e1 * t : 0);
+  return std::min(b, gaps);
+}
+
+void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
+  const KParams& k = b->kp;
+  const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+  const int seqw = (b->maxp + 15) / 16 + (b->maxt + 15) / 16 + 2;
+  const long long wmax = (long long)b->maxp + b->maxt + 1;
+  const int wmax32 = (int)std::min<long long>((wmax + 31) & ~31ll, INT_MAX / 2);
+  const int meta = k.rm * META_INTS;
+  const long long sb = std::min<long long>(score_bound(k, b->maxp, b->maxt), k.max_steps);
+  const long long scap_bound = std::min<long long>(sb + k.max_scope + 4, INT_MAX / 4);
+  const long long cells_bound = std::min<long long>(scap_bound * wmax, (long long)4e18 / 8);
+  const int smem_max = ctx->smem_optin;
+  int last_wcap = 0;
+  auto add_warp = [&](int wcap, long long hcap, int scap) {
+    wcap = std::min(wcap, wmax32);
+    if (wcap <= last_wcap) return;
+    const size_t bytes = 4ull * (seqw + (size_t)ns * wcap + meta);
+    if (bytes > 40 * 1024) return;
+    Tier t;
+    t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = wcap; t.seq_words_cap = seqw;
+    t.smem = bytes * 4;
+    t.hcap = std::min(hcap, cells_bound); t.scap = (int)std::min<long long>(scap, scap_bound);
+    b->tiers.push_back(t);
+    last_wcap = wcap;
+  };
+  add_warp(64, 4096, 512);
+  add_warp(256, 65536, 4096);
+  {
+    const long long avail = (long long)smem_max - 1024 - (long long)block_reduce_smem_bytes() - 4ll * (seqw + meta);
+    long long wcap = avail > 0 ? (avail / (4ll * ns)) & ~31ll : 0;
+    wcap = std::min<long long>(wcap, wmax32);
+    if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax32)) {
+      Tier t;
+      t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = (int)wcap;
+      t.seq_words_cap = seqw;
+      t.smem = 4ull * (seqw + (size_t)ns * wcap + meta) + block_reduce_smem_bytes();
+      t.hcap = std::min<long long>(8ll << 20, cells_bound);
+      t.scap = (int)std::min<long long>(1 << 16, scap_bound);
+      b->tiers.push_back(t);
+      last_wcap = (int)wcap;
+    }
+  }
+  {
+    /* widest tier: ring in HBM, history sized at run time from free memory */
+    Tier t;
+    t.mode = 2; t.threads = 512; t.groups_per_block = 1; t.wcap = wmax32;
+    t.seq_words_cap = (4ll * seqw <= 160 * 1024) ? seqw : 0;
+    t.smem = 4ull * (t.seq_words_cap + meta) + block_reduce_smem_bytes();
+    t.hcap = cells_bound;
+    t.scap = (int)std::min<long long>(2 * scap_bound, INT_MAX / 4);
+    b->tiers.push_back(t);
+  }
+  for (auto& t : b->tiers) {
+    int bps = align_occupancy(b->two_p, b->full, t.mode, t.threads, t.smem);
+    t.blocks_per_sm = std::max(1, bps);
+  }
+}
+
+}  // namespace
+
+/* ---- configuration ------------------------------------------------------------------- */
+extern "C" void wfagpu_config_default(wfagpu_config_t* cfg) {
+  /* pywfa/align.pyx:309-334 */
+  memset(cfg, 0, sizeof *cfg);
+  cfg->distance = WFAGPU_DISTANCE_AFFINE;
+  cfg->scope = WFAGPU_SCOPE_FULL;
+  cfg->span = WFAGPU_SPAN_ENDSFREE;
+  cfg->heuristic = WFAGPU_HEURISTIC_NONE;
+  cfg->min_wavefront_length = 10;
+  cfg->max_distance_threshold = 50;
+  cfg->steps_between_cutoffs = 1;
+  cfg->xdrop = 20;
+  cfg->match = 0; cfg->mismatch = 4;
+  cfg->gap_opening1 = 6; cfg->gap_extension1 = 2;
+  cfg->gap_opening2 = 24; cfg->gap_extension2 = 1;
+  cfg->max_steps = 0;
+}
+
+extern "C" int wfagpu_config_check(const wfagpu_config_t* c, int64_t plen, int64_t tlen, char* err, size_t errlen) {
+  if (!c) { set_err(err, errlen, "null configuration"); return WFAGPU_EINVAL; }
+  if (c->distance != WFAGPU_DISTANCE_AFFINE && c->distance != WFAGPU_DISTANCE_AFFINE2P) {
+    set_err(err, errlen, "distance %d is not on the accelerated path (affine, affine2p)", c->distance);
+    return WFAGPU_EUNSUPPORTED;
+  }
+  if (c->scope != WFAGPU_SCOPE_SCORE && c->scope != WFAGPU_SCOPE_FULL) { set_err(err, errlen, "bad scope %d", c->scope); return WFAGPU_EINVAL; }
+  if (c->span != WFAGPU_SPAN_END2END && c->span != WFAGPU_SPAN_ENDSFREE) { set_err(err, errlen, "bad span %d", c->span); return WFAGPU_EINVAL; }
+  if (c->heuristic < WFAGPU_HEURISTIC_NONE || c->heuristic > WFAGPU_HEURISTIC_XDROP) { set_err(err, errlen, "bad heuristic %d", c->heuristic); return WFAGPU_EINVAL; }
+  /* wavefront_penalties_set_affine/_affine2p, W/wavefront/wavefront_penalties.c:95-173 */
+  if (c->match > 0) { set_err(err, errlen, "[WFA::Penalties] Match score must be negative or zero (M=%d)", c->match); return WFAGPU_EINVAL; }
+  if (c->mismatch <= 0 || c->gap_opening1 < 0 || c->gap_extension1 <= 0) {
+    set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O=%d,E=%d) must be (X>0,O>=0,E>0)", c->mismatch, c->gap_opening1, c->gap_extension1);
+    return WFAGPU_EINVAL;
+  }
+  if (c->distance == WFAGPU_DISTANCE_AFFINE2P && (c->gap_opening2 < 0 || c->gap_extension2 <= 0)) {
+    set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O1=%d,E1=%d,O2=%d,E2=%d) must be (X>0,O1>=0,E1>0,O1>=0,E1>0)",
+            c->mismatch, c->gap_opening1, c->gap_extension1, c->gap_opening2, c->gap_extension2);
+    return WFAGPU_EINVAL;
+  }
+  if (c->match < 0 && c->span == WFAGPU_SPAN_ENDSFREE && (c->pattern_begin_free > 0 || c->text_begin_free > 0)) {
+    set_err(err, errlen, "match < 0 with begin-free ends is outside the accelerated path");
+    return WFAGPU_EUNSUPPORTED;
+  }
+  if (c->span == WFAGPU_SPAN_ENDSFREE) {
+    if (c->pattern_begin_free < 0 || c->pattern_end_free < 0 || c->text_begin_free < 0 || c->text_end_free < 0) {
+      set_err(err, errlen, "ends-free parameters must be non-negative"); return WFAGPU_EINVAL;
+    }
+    /* wavefront_align_presets__checks, W/wavefront/wavefront_align.c:89-100 */
+    if (plen >= 0 && tlen >= 0 &&
+        (c->pattern_begin_free > plen || c->pattern_end_free > plen || c->text_begin_free > tlen || c->text_end_free > tlen)) {
+      set_err(err, errlen, "[WFA] Ends-free parameters must be not larger than the sequences (P0=%d,Pf=%d,T0=%d,Tf=%d). "
+              "Must be (P0<=|P|,Pf<=|P|,T0<=|T|,Tf<=|T|) where (|P|,|T|)=(%lld,%lld)",
+              c->pattern_begin_free, c->pattern_end_free, c->text_begin_free, c->text_end_free, (long long)plen, (long long)tlen);
+      return WFAGPU_EINVAL;
+    }
+  }
+  /* bounded so that penalties * ring slots stay in int range */
+  if (c->mismatch > (1 << 20) || c->gap_opening1 > (1 << 20) || c->gap_extension1 > (1 << 20) ||
+      c->gap_opening2 > (1 << 20) || c->gap_extension2 > (1 << 20) || c->match < -(1 << 20)) {
+    set_err(err, errlen, "penalties above 2^20 are not supported"); return WFAGPU_EUNSUPPORTED;
+  }
+  return WFAGPU_OK;
+}
+
+extern "C" const char* wfagpu_strerror(int code) {
+  switch (code) {
+    case WFAGPU_OK: return "ok";
+    case WFAGPU_EINVAL: return "invalid argument or configuration";
+    case WFAGPU_ECUDA: return "CUDA runtime error";
+    case WFAGPU_ENOMEM: return "out of memory";
+    case WFAGPU_ENODEVICE: return "no CUDA device (this library has no CPU fallback)";
+    case WFAGPU_EUNSUPPORTED: return "input outside the accelerated path";
+    default: return "unknown error";
+  }
+}
+
+/* ---- context ------------------------------------------------------------------------- */
+extern "C" int wfagpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t errlen) {
+  if (!out) return WFAGPU_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    set_err(err, errlen, "no CUDA device visible (%s); wfagpu has no CPU fallback",
+            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return WFAGPU_ENODEVICE;
+  }
+  if (device < 0 || device >= n) { set_err(err, errlen, "device %d out of range (0..%d)", device, n - 1); return WFAGPU_EINVAL; }
+  wfagpu_ctx* ctx = new wfagpu_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
+    delete ctx;
+    return WFAGPU_ECUDA;
+  }
+  if (prop.major < 10) {
+    set_err(err, errlen, "device %d is sm_%d%d; this library ships sm_100a code only", device, prop.major, prop.minor);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return WFAGPU_ENODEVICE;
+  }
+  ctx->sms = prop.multiProcessorCount;
+  ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  *out = ctx;
+  return WFAGPU_OK;
+}
+
+extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ctx->pin_words.release(); ctx->pin_meta.release(); ctx->pin_runs.release(); ctx->pin_small.release();
+  ctx->hist_m0.release(); ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* wfagpu_last_error(const wfagpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+/* ---- batches ------------------------------------------------------------------------- */
+extern "C" void wfagpu_batch_free(wfagpu_ctx* ctx, wfagpu_batch* b) {
+  if (!b) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  for (DevBuf* d : {&b->pairs, &b->words, &b->score, &b->status, &b->locs, &b->nruns, &b->runs_base, &b->runs_tmp,
+                    &b->retry_a, &b->retry_b, &b->counters, &b->cig_off, &b->tile_sums, &b->runs_out})
+    d->release();
+  delete b;
+}
+
+extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq,
+                                    const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
+                                    const int32_t* t_len, int64_t n, wfagpu_batch** out) {
+  if (!ctx || !cfg || !out || n < 0 || (n > 0 && (!seq || !p_off || !p_len || !t_off || !t_len)))
+    return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_prepare");
+  *out = nullptr;
+  if (n > INT_MAX / 2) return fail(ctx, WFAGPU_EINVAL, "at most %d pairs per batch", INT_MAX / 2);
+  char msg[400];
+  int rc = wfagpu_config_check(cfg, -1, -1, msg, sizeof msg);
+  if (rc != WFAGPU_OK) return fail(ctx, rc, "%s", msg);
+  CK(cudaSetDevice(ctx->device));
+  wfagpu_batch* b = new wfagpu_batch();
+  b->cfg = *cfg; b->n = n;
+  b->two_p = cfg->distance == WFAGPU_DISTANCE_AFFINE2P;
+  b->full = cfg->scope == WFAGPU_SCOPE_FULL;
+  memset(&b->stats, 0, sizeof b->stats);
+  memset(&b->kp, 0, sizeof b->kp);
+  b->stats.n_pairs = n;
+#define CKB(call)                                                                           \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      wfagpu_batch_free(ctx, b);                                                            \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFAGPU_ENOMEM : WFAGPU_ECUDA,      \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                       \
+  } while (0)
+  /* layout + per-pair checks */
+  CKB(ctx->pin_meta.ensure(sizeof(PairMetaHost) * (size_t)std::max<int64_t>(n, 1)));
+  PairMetaHost* meta = ctx->pin_meta.as<PairMetaHost>();
+  int64_t seq_bytes = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    if (p_len[i] < 0 || t_len[i] < 0) { wfagpu_batch_free(ctx, b); return fail(ctx, WFAGPU_EINVAL, "negative length at pair %lld", (long long)i); }
+    seq_bytes += (int64_t)p_len[i] + t_len[i];
+  }
+  if (cfg->span == WFAGPU_SPAN_ENDSFREE &&
+      (cfg->pattern_begin_free | cfg->pattern_end_free | cfg->text_begin_free | cfg->text_end_free)) {
+    for (int64_t i = 0; i < n; ++i) {
+      rc = wfagpu_config_check(cfg, p_len[i], t_len[i], msg, sizeof msg);
+      if (rc != WFAGPU_OK) { wfagpu_batch_free(ctx, b); return fail(ctx, rc, "pair %lld: %s", (long long)i, msg); }
+    }
+  }
+  b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt);
+  if ((long long)b->maxp + b->maxt > (1ll << 27)) { wfagpu_batch_free(ctx, b); return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases"); }
+  CKB(ctx->pin_words.ensure(4 * (size_t)(b->total_words + 1)));
+  uint32_t* words = ctx->pin_words.as<uint32_t>();
+  const int64_t bad = pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes);
+  if (bad >= 0) {
+    wfagpu_batch_free(ctx, b);
+    return fail(ctx, WFAGPU_EUNSUPPORTED, "pair %lld holds a base other than A/C/G/T: the 2-bit accelerated path cannot represent it", (long long)bad);
+  }
+  words[b->total_words] = 0;
+  /* upload */
+  CKB(b->pairs.ensure(sizeof(PairMetaHost) * (size_t)std::max<int64_t>(n, 1)));
+  CKB(b->words.ensure(4 * (size_t)(b->total_words + 1)));
+  CKB(cudaMemcpyAsync(b->pairs.p, meta, sizeof(PairMetaHost) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  CKB(cudaMemcpyAsync(b->words.p, words, 4 * (size_t)(b->total_words + 1), cudaMemcpyHostToDevice, ctx->stream));
+  b->stats.packed_bytes = 4 * b->total_words;
+  b->stats.h2d_bytes = (int64_t)(sizeof(PairMetaHost) * (size_t)n + 4 * (size_t)(b->total_words + 1));
+  /* results */
+  const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+  CKB(b->score.ensure(4 * n1));
+  CKB(b->status.ensure(4 * n1));
+  CKB(b->retry_a.ensure(4 * n1));
+  CKB(b->retry_b.ensure(4 * n1));
+  CKB(b->counters.ensure(sizeof(DevCounters)));
+  if (b->full) {
+    CKB(b->locs.ensure(16 * n1));
+    CKB(b->nruns.ensure(4 * n1));
+    CKB(b->runs_base.ensure(8 * n1));
+    CKB(b->cig_off.ensure(8 * (n1 + 1)));
+    CKB(b->tile_sums.ensure(8 * (size_t)(cigar_order_tiles(n) + 2)));
+    unsigned long long cap = (unsigned long long)seq_bytes + 2ull * (unsigned long long)n;
+    cap = std::min<unsigned long long>(cap, 4ull << 30);      /* 16 GiB of run words at most */
+    CKB(b->runs_tmp.ensure(4 * (size_t)std::max<unsigned long long>(cap, 1)));
+    b->runs_tmp_cap = cap;
+  }
+  /* kernel parameters */
+  KParams& k = b->kp;
+  fill_kparams(*cfg, k);
+  k.pairs = b->pairs.as<PairMeta>();
+  k.words = b->words.as<uint32_t>();
+  k.score = b->score.as<int>(); k.status = b->status.as<int>();
+  k.locs = b->locs.as<int>(); k.nruns = b->nruns.as<int>(); k.runs_base = b->runs_base.as<long long>();
+  k.runs_tmp = b->runs_tmp.as<uint32_t>(); k.runs_tmp_cap = b->runs_tmp_cap;
+  k.runcap = (int)std::min<long long>((long long)b->maxp + b->maxt + 2, INT_MAX / 2);
+  DevCounters* dc = b->counters.as<DevCounters>();
+  k.runs_cursor = &dc->runs_cursor;
+  k.cells_total = &dc->cells_total;
+  plan_tiers(ctx, b);
+  CKB(cudaStreamSynchronize(ctx->stream));   /* pinned staging is reusable after this */
+#undef CKB
+  *out = b;
+  return WFAGPU_OK;
+}
+
+extern "C" int wfagpu_batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, void* stream) {
+  if (!ctx || !b) return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_run");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  DevCounters* dc = b->counters.as<DevCounters>();
+  b->stats.kernel_launches = 0;
+  b->stats.retried_pairs = 0;
+  b->stats.history_bytes = 0;
+  b->total_runs = 0;
+  if (b->n == 0) { b->ran = true; return WFAGPU_OK; }
+  CK(ctx->pin_small.ensure(256));
+  DevCounters* hc = ctx->pin_small.as<DevCounters>();
+  memset(hc, 0, sizeof *hc);
+  hc->nwork0 = (int)b->n;
+  CK(cudaMemcpyAsync(dc, hc, sizeof *hc, cudaMemcpyHostToDevice, st));
+  long long nwork = b->n;
+  int* lists[2] = {b->retry_a.as<int>(), b->retry_b.as<int>()};
+  const int* cur_list = nullptr;
+  int last_tier = -1;
+  for (size_t ti = 0; ti < b->tiers.size() && nwork > 0; ++ti) {
+    Tier t = b->tiers[ti];
+    KParams k = b->kp;
+    long long groups;
+    int blocks;
+    if (t.mode == 0) {
+      blocks = (int)std::min<long long>((nwork + t.groups_per_block - 1) / t.groups_per_block, (long long)ctx->sms * t.blocks_per_sm);
+      groups = (long long)blocks * t.groups_per_block;
+    } else {
+      blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
+      groups = blocks;
+    }
+    k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap;
+    k.hcap = t.hcap; k.scap = t.scap;
+    if (t.mode == 2) {
+      const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+      k.gring_ints = (long long)ns * t.wcap;
+      CK(ctx->gring.ensure(4ull * (size_t)k.gring_ints * (size_t)groups));
+      k.gring = ctx->gring.as<int>();
+    }
+    if (b->full) {
+      if (t.mode == 2) {
+        /* history arena of the widest tier: what is free now, split over the groups */
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        free_b += ctx->hist_m0.cap + ctx->hist_code.cap;
+        const long long per_group = (long long)((double)free_b * 0.8 / 5.0 / (double)groups);
+        k.hcap = std::max<long long>(1024, std::min<long long>(t.hcap, per_group));
+      }
+      CK(ctx->hist_m0.ensure(4ull * (size_t)k.hcap * (size_t)groups));
+      CK(ctx->hist_code.ensure((size_t)k.hcap * (size_t)groups));
+      CK(ctx->hmeta.ensure(8ull * (size_t)k.scap * (size_t)groups));
+      CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
+      k.hist_m0 = ctx->hist_m0.as<int>(); k.hist_code = ctx->hist_code.as<uint8_t>();
+      k.hmeta = ctx->hmeta.as<int2>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
+    }
+    k.worklist = cur_list;
+    k.n_work = (ti == 0 || last_tier < 0) ? &dc->nwork0 : &dc->retry[last_tier];
+    k.work_counter = &dc->work[ti];
+    k.retry_list = lists[ti & 1];
+    k.retry_count = &dc->retry[ti];
+    CK(launch_align(k, b->two_p, b->full, t.mode, blocks, t.threads, t.smem, st));
+    b->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    nwork = hc->retry[ti];
+    if (ti == 0) b->stats.retried_pairs = nwork;
+    cur_list = lists[ti & 1];
+    last_tier = (int)ti;
+  }
+  b->stats.cells = (int64_t)hc->cells_total;
+  if (nwork > 0) {
+    /* capacity exhausted even on the widest tier: WF_STATUS_OOM (W/wavefront/wfa.h:50) */
+    std::vector<int> ids((size_t)nwork);
+    CK(cudaMemcpyAsync(ids.data(), cur_list, 4 * (size_t)nwork, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const int oom = WFAGPU_STATUS_OOM, sc = INT_MIN, zero = 0;
+    for (int id : ids) {
+      CK(cudaMemcpyAsync(b->score.as<int>() + id, &sc, 4, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(b->status.as<int>() + id, &oom, 4, cudaMemcpyHostToDevice, st));
+      if (b->full) {
+        CK(cudaMemcpyAsync(b->nruns.as<int>() + id, &zero, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(b->locs.as<int>() + 4 * (size_t)id, 0, 16, st));
+      }
+    }
+    CK(cudaStreamSynchronize(st));
+  }
+  if (b->full) {
+    b->total_runs = (long long)std::min<unsigned long long>(hc->runs_cursor, b->runs_tmp_cap);
+    CK(b->runs_out.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
+    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
+                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), nullptr, st));
+    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
+                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), b->runs_out.as<uint32_t>(), st));
+    b->stats.kernel_launches += 3;
+  }
+  b->ran = true;
+  return WFAGPU_OK;
+}
+
+extern "C" int wfagpu_batch_fetch(wfagpu_ctx* ctx, wfagpu_batch* b, int32_t* score, int32_t* status, int32_t* locs,
+                                  int64_t* cig_off, const uint32_t** cig_runs) {
+  if (!ctx || !b) return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_fetch");
+  if (!b->ran) return fail(ctx, WFAGPU_EINVAL, "wfagpu_batch_fetch before wfagpu_batch_run");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CK(cudaDeviceSynchronize());
+  const size_t n = (size_t)b->n;
+  int64_t d2h = 0;
+  if (cig_runs) *cig_runs = nullptr;
+  if (n) {
+    if (score) { CK(cudaMemcpyAsync(score, b->score.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
+    if (status) { CK(cudaMemcpyAsync(status, b->status.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
+  }
+  if (b->full && n) {
+    if (locs) { CK(cudaMemcpyAsync(locs, b->locs.p, 16 * n, cudaMemcpyDeviceToHost, st)); d2h += 16 * n; }
+    if (cig_off) { CK(cudaMemcpyAsync(cig_off, b->cig_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, st)); d2h += 8 * (n + 1); }
+    if (cig_runs) {
+      CK(ctx->pin_runs.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
+      if (b->total_runs) CK(cudaMemcpyAsync(ctx->pin_runs.p, b->runs_out.p, 4 * (size_t)b->total_runs, cudaMemcpyDeviceToHost, st));
+      d2h += 4 * b->total_runs;
+      *cig_runs = ctx->pin_runs.as<uint32_t>();
+    }
+  } else {
+    if (locs && n) memset(locs, 0, 16 * n);
+    if (cig_off) memset(cig_off, 0, 8 * (n + 1));
+    if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->pin_runs.as<uint32_t>(); }
+  }
+  CK(cudaStreamSynchronize(st));
+  b->stats.d2h_bytes = d2h;
+  return WFAGPU_OK;
+}
+
+extern "C" int wfagpu_batch_get_stats(const wfagpu_batch* b, wfagpu_batch_stats_t* out) {
+  if (!b || !out) return WFAGPU_EINVAL;
+  *out = b->stats;
+  return WFAGPU_OK;
+}
+
+extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq,
+                                  const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
+                                  const int32_t* t_len, int64_t n, int32_t* score, int32_t* status,
+                                  int32_t* locs, int64_t* cig_off, const uint32_t** cig_runs) {
+  wfagpu_batch* b = nullptr;
+  int rc = wfagpu_batch_prepare(ctx, cfg, seq, p_off, p_len, t_off, t_len, n, &b);
+  if (rc != WFAGPU_OK) return rc;
+  rc = wfagpu_batch_run(ctx, b, nullptr);
+  if (rc == WFAGPU_OK) rc = wfagpu_batch_fetch(ctx, b, score, status, locs, cig_off, cig_runs);
+  wfagpu_batch_free(ctx, b);
+  return rc;
+}

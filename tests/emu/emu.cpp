@@ -1,0 +1,85 @@
+/*
+ * emu.cpp -- TEST INFRASTRUCTURE ONLY (tests/).  Compiles the device source
+ * pywfa_b200/csrc/wfa_core.cuh as plain host C++ with a one-thread "group", so that the
+ * CPU-only CI (`pytest -m "not gpu"`) can check the kernel's wavefront logic, capacity
+ * handling and the host packer against the oracle without a GPU.  It is never linked into,
+ * loaded by or reachable from the product package: libwfagpu.so has no CPU alignment path.
+ */
+#include <cuda_runtime.h>   /* int2 / make_int2 only; nothing is linked */
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/wfagpu.h"
+#include "../../pywfa_b200/csrc/pack.h"
+#include "../../pywfa_b200/csrc/wfa_core.cuh"
+#include "../../pywfa_b200/csrc/wfa_params.h"
+
+using namespace wfagpu;
+
+struct EmuGroup {
+  int rank = 0, size = 1;
+  void sync() {}
+  template <int N> void allmin(int (&)[N]) {}
+};
+
+template <bool TWO_P, bool FULL>
+static int run_one(const KParams& P, const GroupMem& gm, int plen, int tlen, PairResult& res) {
+  EmuGroup g;
+  return align_pair<EmuGroup, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+}
+
+extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
+                               const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
+                               int wcap, long long hcap, int scap, int32_t* score, int32_t* status,
+                               int32_t* locs, int64_t* cig_off, uint32_t* runs, int64_t runs_cap,
+                               int32_t* overflow, int64_t* cells) {
+  KParams P;
+  memset(&P, 0, sizeof P);
+  fill_kparams(*cfg, P);
+  const bool two_p = cfg->distance == WFAGPU_DISTANCE_AFFINE2P;
+  const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
+  P.wcap = wcap; P.hcap = hcap; P.scap = scap;
+  const int ns = P.rm + 2 * P.r1 + (two_p ? 2 * P.r2 : 0);
+  std::vector<int> ring((size_t)ns * wcap), meta((size_t)P.rm * META_INTS);
+  std::vector<int> h_m0(full ? (size_t)hcap : 1);
+  std::vector<uint8_t> h_code(full ? (size_t)hcap : 1);
+  std::vector<int2> hmeta(full ? (size_t)scap : 1);
+  int64_t used = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int plen = p_len[i], tlen = t_len[i];
+    std::vector<uint32_t> pw((plen + 15) / 16 + 1, 0), tw((tlen + 15) / 16 + 1, 0);
+    if (!pack_sequence(seq + p_off[i], plen, pw.data())) return -2;
+    if (!pack_sequence(seq + t_off[i], tlen, tw.data())) return -2;
+    std::vector<uint32_t> stage((size_t)plen + tlen + 2);
+    P.runcap = (int)stage.size();
+    GroupMem gm;
+    gm.pw = pw.data(); gm.tw = tw.data();
+    gm.ring[CM] = ring.data();
+    gm.ring[CI1] = gm.ring[CM] + P.rm * wcap;
+    gm.ring[CD1] = gm.ring[CI1] + P.r1 * wcap;
+    gm.ring[CI2] = gm.ring[CD1] + P.r1 * wcap;
+    gm.ring[CD2] = gm.ring[CI2] + (two_p ? P.r2 * wcap : 0);
+    gm.meta = meta.data();
+    gm.h_m0 = h_m0.data(); gm.h_code = h_code.data(); gm.hmeta = hmeta.data(); gm.runs_stage = stage.data();
+    PairResult res;
+    memset(&res, 0, sizeof res);
+    int rc;
+    if (two_p) rc = full ? run_one<true, true>(P, gm, plen, tlen, res) : run_one<true, false>(P, gm, plen, tlen, res);
+    else rc = full ? run_one<false, true>(P, gm, plen, tlen, res) : run_one<false, false>(P, gm, plen, tlen, res);
+    cig_off[i] = used;
+    overflow[i] = (rc == PAIR_OVERFLOW);
+    if (rc == PAIR_OVERFLOW) { score[i] = 0; status[i] = 0; cells[i] = 0; memset(locs + 4 * i, 0, 16); continue; }
+    score[i] = res.score; status[i] = res.status; cells[i] = res.cells;
+    memcpy(locs + 4 * i, res.locs, 16);
+    if (used + res.nruns > runs_cap) return -1;
+    for (int r = 0; r < res.nruns; ++r) runs[used + r] = stage[res.nruns - 1 - r];
+    used += res.nruns;
+  }
+  cig_off[n] = used;
+  return 0;
+}
+
+/* expose the host packer for tests */
+extern "C" int emu_pack(const uint8_t* s, int len, uint32_t* out) { return pack_sequence(s, len, out) ? 1 : 0; }

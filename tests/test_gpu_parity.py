@@ -1,0 +1,86 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU checker on the same
+seeded inputs (bit-exact score, status, CIGAR incl. tie-breaks, start/end coordinates)."""
+import numpy as np
+import pytest
+
+from conftest import assert_same
+from pywfa_b200.synth import generate_pairs, pairs_from_strings
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, config kwargs, n, length, divergence, text_flank
+    ("cfg1-150bp-affine-e2e-full", dict(span="end-to-end"), 20000, 150, 0.05, 0),
+    ("cfg1-endsfree-default", dict(), 5000, 150, 0.05, 0),
+    ("cfg2-250bp-affine-score", dict(span="end-to-end", scope="score"), 10000, 250, 0.10, 0),
+    ("cfg2-250bp-affine-full", dict(span="end-to-end"), 5000, 250, 0.10, 0),
+    ("cfg3a-1kbp-2p-endsfree0", dict(distance="affine2p"), 300, 1000, 0.10, 0),
+    ("cfg3b-1kbp-2p-flanks", dict(distance="affine2p", text_begin_free=50, text_end_free=50), 300, 1000, 0.10, 50),
+    ("cfg3-1kbp-2p-score", dict(distance="affine2p", scope="score", span="end-to-end"), 300, 1000, 0.10, 0),
+    ("cfg4-10kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 48, 10000, 0.15, 0),
+    ("cfg4-10kbp-adaptive-score", dict(span="end-to-end", heuristic="adaptive", scope="score"), 48, 10000, 0.15, 0),
+    ("cfg4-10kbp-xdrop", dict(span="end-to-end", heuristic="X-drop", xdrop=20), 64, 10000, 0.15, 0),
+    ("cfg4-10kbp-xdrop-score", dict(span="end-to-end", heuristic="X-drop", xdrop=20, scope="score"), 64, 10000, 0.15, 0),
+    ("cfg4-3kbp-none", dict(span="end-to-end"), 24, 3000, 0.15, 0),
+    ("2p-300bp-e2e", dict(distance="affine2p", span="end-to-end"), 3000, 300, 0.10, 0),
+    ("endsfree-all-four", dict(pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7), 3000, 150, 0.10, 4),
+    ("adaptive-short", dict(heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=10, steps_between_cutoffs=2), 3000, 200, 0.2, 0),
+    ("xdrop-short", dict(heuristic="X-drop", xdrop=100, steps_between_cutoffs=3), 3000, 200, 0.1, 0),
+    ("xdrop-2p", dict(heuristic="X-drop", xdrop=200, distance="affine2p"), 1000, 300, 0.1, 0),
+    ("max-steps", dict(span="end-to-end", max_steps=10), 2000, 150, 0.1, 0),
+    ("match-1", dict(span="end-to-end", match=-1), 2000, 150, 0.1, 0),
+    ("match-2-2p", dict(span="end-to-end", match=-2, distance="affine2p"), 1000, 150, 0.1, 0),
+    ("penalties-odd", dict(span="end-to-end", mismatch=3, gap_opening=1, gap_extension=1), 3000, 120, 0.15, 0),
+    ("penalties-2p-odd", dict(distance="affine2p", mismatch=7, gap_opening=2, gap_extension=3, gap_opening2=11, gap_extension2=2), 1500, 200, 0.15, 0),
+    ("high-divergence", dict(span="end-to-end"), 2000, 100, 0.5, 0),
+]
+
+
+@pytest.mark.parametrize("name,kw,n,length,div,flank", CASES, ids=[c[0] for c in CASES])
+def test_parity_synthetic(gpu_ctx, oracle, name, kw, n, length, div, flank):
+    batch = generate_pairs(n, length, div, seed=hash(name) % 10007, text_flank=flank)
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = gpu_ctx.align_batch(cfg, *batch)
+    assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=name)
+
+
+def test_parity_ragged_and_empty(gpu_ctx, oracle):
+    rng = np.random.default_rng(5)
+    acgt = "ACGT"
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C"), ("ACGT" * 40, "ACGT" * 40)]
+    for _ in range(400):
+        lp, lt = int(rng.integers(0, 400)), int(rng.integers(0, 400))
+        p = "".join(acgt[i] for i in rng.integers(0, 4, lp))
+        if rng.random() < 0.5 and lp:
+            cut = int(rng.integers(0, lp))
+            t = p[:cut] + "".join(acgt[i] for i in rng.integers(0, 4, int(rng.integers(0, 9)))) + p[cut + int(rng.integers(0, 5)):]
+        else:
+            t = "".join(acgt[i] for i in rng.integers(0, 4, lt))
+        pairs.append((p, t))
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(span="end-to-end"), dict(), dict(distance="affine2p", span="end-to-end"),
+               dict(scope="score", span="end-to-end")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = gpu_ctx.align_batch(cfg, *batch)
+        assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"ragged {kw}")
+
+
+def test_empty_batch(gpu_ctx, oracle):
+    cfg = oracle.make_config()
+    z64, z32 = np.zeros(0, np.int64), np.zeros(0, np.int32)
+    got = gpu_ctx.align_batch(cfg, np.zeros(1, np.uint8), z64, z32, z64, z32)
+    assert len(got["score"]) == 0 and got["cig_off"].tolist() == [0]
+
+
+def test_reference_agrees_when_present(gpu_ctx, oracle):
+    """oracle/_ref (the unmodified reference compiled in the build container) travels with the
+    snapshot; when present the GPU is also checked against it directly."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    batch = generate_pairs(4000, 150, 0.05, seed=99)
+    cfg = oracle.make_config(span="end-to-end")
+    want = oracle.align_batch(cfg, *batch, kind="reference")
+    got = gpu_ctx.align_batch(cfg, *batch)
+    assert_same(got, want, what="reference cfg1")
