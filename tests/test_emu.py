@@ -1,0 +1,112 @@
+"""CPU check of the DEVICE source: pywfa_b200/csrc/wfa_core.cuh compiled for the host with a
+one-thread group (tests/emu/, test infrastructure) must reproduce the oracle bit-exactly,
+report capacity overflows instead of wrong answers, and share the host packer with the library."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pywfa_b200.synth import generate_pairs, pairs_from_strings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SYN = json.load(open(os.path.join(HERE, "golden", "synthetic.json")))
+
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(HERE, "emu", "libwfaemu.so"))
+    lib.emu_align_batch.argtypes = [C.c_void_p, _u8p, _i64p, _i32p, _i64p, _i32p, C.c_int64, C.c_int,
+                                    C.c_longlong, C.c_int, _i32p, _i32p, _i32p, _i64p, _u32p, C.c_int64,
+                                    _i32p, _i64p]
+    lib.emu_align_batch.restype = C.c_int
+    lib.emu_pack.argtypes = [_u8p, C.c_int, _u32p]
+    lib.emu_pack.restype = C.c_int
+
+    def run(cfg, batch, wcap=1 << 15, hcap=1 << 25, scap=1 << 18):
+        seq, po, pl, to, tl = batch
+        n = len(pl)
+        out = dict(score=np.zeros(n, np.int32), status=np.zeros(n, np.int32), locs=np.zeros((n, 4), np.int32),
+                   cig_off=np.zeros(n + 1, np.int64), ovf=np.zeros(n, np.int32), cells=np.zeros(n, np.int64))
+        cap = int(pl.sum() + tl.sum()) + 16
+        runs = np.zeros(cap, np.uint32)
+        rc = lib.emu_align_batch(C.addressof(cfg), np.ascontiguousarray(seq), po, pl, to, tl, n, wcap, hcap, scap,
+                                 out["score"], out["status"], out["locs"], out["cig_off"], runs, cap,
+                                 out["ovf"], out["cells"])
+        assert rc == 0, rc
+        out["runs"] = runs[:out["cig_off"][-1]]
+        return out
+    run.lib = lib
+    return run
+
+
+@pytest.mark.parametrize("case", SYN, ids=[c["name"] for c in SYN])
+def test_device_source_matches_golden(emu, oracle, case):
+    batch = generate_pairs(case["n"], case["length"], case["div"], case["seed"], text_flank=case["flank"])
+    cfg = oracle.make_config(**case["config"])
+    r = emu(cfg, batch)
+    assert not r["ovf"].any()
+    assert r["score"].tolist() == case["score"]
+    assert r["status"].tolist() == case["status"]
+    cig = [oracle.runs_to_cigarstring(r["runs"][r["cig_off"][j]:r["cig_off"][j + 1]]) for j in range(case["n"])]
+    assert cig == case["cigars"]
+    assert r["locs"].tolist() == case["locations"]
+    if case["config"].get("scope", "full") == "full":
+        assert r["cells"].tolist() == case["cells"]
+
+
+def test_device_source_matches_oracle_ragged(emu, oracle):
+    rng = np.random.default_rng(17)
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C")]
+    for _ in range(300):
+        lp, lt = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        pairs.append(("".join("ACGT"[i] for i in rng.integers(0, 4, lp)),
+                      "".join("ACGT"[i] for i in rng.integers(0, 4, lt))))
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(span="end-to-end"), dict(), dict(distance="affine2p"),
+               dict(heuristic="adaptive", min_wavefront_length=3, max_distance_threshold=5),
+               dict(heuristic="X-drop", xdrop=30), dict(span="end-to-end", scope="score", max_steps=50)):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = emu(cfg, batch)
+        for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
+            assert np.array_equal(got[k], want[k]), (kw, k)
+
+
+def test_capacity_overflow_is_reported_not_wrong(emu, oracle):
+    batch = generate_pairs(200, 250, 0.10, seed=2)
+    cfg = oracle.make_config(span="end-to-end")
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    small = emu(cfg, batch, wcap=64)
+    assert small["ovf"].any(), "250 bp / 10 % pairs need wavefronts wider than 64"
+    ok = small["ovf"] == 0
+    assert np.array_equal(small["score"][ok], want["score"][ok])
+    tiny_hist = emu(cfg, batch, hcap=2000)
+    ok = tiny_hist["ovf"] == 0
+    assert (~ok).any() and np.array_equal(tiny_hist["score"][ok], want["score"][ok])
+    few_scores = emu(cfg, batch, scap=64)
+    ok = few_scores["ovf"] == 0
+    assert (~ok).any() and np.array_equal(few_scores["score"][ok], want["score"][ok])
+
+
+def test_host_packer(emu):
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 15, 16, 17, 31, 32, 33, 64, 150, 1000):
+        codes = rng.integers(0, 4, n)
+        s = np.frombuffer("".join("ACTG"[c] for c in codes).encode(), np.uint8).copy()   # A=0 C=1 T=2 G=3
+        if n % 2:
+            s[::3] |= 0x20                                   # lower case packs alike
+        out = np.zeros(n // 16 + 2, np.uint32)
+        assert emu.lib.emu_pack(np.ascontiguousarray(s), n, out) == 1
+        got = [(int(out[i // 16]) >> (2 * (i % 16))) & 3 for i in range(n)]
+        assert got == codes.tolist()
+    bad = np.frombuffer(b"ACGTNACGT" * 8, np.uint8).copy()
+    assert emu.lib.emu_pack(bad, len(bad), np.zeros(8, np.uint32)) == 0

@@ -1,0 +1,172 @@
+"""Host logic without a GPU: the C-ABI library loads and exports every symbol of
+include/wfagpu.h, configuration checks mirror the reference's exit(1) conditions, the Python
+mirror of pywfa's interface behaves like the reference (golden vectors), and the product path
+fails loudly -- never silently on a CPU -- when no device is present."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pywfa_b200
+from pywfa_b200 import _ffi
+from pywfa_b200.align import AlignmentResult
+from pywfa_b200.build import build_library
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+POST = json.load(open(os.path.join(HERE, "golden", "postprocess.json")))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_library()
+    return _ffi.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "wfagpu.h")).read()
+    names = set(re.findall(r"\b(wfagpu_[a-z_]+)\s*\(", header))
+    assert len(names) >= 13
+    for name in sorted(names):
+        assert hasattr(lib, name), f"{name} declared in include/wfagpu.h but not exported"
+
+
+def test_config_default_and_layout(lib):
+    cfg = _ffi.Config()
+    lib.wfagpu_config_default(C.addressof(cfg))
+    assert C.sizeof(cfg) == 80
+    assert (cfg.distance, cfg.scope, cfg.span, cfg.heuristic) == (0, 1, 1, 0)
+    assert (cfg.match, cfg.mismatch, cfg.gap_opening1, cfg.gap_extension1, cfg.gap_opening2, cfg.gap_extension2) == (0, 4, 6, 2, 24, 1)
+
+
+@pytest.mark.parametrize("field,value,code", [
+    ("match", 1, _ffi.EINVAL), ("mismatch", 0, _ffi.EINVAL), ("gap_opening1", -1, _ffi.EINVAL),
+    ("gap_extension1", 0, _ffi.EINVAL), ("scope", 7, _ffi.EINVAL), ("span", 3, _ffi.EINVAL),
+    ("heuristic", 9, _ffi.EINVAL), ("distance", 4, _ffi.EUNSUPPORTED),
+])
+def test_config_check_rejects_what_the_reference_exits_on(lib, field, value, code):
+    cfg = _ffi.Config()
+    lib.wfagpu_config_default(C.addressof(cfg))
+    setattr(cfg, field, value)
+    err = C.create_string_buffer(256)
+    assert lib.wfagpu_config_check(C.addressof(cfg), -1, -1, err, 256) == code
+    assert err.value
+
+
+def test_config_check_endsfree_bounds(lib):
+    cfg = _ffi.Config()
+    lib.wfagpu_config_default(C.addressof(cfg))
+    cfg.text_begin_free = 20
+    err = C.create_string_buffer(256)
+    assert lib.wfagpu_config_check(C.addressof(cfg), 100, 20, err, 256) == _ffi.OK
+    assert lib.wfagpu_config_check(C.addressof(cfg), 100, 19, err, 256) == _ffi.EINVAL
+    assert b"Ends-free parameters" in err.value
+
+
+def test_strerror(lib):
+    for code in range(0, -6, -1):
+        assert lib.wfagpu_strerror(code)
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the product path must raise (this test is skipped on a GPU box)."""
+    if lib.wfagpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(_ffi.WfaGpuError) as ei:
+        _ffi.Context(0)
+    assert ei.value.code == _ffi.ENODEVICE
+    a = pywfa_b200.WavefrontAligner("ACGT")
+    with pytest.raises(_ffi.WfaGpuError):
+        a("ACGT")
+    with pytest.raises(_ffi.WfaGpuError):
+        a.align_batch(["ACGT", "AC"])
+
+
+def test_product_package_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pywfa_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.lower() or f == "wfa_core.cuh", f"{f} mentions the oracle"
+    assert "oracle" not in open(os.path.join(ROOT, "pywfa_b200", "csrc", "wfa_core.cuh")).read().lower()
+
+
+# ---- the Python mirror of pywfa's interface ---------------------------------------------------
+def test_constructor_defaults_and_errors():
+    a = pywfa_b200.WavefrontAligner()
+    assert (a.distance, a.scope, a.span, a.heuristic, a.memory_mode) == ("affine", "full", "ends-free", None, "high")
+    assert (a.match_score, a.mismatch_penalty, a.gap_opening_penalty, a.gap_extension_penalty) == (0, 4, 6, 2)
+    assert (a.gap_opening2_penalty, a.gap_extension2_penalty) == (-1, -1)      # unused piece-2 penalties read -1
+    assert a.max_steps == 2 ** 31 - 1
+    b = pywfa_b200.WavefrontAligner(distance="affine2p", match=-1)
+    assert (b.match_score, b.mismatch_penalty, b.gap_opening_penalty, b.gap_extension_penalty,
+            b.gap_opening2_penalty, b.gap_extension2_penalty) == (-1, 10, 12, 5, 48, 3)   # Eizenga transform
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(distance="hamming")
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(distance="levenshtein")     # reference supports it; not on this path
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(scope="partial")
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(memory_mode="tiny")
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(span="local")
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(heuristic="z-drop")
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(mismatch=0)                 # the reference exit(1)s here
+    with pytest.raises(TypeError):
+        pywfa_b200.WavefrontAligner(wildcard=5)
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(wildcard="NN")
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner()("ACGT")                   # pattern is None
+
+
+def test_property_setters():
+    a = pywfa_b200.WavefrontAligner("ACGT", heuristic="adaptive", min_wavefront_length=7, max_steps=5)
+    assert (a.min_wavefront_length, a.max_distance_threshold, a.steps_between_cutoffs, a.max_steps) == (7, 50, 1, 5)
+    a.scope = "score"; a.span = "end-to-end"; a.heuristic = "X-drop"; a.xdrop = 33; a.max_steps = 0
+    assert (a.scope, a.span, a.heuristic, a.xdrop, a.max_steps) == ("score", "end-to-end", "X-drop", 33, 2 ** 31 - 1)
+    a.gap_opening_penalty = 5; a.mismatch_penalty = 3
+    assert (a.gap_opening_penalty, a.mismatch_penalty) == (5, 3)
+    with pytest.raises(ValueError):
+        a.gap_extension_penalty = 0
+    assert a.gap_extension_penalty == 2
+    with pytest.raises(ValueError):
+        a.scope = "nope"
+    a.text_end_free = 9
+    assert a.text_end_free == 9
+
+
+def _result(case):
+    ct = [tuple(c) for c in case["cigartuples"]]
+    return AlignmentResult(case["pattern_length"], case["text_length"], 0, case["pattern_length"],
+                           case["text_start"], case["text_length"], ct, -1, "", "", 0)
+
+
+def test_postprocessing_matches_reference_golden():
+    n = {"clip": 0, "elide": 0, "str": 0}
+    for case in POST:
+        ct = [tuple(c) for c in case["cigartuples"]]
+        if case["kind"] == "clip":
+            res = pywfa_b200.clip_cigartuples(_result(case), case["left"], case["right"])
+            assert [list(c) for c in res.cigartuples] == case["expect"]["cigartuples"]
+            assert [res.pattern_start, res.pattern_end, res.text_start, res.text_end] == case["expect"]["locations"]
+        elif case["kind"] == "elide":
+            assert [list(c) for c in pywfa_b200.elide_mismatches_from_cigar(ct)] == case["expect"]
+        else:
+            assert pywfa_b200.cigartuples_to_str(ct) == case["expect"]
+        n[case["kind"]] += 1
+    assert min(n.values()) > 20
+
+
+def test_alignment_result_helpers():
+    r = AlignmentResult(8, 8, 0, 8, 0, 8, [(0, 3), (8, 1), (0, 4)], -4, "ACGTACGT", "ACGAACGT", 0)
+    assert r.cigarstring == "3M1X4M"
+    assert "ALIGNMENT" in r.pretty and "|||*||||" in r.pretty
+    assert "score: -4" in repr(r)
+    assert str(AlignmentResult(0, 0, 0, 0, 0, 0, [], -3, "", "", 0)) == "Score: -3"

@@ -1,0 +1,86 @@
+"""The oracle (oracle/wfa_oracle.c, a CPU restatement of the reference algorithm) is pinned
+against (a) the golden vectors recorded from the unmodified reference (tests/golden/, made by
+tests/golden/make_golden.py) and (b) the reference itself when oracle/_ref is built."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from pywfa_b200.synth import generate_pairs, pairs_from_strings
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KAT = json.load(open(os.path.join(GOLD, "reference_kat.json")))
+SYN = json.load(open(os.path.join(GOLD, "synthetic.json")))
+
+_CTOR_MAP = dict(gap_opening="gap_opening", gap_extension="gap_extension")
+
+
+def config_from_ctor(oracle, ctor):
+    """pywfa constructor kwargs -> wfagpu_config_t (pattern is not a config field)."""
+    kw = {k: v for k, v in ctor.items() if k != "pattern"}
+    h = kw.get("heuristic")
+    cfg = oracle.make_config(**kw)
+    # only the chosen heuristic's parameters reach the aligner (wavefront_aligner.c:188-224)
+    if h is None:
+        cfg.min_wavefront_length = cfg.max_distance_threshold = cfg.steps_between_cutoffs = cfg.xdrop = 0
+    elif h == "adaptive":
+        cfg.xdrop = 0
+    else:
+        cfg.min_wavefront_length = cfg.max_distance_threshold = 0
+    return cfg
+
+
+@pytest.mark.parametrize("case", KAT, ids=[c["name"] for c in KAT])
+def test_oracle_matches_reference_kat(oracle, case):
+    cfg = config_from_ctor(oracle, case["ctor"])
+    batch = pairs_from_strings([(case["pattern"], case["text"])])
+    r = oracle.align_batch(cfg, *batch, kind="port")
+    e = case["expect"]
+    assert int(r["score"][0]) == e["aligner_score"]
+    assert int(r["status"][0]) == e["aligner_status"]
+    assert oracle.runs_to_cigarstring(r["runs"]) == e["aligner_cigarstring"]
+    if cfg.scope == 1 and not case["call"].get("clip_cigar"):
+        assert r["locs"][0].tolist() == e["locations"]
+
+
+@pytest.mark.parametrize("case", SYN, ids=[c["name"] for c in SYN])
+@pytest.mark.parametrize("bt_mode", [0, 1], ids=["bt-reference", "bt-origin-codes"])
+def test_oracle_matches_reference_synthetic(oracle, case, bt_mode):
+    """bt_mode 1 = backtrace from forward-recorded origin codes, the scheme the CUDA kernels use."""
+    batch = generate_pairs(case["n"], case["length"], case["div"], case["seed"], text_flank=case["flank"])
+    assert int(batch[0].astype(np.uint64).sum()) == case["input_checksum"], "synthetic generator drifted"
+    cfg = oracle.make_config(**case["config"])
+    r = oracle.align_batch(cfg, *batch, kind="port", bt_mode=bt_mode)
+    assert r["score"].tolist() == case["score"]
+    assert r["status"].tolist() == case["status"]
+    cig = [oracle.runs_to_cigarstring(r["runs"][r["cig_off"][j]:r["cig_off"][j + 1]]) for j in range(case["n"])]
+    assert cig == case["cigars"]
+    assert r["locs"].tolist() == case["locations"]
+    if case["config"].get("scope", "full") == "full":
+        assert r["cells"].tolist() == case["cells"]
+
+
+LIVE = [
+    ("affine-e2e", dict(span="end-to-end"), 600, 150, 0.08, 0),
+    ("affine-score", dict(span="end-to-end", scope="score"), 300, 250, 0.10, 0),
+    ("2p-endsfree", dict(distance="affine2p", pattern_end_free=15, text_begin_free=9), 200, 300, 0.12, 6),
+    ("adaptive", dict(heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=10), 200, 300, 0.2, 0),
+    ("xdrop", dict(heuristic="X-drop", xdrop=60, steps_between_cutoffs=2), 200, 300, 0.1, 0),
+    ("match-2", dict(span="end-to-end", match=-2, distance="affine2p"), 200, 150, 0.1, 0),
+]
+
+
+@pytest.mark.parametrize("name,kw,n,length,div,flank", LIVE, ids=[c[0] for c in LIVE])
+def test_oracle_matches_reference_live(oracle, name, kw, n, length, div, flank):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    batch = generate_pairs(n, length, div, seed=31, text_flank=flank)
+    cfg = oracle.make_config(**kw)
+    ref = oracle.align_batch(cfg, *batch, kind="reference")
+    for bt in (0, 1):
+        port = oracle.align_batch(cfg, *batch, kind="port", bt_mode=bt)
+        for k in ("score", "status", "cig_off", "runs"):
+            assert np.array_equal(ref[k], port[k]), (name, bt, k)
+        if kw.get("scope", "full") == "full":
+            assert np.array_equal(ref["cells"], port["cells"])
