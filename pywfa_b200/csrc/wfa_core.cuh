@@ -10,10 +10,13 @@
  *     (W/wavefront/wavefront_extend_kernels.c:64-163) are FUSED: the lane that produces
  *     M[s][k] extends it at once, 16 bases per step, by XOR-ing two funnel-shifted 32-bit
  *     words of the 2-bit packed sequences and counting the agreeing low bit pairs;
- *   - the offset wavefronts live in a ring of max_score_scope slots (M) and e+1 slots
- *     (I1/D1/I2/D2) in shared memory (or in an L2-resident HBM arena for very wide
- *     wavefronts); "outside [lo,hi] reads as NULL" (W/wavefront/wavefront_compute.c:490-567)
- *     is a range check at load time instead of NULL padding;
+ *   - scores advance in units of g = gcd of the penalties (every reachable score is a
+ *     multiple of g), so x=4,o=6,e=2 needs half the steps and a 5-slot ring;
+ *   - the offset wavefronts live in rings of max_score_scope/g slots (M) and e/g+1 slots
+ *     (I1/D1/I2/D2) in shared memory -- int16 offsets for short reads, int32 otherwise -- or
+ *     in an L2-resident HBM arena for very wide wavefronts; a slot is indexed circularly by
+ *     (k & (wcap-1)), and "outside [lo,hi] reads as NULL"
+ *     (W/wavefront/wavefront_compute.c:490-567) is a range check at load time;
  *   - trim_ends (W/wavefront/wavefront_compute.c:571-605), end-to-end / ends-free termination
  *     (W/wavefront/wavefront_termination.c:37-162) and the WF-adaptive / X-drop cut-offs
  *     (W/wavefront/wavefront_heuristic.c:257-383,509-567) are min-reductions over the group;
@@ -32,10 +35,8 @@
 
 #ifdef __CUDACC__
 #define WFA_DEV __device__ __forceinline__
-#define WFA_DEV_NOINLINE __device__ __noinline__
 #else
 #define WFA_DEV inline
-#define WFA_DEV_NOINLINE inline
 #endif
 
 namespace wfagpu {
@@ -54,12 +55,19 @@ enum { PAIR_DONE = 0, PAIR_OVERFLOW = 1 };
 /* status codes, W/wavefront/wfa.h:46-55 */
 constexpr int ST_COMPLETED = 0, ST_PARTIAL = 1, ST_MAX_STEPS = -100, ST_OOM = -200;
 
-constexpr int META_INTS = 12;   /* flags, clo, (lo,hi) x 5 components */
-constexpr int FLAG_EXISTS = 1;  /* M wavefront allocated at this score   */
-WFA_DEV int comp_bit(int c) { return 2 << c; }
-
 /* SAM op codes (pywfa/align.pyx:11-14) */
 constexpr uint32_t OP_M = 0, OP_I = 1, OP_D = 2, OP_X = 8;
+
+/* Offsets as stored in the rings / history.  Everything negative is "null": the reference's
+ * drifting nulls (NULL+1, NULL+2, ... in I/D cells, compute_affine.c:69-75) never take part in
+ * a comparison whose outcome matters, so a narrow type only has to keep negatives negative. */
+template <class T> struct OffTraits;
+template <> struct OffTraits<int32_t> { static constexpr int kNull = OFFNULL; };
+template <> struct OffTraits<int16_t> { static constexpr int kNull = -30000; };
+template <class T> WFA_DEV T off_store(int v) {
+  const int n = OffTraits<T>::kNull;
+  return (T)(v > n ? v : n);
+}
 
 struct PairMeta {      /* 16 bytes, one per pair, in HBM */
   int64_t woff;        /* first 32-bit word of the packed pattern; text words follow it */
@@ -69,17 +77,19 @@ struct PairMeta {      /* 16 bytes, one per pair, in HBM */
 struct KParams {
   /* normalised penalties (W/wavefront/wavefront_penalties.c:95-173) */
   int x, o1, e1, o2, e2, match;
-  int max_scope;                 /* W/wavefront/wavefront_components.c:81-124 */
-  int rm, r1, r2;                /* ring slots: M, I1/D1, I2/D2 */
+  int max_scope;                 /* W/wavefront/wavefront_components.c:81-124 (original units) */
+  /* score unit g = gcd(x, o1+e1, e1[, o2+e2, e2]) and the penalties in that unit */
+  int g, dx, doe1, de1, doe2, de2;
+  int rm, r1, r2;                /* ring slots: M, I1/D1, I2/D2 (scaled look-back + 1) */
+  int mr;                        /* metadata ring entries: power of two >= rm */
   int endsfree;                  /* span */
   int pbf, pef, tbf, tef;
   int heuristic, min_wf_len, max_dist_thr, steps_between, xdrop;
   int max_steps;                 /* INT_MAX = unlimited */
-  /* user (un-normalised) penalties are not needed on the device: maxtrim only ever
-   * sees an empty CIGAR on this path. */
   /* tier capacities */
-  int wcap;                      /* max wavefront width (diagonals) per ring slot */
+  int wcap;                      /* wavefront width capacity per ring slot: power of two */
   int seq_words_cap;             /* words of smem for both packed sequences (0: read HBM) */
+  int group_bytes;               /* shared memory of one group (multiple of 16) */
   long long hcap;                /* history cells per group */
   int scap;                      /* history score-table entries per group */
   int runcap;                    /* CIGAR run staging words per group */
@@ -93,19 +103,20 @@ struct KParams {
   /* results (SoA) */
   int* score; int* status; int* locs; int* nruns; long long* runs_base;
   /* scope=full scratch */
-  int* hist_m0; uint8_t* hist_code; int2* hmeta; uint32_t* runs_stage;
+  void* hist_m0; uint8_t* hist_code; int2* hmeta; uint32_t* runs_stage;
   uint32_t* runs_tmp; unsigned long long* runs_cursor; unsigned long long runs_tmp_cap;
-  /* global ring arena for the widest tier (ints per group = ring_ints) */
-  int* gring; long long gring_ints;
+  /* global ring arena for the widest tier (elements per group = gring_elems) */
+  int* gring; long long gring_elems;
   unsigned long long* cells_total;
 };
 
 /* pointers a group works with for the current pair */
+template <class OffT>
 struct GroupMem {
   const uint32_t* pw; const uint32_t* tw;   /* packed sequences, readable one word past the end */
-  int* ring[5];
-  int* meta;
-  int* h_m0; uint8_t* h_code; int2* hmeta; uint32_t* runs_stage;
+  OffT* ring[5];
+  int4* meta;                               /* [mr][NC] : lo, hi, ring slot, exists */
+  OffT* h_m0; uint8_t* h_code; int2* hmeta; uint32_t* runs_stage;
 };
 
 struct PairResult {
@@ -141,7 +152,7 @@ WFA_DEV uint32_t fetch16(const uint32_t* w, int i) {
  * here 16 bases per XOR, clamped to the sequence ends instead of sentinels.
  */
 WFA_DEV int extend_offset(const uint32_t* pw, const uint32_t* tw, int plen, int tlen, int k, int off) {
-  int v = off - k, h = off;
+  const int v = off - k, h = off;
   const int rem = imin(plen - v, tlen - h);
   int n = 0;
   while (n < rem) {
@@ -167,16 +178,15 @@ WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
 }
 
 /* one source wavefront component as the recurrence reads it */
+template <class OffT>
 struct Src {
-  const int* slot;   /* ring slot base */
-  int clo;           /* diagonal stored at slot[0] */
+  const OffT* slot;  /* ring slot base (circular: element of diagonal k is slot[k & wmask]) */
   int lo, hi;        /* valid range; lo > hi = null */
 };
-WFA_DEV int rd(const Src& s, int k) {
-  return (k >= s.lo && k <= s.hi) ? s.slot[k - s.clo] : OFFNULL;
+template <class OffT>
+WFA_DEV int rd(const Src<OffT>& s, int k, int km) {
+  return (k >= s.lo && k <= s.hi) ? (int)s.slot[km] : OFFNULL;
 }
-
-WFA_DEV int wrap_sub(int cur, int d, int n) { int t = cur - d; return t < 0 ? t + n : t; }
 
 /* ---- CIGAR run emitter (rank 0 only); runs are produced end -> start --------------- */
 struct RunEmitter {
@@ -194,10 +204,10 @@ struct RunEmitter {
  * Backtrace over the recorded history (W/wavefront/wavefront_backtrace.c:320-529).  One
  * thread.  At an M cell the origin code gives the winning source type and the stored
  * pre-extension offset gives the length of the match run; inside a gap only the ext/open
- * bit of that component is needed.  Runs are written end -> start into `em`.
+ * bit of that component is needed.  Scores are in units of g.  Runs are written end -> start.
  */
-template <bool TWO_P>
-WFA_DEV void backtrace(const KParams& P, const GroupMem& gm, int plen, int tlen,
+template <class OffT>
+WFA_DEV void backtrace(const KParams& P, const GroupMem<OffT>& gm, int plen, int tlen,
                        int a_score, int a_k, int a_off, RunEmitter& em) {
   int mt = CM, score = a_score, k = a_k;
   int off = a_off;
@@ -212,7 +222,7 @@ WFA_DEV void backtrace(const KParams& P, const GroupMem& gm, int plen, int tlen,
     if (mt == CM) {
       type = code & 15;
       if (type == BT_NONE) break;
-      const int m0 = gm.h_m0[idx];
+      const int m0 = (int)gm.h_m0[idx];
       em.push(OP_M, off - m0);
       off = m0;
       v = off - k; h = off;
@@ -222,15 +232,15 @@ WFA_DEV void backtrace(const KParams& P, const GroupMem& gm, int plen, int tlen,
     else if (mt == CI2) type = (code & 0x40) ? BT_I2_EXT : BT_I2_OPEN;
     else type = (code & 0x80) ? BT_D2_EXT : BT_D2_OPEN;
     switch (type) {
-      case BT_M: score -= P.x; mt = CM; break;
-      case BT_I1_OPEN: score -= P.o1 + P.e1; mt = CM; break;
-      case BT_I1_EXT: score -= P.e1; mt = CI1; break;
-      case BT_I2_OPEN: score -= P.o2 + P.e2; mt = CM; break;
-      case BT_I2_EXT: score -= P.e2; mt = CI2; break;
-      case BT_D1_OPEN: score -= P.o1 + P.e1; mt = CM; break;
-      case BT_D1_EXT: score -= P.e1; mt = CD1; break;
-      case BT_D2_OPEN: score -= P.o2 + P.e2; mt = CM; break;
-      default: score -= P.e2; mt = CD2; break;
+      case BT_M: score -= P.dx; mt = CM; break;
+      case BT_I1_OPEN: score -= P.doe1; mt = CM; break;
+      case BT_I1_EXT: score -= P.de1; mt = CI1; break;
+      case BT_I2_OPEN: score -= P.doe2; mt = CM; break;
+      case BT_I2_EXT: score -= P.de2; mt = CI2; break;
+      case BT_D1_OPEN: score -= P.doe1; mt = CM; break;
+      case BT_D1_EXT: score -= P.de1; mt = CD1; break;
+      case BT_D2_OPEN: score -= P.doe2; mt = CM; break;
+      default: score -= P.de2; mt = CD2; break;
     }
     if (type == BT_M) { em.push(OP_X, 1); --off; }
     else if (type <= BT_I2_EXT) { em.push(OP_I, 1); --k; --off; }
@@ -268,6 +278,14 @@ WFA_DEV void locations_from_stage(const uint32_t* stage, int n, int plen, int tl
   locs[0] = ps; locs[1] = pe; locs[2] = ts; locs[3] = te;
 }
 
+WFA_DEV bool term_cell(const KParams& P, int plen, int tlen, int ak, int k, int off) {
+  if (P.endsfree) {                            /* termination.c:115-162 */
+    const int hh = off, vv = off - k;
+    return (hh >= tlen && plen - vv <= P.pef) || (vv >= plen && tlen - hh <= P.tef);
+  }
+  return k == ak && off >= tlen;               /* termination.c:37-61 */
+}
+
 /* ------------------------------------------------------------------------------------ */
 /*
  * Align one pair with the thread group `g`.  G provides: rank, size, sync(),
@@ -275,69 +293,60 @@ WFA_DEV void locations_from_stage(const uint32_t* stage, int n, int plen, int tl
  * Returns PAIR_DONE (res filled; for scope=full the reversed runs are in gm.runs_stage)
  * or PAIR_OVERFLOW (a tier capacity was exceeded; retry on a larger tier).
  */
-template <class G, bool TWO_P, bool FULL>
-WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int tlen, PairResult& res) {
-  const int NC = TWO_P ? 5 : 3;
-  const int wcap = P.wcap;
-  int* const meta = gm.meta;
+template <class G, class OffT, bool TWO_P, bool FULL>
+WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int plen, int tlen, PairResult& res) {
+  constexpr int NC = TWO_P ? 5 : 3;
+  const int wcap = P.wcap, wmask = P.wcap - 1, mmask = P.mr - 1;
+  int4* const meta = gm.meta;
   const int ak = tlen - plen;
 
-  int s = 0, cur = 0, c1 = 0, c2 = 0;
-  int num_null = 0;
-  int steps_wait = P.steps_between;          /* W/wavefront/wavefront_heuristic.c:114-121 */
+  int s = 0;                                  /* score in units of g */
+  int cm = 0, c1 = 0, c2 = 0;                 /* ring slots of the current score */
+  int s_exist = 0;                            /* last score (original units) whose wavefront exists */
+  int steps_wait = P.steps_between;           /* W/wavefront/wavefront_heuristic.c:114-121 */
   int max_sw = 0; bool sw_init = false;
   long long cells = 0;
   long long cell_off = 0;
   /* state of the current score's wavefront, uniform across the group */
-  bool cur_exists;
+  bool cur_exists = true;
   int clo[5], chi[5];
   int term_k;
   int end_k = KNONE, end_off = OFFNULL;
-  int status;                                 /* 0 running, 1 end reached, 2 unreachable, 3 max steps */
+  int end_score = 0;                          /* original units */
+  int status;                                 /* 1 end reached, 2 unreachable, 3 max steps */
 
   /* ---- score 0: wavefront_aligner_init_wf_m, W/wavefront/wavefront_aligner.c:251-310 ---- */
   {
     const bool ef = P.endsfree && P.match == 0;
     const int lo = ef ? -P.pbf : 0, hi = ef ? P.tbf : 0;
     if (hi - lo + 1 > wcap) return PAIR_OVERFLOW;
+    /* every metadata slot starts null: scores < 0 read as the null wavefront */
+    for (int i = g.rank; i < P.mr * NC; i += g.size) meta[i] = make_int4(1, -1, 0, 0);
+    g.sync();
     int t = KNONE;
-    int* const mslot = gm.ring[CM];
+    OffT* const mslot = gm.ring[CM];
     for (int k = lo + g.rank; k <= hi; k += g.size) {
       const int off0 = k > 0 ? k : 0;
       const int off = extend_offset(gm.pw, gm.tw, plen, tlen, k, off0);
-      mslot[k - lo] = off;
-      bool term;
-      if (P.endsfree) {
-        const int hh = off, vv = off - k;
-        term = (hh >= tlen && plen - vv <= P.pef) || (vv >= plen && tlen - hh <= P.tef);
-      } else term = (k == ak && off >= tlen);
-      if (term) t = imin(t, k);
+      mslot[k & wmask] = (OffT)off;
+      if (term_cell(P, plen, tlen, ak, k, off)) t = imin(t, k);
     }
     int r[1] = {t};
     g.template allmin<1>(r);
     term_k = r[0];
     for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
     clo[CM] = lo; chi[CM] = hi;
-    cur_exists = true;
-    if (g.rank == 0) {
-      meta[0] = FLAG_EXISTS | comp_bit(CM);
-      meta[1] = lo;
-      meta[2] = lo; meta[3] = hi;
-      for (int c = 1; c < 5; ++c) { meta[2 + 2 * c] = 1; meta[3 + 2 * c] = -1; }
-    }
+    if (g.rank == 0) meta[CM] = make_int4(lo, hi, 0, 1);
     g.sync();
   }
 
   for (;;) {
     /* ---- after-extend step of score s (extend.c:90-125 / :263-297) ---- */
-    if (!cur_exists) {
-      if (num_null > P.max_scope) { status = 2; break; }          /* extend.c:99-106 */
-    } else {
-      const int cur_clo = meta[cur * META_INTS + 1];
+    if (cur_exists) {
       if (term_k != KNONE) {
         end_k = term_k;
-        end_off = gm.ring[CM][cur * wcap + (term_k - cur_clo)];
-        status = 1;
+        end_off = (int)gm.ring[CM][cm * wcap + (term_k & wmask)];
+        status = 1; end_score = s * P.g;
         cells += imax(0, chi[CM] - clo[CM] + 1);
         break;
       }
@@ -345,14 +354,14 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
         /* wavefront_heuristic_cufoff, heuristic.c:509-567 */
         --steps_wait;
         const int lo_base = clo[CM], hi_base = chi[CM];
-        const int* const mslot = gm.ring[CM] + cur * wcap;
+        const OffT* const mslot = gm.ring[CM] + cm * wcap;
         if (steps_wait <= 0) {
           if (P.heuristic == 1) {
             /* wavefront_heuristic_wfadaptive, heuristic.c:257-293 */
             if (hi_base - lo_base + 1 >= P.min_wf_len) {
               int dm = INT_MAX;
               for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-                const int f = mslot[k - cur_clo];
+                const int f = (int)mslot[k & wmask];
                 const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
                 dm = imin(dm, d);
               }
@@ -361,7 +370,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
               const int min_d = imin(imax(plen, tlen), r1[0]);
               int kf = INT_MAX, kl = INT_MIN;
               for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-                const int f = mslot[k - cur_clo];
+                const int f = (int)mslot[k & wmask];
                 const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
                 if (d - min_d <= P.max_dist_thr) { kf = imin(kf, k); kl = imax(kl, k); }
               }
@@ -378,11 +387,12 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
           } else {
             /* wavefront_heuristic_xdrop, heuristic.c:329-383 (+ sw scores :297-328) */
             const int swg = (P.match != 0) ? -P.match : -1;
+            const int so = s * P.g;
             int cmax = INT_MIN, kf = INT_MAX, kl = INT_MIN;
             for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-              const int f = mslot[k - cur_clo];
+              const int f = (int)mslot[k & wmask];
               if (f < 0) continue;
-              const int sw = (swg * (2 * f - k) - s) / 2;
+              const int sw = (swg * (2 * f - k) - so) / 2;
               cmax = imax(cmax, sw);
               if (sw_init && max_sw - sw < P.xdrop) { kf = imin(kf, k); kl = imax(kl, k); }
             }
@@ -407,14 +417,13 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
             if (chi[CM] < chi[c]) chi[c] = chi[CM];
           }
           if (g.rank == 0) {
-            int fl = FLAG_EXISTS;
+            int4* const mrow = meta + (s & mmask) * NC;
             for (int c = 0; c < NC; ++c) {
               const bool nn = clo[c] <= chi[c];
-              if (nn) fl |= comp_bit(c);
-              meta[cur * META_INTS + 2 + 2 * c] = nn ? clo[c] : 1;
-              meta[cur * META_INTS + 3 + 2 * c] = nn ? chi[c] : -1;
+              int4 m = mrow[c];
+              m.x = nn ? clo[c] : 1; m.y = nn ? chi[c] : -1;
+              mrow[c] = m;
             }
-            meta[cur * META_INTS] = fl;
           }
           g.sync();
         }
@@ -424,56 +433,45 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
 
     /* ---- compute score s+1 (compute_affine.c:229-260 / compute_affine2p.c:334-368) ---- */
     ++s;
-    if (++cur == P.rm) cur = 0;
+    if (++cm == P.rm) cm = 0;
     if (++c1 == P.r1) c1 = 0;
     if (TWO_P) { if (++c2 == P.r2) c2 = 0; }
     {
-      const int sx = s - P.x, so1 = s - P.o1 - P.e1, se1 = s - P.e1;
-      const int slx = wrap_sub(cur, P.x, P.rm), slo1 = wrap_sub(cur, P.o1 + P.e1, P.rm),
-                sle1 = wrap_sub(cur, P.e1, P.rm);
-      const int fx = sx >= 0 ? meta[slx * META_INTS] : 0;
-      const int fo1 = so1 >= 0 ? meta[slo1 * META_INTS] : 0;
-      const int fe1 = se1 >= 0 ? meta[sle1 * META_INTS] : 0;
-      int slo2 = 0, sle2 = 0, fo2 = 0, fe2 = 0;
+      /* fetch_input, compute.c:298-344: one 16-byte metadata read per source component */
+      const int4 aMx = meta[((s - P.dx) & mmask) * NC + CM];
+      const int4 aMo1 = meta[((s - P.doe1) & mmask) * NC + CM];
+      const int4* const rowe1 = meta + ((s - P.de1) & mmask) * NC;
+      const int4 aI1 = rowe1[CI1], aD1 = rowe1[CD1];
+      int4 aMo2 = make_int4(1, -1, 0, 0), aI2 = aMo2, aD2 = aMo2;
       if (TWO_P) {
-        const int so2 = s - P.o2 - P.e2, se2 = s - P.e2;
-        slo2 = wrap_sub(cur, P.o2 + P.e2, P.rm); sle2 = wrap_sub(cur, P.e2, P.rm);
-        fo2 = so2 >= 0 ? meta[slo2 * META_INTS] : 0;
-        fe2 = se2 >= 0 ? meta[sle2 * META_INTS] : 0;
+        aMo2 = meta[((s - P.doe2) & mmask) * NC + CM];
+        const int4* const rowe2 = meta + ((s - P.de2) & mmask) * NC;
+        aI2 = rowe2[CI2]; aD2 = rowe2[CD2];
       }
-      const bool n_mx = !(fx & comp_bit(CM)), n_mo1 = !(fo1 & comp_bit(CM));
-      const bool n_i1 = !(fe1 & comp_bit(CI1)), n_d1 = !(fe1 & comp_bit(CD1));
-      const bool n_mo2 = TWO_P ? !(fo2 & comp_bit(CM)) : true;
-      const bool n_i2 = TWO_P ? !(fe2 & comp_bit(CI2)) : true;
-      const bool n_d2 = TWO_P ? !(fe2 & comp_bit(CD2)) : true;
+      const bool n_mx = aMx.x > aMx.y, n_mo1 = aMo1.x > aMo1.y, n_i1 = aI1.x > aI1.y, n_d1 = aD1.x > aD1.y;
+      const bool n_mo2 = TWO_P ? aMo2.x > aMo2.y : true;
+      const bool n_i2 = TWO_P ? aI2.x > aI2.y : true;
+      const bool n_d2 = TWO_P ? aD2.x > aD2.y : true;
+      int4* const mrow = meta + (s & mmask) * NC;
       if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
         /* null step: allocate_output_null, compute.c:374-400 */
-        ++num_null;
         cur_exists = false;
         for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
         term_k = KNONE;
-        if (g.rank == 0) meta[cur * META_INTS] = 0;
+        for (int c = g.rank; c < NC; c += g.size) mrow[c] = make_int4(1, -1, 0, 0);
         g.sync();
       } else {
-        num_null = 0;
-        Src sMx, sMo1, sI1, sD1, sMo2, sI2, sD2;
-#define WFA_SRC(S, isnull, slotidx, ring_, ringslot, comp)                              \
-        if (isnull) { S.slot = gm.ring[ring_]; S.clo = 0; S.lo = 1; S.hi = -1; }          \
-        else { S.slot = gm.ring[ring_] + (ringslot) * wcap; S.clo = meta[(slotidx) * META_INTS + 1]; \
-               S.lo = meta[(slotidx) * META_INTS + 2 + 2 * (comp)];                        \
-               S.hi = meta[(slotidx) * META_INTS + 3 + 2 * (comp)]; }
-        WFA_SRC(sMx, n_mx, slx, CM, slx, CM)
-        WFA_SRC(sMo1, n_mo1, slo1, CM, slo1, CM)
-        const int r1src = wrap_sub(c1, P.e1, P.r1);
-        WFA_SRC(sI1, n_i1, sle1, CI1, r1src, CI1)
-        WFA_SRC(sD1, n_d1, sle1, CD1, r1src, CD1)
+        s_exist = s * P.g;
+        Src<OffT> sMx, sMo1, sI1, sD1, sMo2, sI2, sD2;
+        sMx.slot = gm.ring[CM] + aMx.z * wcap; sMx.lo = aMx.x; sMx.hi = aMx.y;
+        sMo1.slot = gm.ring[CM] + aMo1.z * wcap; sMo1.lo = aMo1.x; sMo1.hi = aMo1.y;
+        sI1.slot = gm.ring[CI1] + aI1.z * wcap; sI1.lo = aI1.x; sI1.hi = aI1.y;
+        sD1.slot = gm.ring[CD1] + aD1.z * wcap; sD1.lo = aD1.x; sD1.hi = aD1.y;
         if (TWO_P) {
-          WFA_SRC(sMo2, n_mo2, slo2, CM, slo2, CM)
-          const int r2src = wrap_sub(c2, P.e2, P.r2);
-          WFA_SRC(sI2, n_i2, sle2, CI2, r2src, CI2)
-          WFA_SRC(sD2, n_d2, sle2, CD2, r2src, CD2)
+          sMo2.slot = gm.ring[CM] + aMo2.z * wcap; sMo2.lo = aMo2.x; sMo2.hi = aMo2.y;
+          sI2.slot = gm.ring[CI2] + aI2.z * wcap; sI2.lo = aI2.x; sI2.hi = aI2.y;
+          sD2.slot = gm.ring[CD2] + aD2.z * wcap; sD2.lo = aD2.x; sD2.hi = aD2.y;
         }
-#undef WFA_SRC
         /* wavefront_compute_limits_input, compute.c:40-86 (null inputs carry lo=1, hi=-1) */
         int lo = sMx.lo, hi = sMx.hi;
         lo = imin(lo, sMo1.lo - 1); hi = imax(hi, sMo1.hi + 1);
@@ -490,36 +488,36 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
         /* allocate_output, compute.c:401-486 */
         const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
         const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
-        int* const oM = gm.ring[CM] + cur * wcap;
-        int* const oI1 = gm.ring[CI1] + c1 * wcap;
-        int* const oD1 = gm.ring[CD1] + c1 * wcap;
-        int* const oI2 = TWO_P ? gm.ring[CI2] + c2 * wcap : nullptr;
-        int* const oD2 = TWO_P ? gm.ring[CD2] + c2 * wcap : nullptr;
-        /* reductions: [2c] = first in-bounds k, [2c+1] = -(last in-bounds k), [2*NC] = term */
+        OffT* const oM = gm.ring[CM] + cm * wcap;
+        OffT* const oI1 = gm.ring[CI1] + c1 * wcap;
+        OffT* const oD1 = gm.ring[CD1] + c1 * wcap;
+        OffT* const oI2 = TWO_P ? gm.ring[CI2] + c2 * wcap : nullptr;
+        OffT* const oD2 = TWO_P ? gm.ring[CD2] + c2 * wcap : nullptr;
+        /* reductions: [2c] = first in-bounds k, [2c+1] = -(last in-bounds k), [10] = term */
         int red[2 * 5 + 1];
         for (int i = 0; i < 2 * 5 + 1; ++i) red[i] = INT_MAX;
         for (int k = lo + g.rank; k <= hi; k += g.size) {
-          const int i1o = rd(sMo1, k - 1), i1e = rd(sI1, k - 1);
-          const int d1o = rd(sMo1, k + 1), d1e = rd(sD1, k + 1);
-          const int mis = rd(sMx, k) + 1;
+          const int km = k & wmask, kl = (k - 1) & wmask, kr = (k + 1) & wmask;
+          const int i1o = rd(sMo1, k - 1, kl), i1e = rd(sI1, k - 1, kl);
+          const int d1o = rd(sMo1, k + 1, kr), d1e = rd(sD1, k + 1, kr);
+          const int mis = rd(sMx, k, km) + 1;
           const int ins1 = imax(i1o, i1e) + 1, del1 = imax(d1o, d1e);
           int ins = ins1, del = del1;
           int i2o = OFFNULL, i2e = OFFNULL, d2o = OFFNULL, d2e = OFFNULL, ins2 = OFFNULL, del2 = OFFNULL;
           if (TWO_P) {
-            i2o = rd(sMo2, k - 1); i2e = rd(sI2, k - 1);
-            d2o = rd(sMo2, k + 1); d2e = rd(sD2, k + 1);
+            i2o = rd(sMo2, k - 1, kl); i2e = rd(sI2, k - 1, kl);
+            d2o = rd(sMo2, k + 1, kr); d2e = rd(sD2, k + 1, kr);
             ins2 = imax(i2o, i2e) + 1; del2 = imax(d2o, d2e);
             ins = imax(ins1, ins2); del = imax(del1, del2);
           }
           int mx = imax(del, imax(mis, ins));
           const bool m_in = in_bounds(k, mx, plen, tlen);
           if (!m_in) mx = OFFNULL;
-          const int i = k - lo;
-          if (has_i1) { oI1[i] = ins1; if (in_bounds(k, ins1, plen, tlen)) { red[2] = imin(red[2], k); red[3] = imin(red[3], -k); } }
-          if (has_d1) { oD1[i] = del1; if (in_bounds(k, del1, plen, tlen)) { red[4] = imin(red[4], k); red[5] = imin(red[5], -k); } }
+          if (has_i1) { oI1[km] = off_store<OffT>(ins1); if (in_bounds(k, ins1, plen, tlen)) { red[2] = imin(red[2], k); red[3] = imin(red[3], -k); } }
+          if (has_d1) { oD1[km] = off_store<OffT>(del1); if (in_bounds(k, del1, plen, tlen)) { red[4] = imin(red[4], k); red[5] = imin(red[5], -k); } }
           if (TWO_P) {
-            if (has_i2) { oI2[i] = ins2; if (in_bounds(k, ins2, plen, tlen)) { red[6] = imin(red[6], k); red[7] = imin(red[7], -k); } }
-            if (has_d2) { oD2[i] = del2; if (in_bounds(k, del2, plen, tlen)) { red[8] = imin(red[8], k); red[9] = imin(red[9], -k); } }
+            if (has_i2) { oI2[km] = off_store<OffT>(ins2); if (in_bounds(k, ins2, plen, tlen)) { red[6] = imin(red[6], k); red[7] = imin(red[7], -k); } }
+            if (has_d2) { oD2[km] = off_store<OffT>(del2); if (in_bounds(k, del2, plen, tlen)) { red[8] = imin(red[8], k); red[9] = imin(red[9], -k); } }
           }
           if (FULL) {
             /* origin code: winner of max over (offset<<4 | type), backtrace.c:366-389 */
@@ -535,20 +533,15 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
               code |= (x2 << 6) | (y2 << 7);
             }
             code |= (best >= 0) ? (best & 15) : 0;
-            gm.h_m0[cell_off + i] = mx;
-            gm.h_code[cell_off + i] = (uint8_t)code;
+            gm.h_m0[cell_off + (k - lo)] = off_store<OffT>(mx);
+            gm.h_code[cell_off + (k - lo)] = (uint8_t)code;
           }
           if (m_in) {
             red[0] = imin(red[0], k); red[1] = imin(red[1], -k);
             mx = extend_offset(gm.pw, gm.tw, plen, tlen, k, mx);
-            bool term;
-            if (P.endsfree) {
-              const int hh = mx, vv = mx - k;
-              term = (hh >= tlen && plen - vv <= P.pef) || (vv >= plen && tlen - hh <= P.tef);
-            } else term = (k == ak && mx >= tlen);
-            if (term) red[2 * 5] = imin(red[2 * 5], k);
+            if (term_cell(P, plen, tlen, ak, k, mx)) red[10] = imin(red[10], k);
           }
-          oM[i] = mx;
+          oM[km] = off_store<OffT>(mx);
         }
         if (TWO_P) g.template allmin<11>(red);
         else {
@@ -565,25 +558,38 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
           else { clo[c] = 1; chi[c] = -1; }
         }
         cur_exists = true;
-        if (g.rank == 0) {
-          int fl = FLAG_EXISTS;
-          for (int c = 0; c < NC; ++c) {
-            if (clo[c] <= chi[c]) fl |= comp_bit(c);
-            meta[cur * META_INTS + 2 + 2 * c] = clo[c];
-            meta[cur * META_INTS + 3 + 2 * c] = chi[c];
+        for (int c = g.rank; c < NC; c += g.size) {
+          /* lane c publishes component c */
+          int l = clo[0], h = chi[0], z = cm;
+          if (c == 1) { l = clo[1]; h = chi[1]; z = c1; }
+          if (c == 2) { l = clo[2]; h = chi[2]; z = c1; }
+          if (TWO_P) {
+            if (c == 3) { l = clo[3]; h = chi[3]; z = c2; }
+            if (c == 4) { l = clo[4]; h = chi[4]; z = c2; }
           }
-          meta[cur * META_INTS] = fl;
-          meta[cur * META_INTS + 1] = lo;
-          if (FULL) gm.hmeta[s] = make_int2((int)cell_off, lo);
+          mrow[c] = make_int4(l, h, z, 1);
         }
-        if (FULL) cell_off += width;
+        if (FULL) {
+          if (g.rank == 0) gm.hmeta[s] = make_int2((int)cell_off, lo);
+          cell_off += width;
+        }
         g.sync();
       }
     }
-    if (s >= P.max_steps) {                         /* unialign.c:98-109 */
-      status = 3;
-      cells += imax(0, chi[CM] - clo[CM] + 1);
-      break;
+    /* unreachable (extend.c:99-106: M[s] missing and num_null_steps > max_score_scope) and the
+     * step limit (unialign.c:98-109), decided in ORIGINAL score units: between two multiples
+     * of g every score is a null step of the reference. */
+    {
+      const int so = s * P.g;
+      if (!cur_exists) {
+        const int su = s_exist + P.max_scope + 1;
+        if (su <= so && su < P.max_steps) { status = 2; end_score = su; break; }
+      }
+      if (so >= P.max_steps) {
+        status = 3;
+        if (so == P.max_steps) cells += imax(0, chi[CM] - clo[CM] + 1);
+        break;
+      }
     }
   }
 
@@ -594,21 +600,21 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem& gm, int plen, int
   if (status == 3) {
     res.score = -P.max_steps; res.status = ST_MAX_STEPS;
   } else if (!FULL) {
-    if (status == 1) { res.score = classic_score(P.match, plen, tlen, s); res.status = ST_COMPLETED; }
+    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score); res.status = ST_COMPLETED; }
     else {
       /* end position was never assigned: end_v = NULL - DIAGONAL_NULL with int32 wrap */
       const int32_t end_v = (int32_t)((uint32_t)OFFNULL - (uint32_t)INT_MAX);
-      res.score = classic_score(P.match, end_v, OFFNULL, s); res.status = ST_PARTIAL;
+      res.score = classic_score(P.match, end_v, OFFNULL, end_score); res.status = ST_PARTIAL;
     }
   } else {
     if (status == 1) {
       if (g.rank == 0) {
         RunEmitter em; em.init(gm.runs_stage, P.runcap);
-        backtrace<TWO_P>(P, gm, plen, tlen, s, end_k, end_off, em);
+        backtrace<OffT>(P, gm, plen, tlen, s, end_k, end_off, em);
         res.nruns = em.n;
         locations_from_stage(gm.runs_stage, imin(em.n, P.runcap), plen, tlen, res.locs);
       }
-      res.score = classic_score(P.match, end_off - end_k, end_off, s);
+      res.score = classic_score(P.match, end_off - end_k, end_off, end_score);
       res.status = ST_COMPLETED;
     } else {
       /* dropped: no end position -> empty CIGAR; maxtrim on an empty CIGAR clears the

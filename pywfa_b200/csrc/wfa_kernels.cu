@@ -74,42 +74,41 @@ struct BlockGroup {
 };
 
 /* ---- the persistent alignment kernel ------------------------------------------------- */
-template <bool TWO_P, bool FULL, int MODE>
+/* shared memory of one group: [metadata int4 x mr*NC][packed sequences][offset rings OffT] */
+template <bool TWO_P, bool FULL, int MODE, class OffT>
 __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) int smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool BLOCK = (MODE != 0);
+  constexpr int NC = TWO_P ? 5 : 3;
   using G = typename std::conditional<BLOCK, BlockGroup, WarpGroup>::type;
-
-  const int NS = P.rm + 2 * P.r1 + (TWO_P ? 2 * P.r2 : 0);
-  const int ring_ints = (MODE == 2) ? 0 : NS * P.wcap;
-  const int group_ints = P.seq_words_cap + ring_ints + P.rm * META_INTS;
 
   G g;
   int group_id;
-  int* base;
+  unsigned char* base;
   if (BLOCK) {
     g.rank = threadIdx.x; g.size = blockDim.x;
     group_id = blockIdx.x;
-    base = smem;
+    base = smem_raw;
   } else {
     g.rank = threadIdx.x & 31; g.size = 32;
     const int wpb = blockDim.x >> 5;
     group_id = blockIdx.x * wpb + (threadIdx.x >> 5);
-    base = smem + (threadIdx.x >> 5) * group_ints;
+    base = smem_raw + (size_t)(threadIdx.x >> 5) * P.group_bytes;
   }
-  if constexpr (BLOCK) { g.red = smem + group_ints; g.parity = 0; }
+  if constexpr (BLOCK) { g.red = reinterpret_cast<int*>(smem_raw + P.group_bytes); g.parity = 0; }
 
-  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base);
-  int* ringbase = (MODE == 2) ? (P.gring + (long long)group_id * P.gring_ints) : (base + P.seq_words_cap);
-  GroupMem gm;
+  GroupMem<OffT> gm;
+  gm.meta = reinterpret_cast<int4*>(base);
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * NC * 16);
+  OffT* ringbase = (MODE == 2) ? reinterpret_cast<OffT*>(P.gring) + (long long)group_id * P.gring_elems
+                               : reinterpret_cast<OffT*>(sm_seq + P.seq_words_cap);
   gm.ring[CM] = ringbase;
   gm.ring[CI1] = gm.ring[CM] + P.rm * P.wcap;
   gm.ring[CD1] = gm.ring[CI1] + P.r1 * P.wcap;
   gm.ring[CI2] = gm.ring[CD1] + P.r1 * P.wcap;
   gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * P.wcap : 0);
-  gm.meta = base + P.seq_words_cap + ring_ints;
   if (FULL) {
-    gm.h_m0 = P.hist_m0 + (long long)group_id * P.hcap;
+    gm.h_m0 = reinterpret_cast<OffT*>(P.hist_m0) + (long long)group_id * P.hcap;
     gm.h_code = P.hist_code + (long long)group_id * P.hcap;
     gm.hmeta = P.hmeta + (long long)group_id * P.scap;
     gm.runs_stage = P.runs_stage + (long long)group_id * P.runcap;
@@ -146,7 +145,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
         gm.pw = gw; gm.tw = gw + pwn;      /* device buffer carries one pad word */
       }
       g.sync();
-      rc = align_pair<G, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+      rc = align_pair<G, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
     }
     if (rc == PAIR_OVERFLOW) {
       if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
@@ -264,49 +263,58 @@ __global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long lo
 }
 
 /* ---- launch wrappers (C++ linkage, used by wfagpu_api.cpp) -------------------------- */
-template <bool TWO_P, bool FULL, int MODE>
+template <bool TWO_P, bool FULL, int MODE, class OffT>
 static cudaError_t launch_one(const KParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-  auto kern = wfa_align_kernel<TWO_P, FULL, MODE>;
+  auto kern = wfa_align_kernel<TWO_P, FULL, MODE, OffT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, block, smem, st>>>(P);
   return cudaGetLastError();
 }
 
-template <bool TWO_P, bool FULL, int MODE>
+template <bool TWO_P, bool FULL, int MODE, class OffT>
 static int occupancy_one(int block, size_t smem) {
-  auto kern = wfa_align_kernel<TWO_P, FULL, MODE>;
+  auto kern = wfa_align_kernel<TWO_P, FULL, MODE, OffT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem) != cudaSuccess) return 0;
   return nb;
 }
 
+/* int16 offset rings exist for the warp tiers only */
 #define WFA_DISPATCH(FN, ...)                                                   \
   do {                                                                          \
     const int key = (two_p ? 1 : 0) | (full ? 2 : 0) | (mode << 2);             \
+    if (off16 && mode == 0) {                                                   \
+      switch (key) {                                                            \
+        case 0: return FN<false, false, 0, int16_t>(__VA_ARGS__);               \
+        case 1: return FN<true, false, 0, int16_t>(__VA_ARGS__);                \
+        case 2: return FN<false, true, 0, int16_t>(__VA_ARGS__);                \
+        default: return FN<true, true, 0, int16_t>(__VA_ARGS__);                \
+      }                                                                         \
+    }                                                                           \
     switch (key) {                                                              \
-      case 0: return FN<false, false, 0>(__VA_ARGS__);                          \
-      case 1: return FN<true, false, 0>(__VA_ARGS__);                           \
-      case 2: return FN<false, true, 0>(__VA_ARGS__);                           \
-      case 3: return FN<true, true, 0>(__VA_ARGS__);                            \
-      case 4: return FN<false, false, 1>(__VA_ARGS__);                          \
-      case 5: return FN<true, false, 1>(__VA_ARGS__);                           \
-      case 6: return FN<false, true, 1>(__VA_ARGS__);                           \
-      case 7: return FN<true, true, 1>(__VA_ARGS__);                            \
-      case 8: return FN<false, false, 2>(__VA_ARGS__);                          \
-      case 9: return FN<true, false, 2>(__VA_ARGS__);                           \
-      case 10: return FN<false, true, 2>(__VA_ARGS__);                          \
-      default: return FN<true, true, 2>(__VA_ARGS__);                           \
+      case 0: return FN<false, false, 0, int32_t>(__VA_ARGS__);                 \
+      case 1: return FN<true, false, 0, int32_t>(__VA_ARGS__);                  \
+      case 2: return FN<false, true, 0, int32_t>(__VA_ARGS__);                  \
+      case 3: return FN<true, true, 0, int32_t>(__VA_ARGS__);                   \
+      case 4: return FN<false, false, 1, int32_t>(__VA_ARGS__);                 \
+      case 5: return FN<true, false, 1, int32_t>(__VA_ARGS__);                  \
+      case 6: return FN<false, true, 1, int32_t>(__VA_ARGS__);                  \
+      case 7: return FN<true, true, 1, int32_t>(__VA_ARGS__);                   \
+      case 8: return FN<false, false, 2, int32_t>(__VA_ARGS__);                 \
+      case 9: return FN<true, false, 2, int32_t>(__VA_ARGS__);                  \
+      case 10: return FN<false, true, 2, int32_t>(__VA_ARGS__);                 \
+      default: return FN<true, true, 2, int32_t>(__VA_ARGS__);                  \
     }                                                                           \
   } while (0)
 
-cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, int grid, int block,
+cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool off16, int grid, int block,
                          size_t smem, cudaStream_t st) {
   WFA_DISPATCH(launch_one, P, grid, block, smem, st);
 }
 
-int align_occupancy(bool two_p, bool full, int mode, int block, size_t smem) {
+int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size_t smem) {
   WFA_DISPATCH(occupancy_one, block, smem);
 }
 

@@ -9,9 +9,9 @@ namespace wfagpu {
 struct KParams;
 
 /* mode 0: warp-per-pair (smem ring), 1: block-per-pair (smem ring), 2: block-per-pair (HBM ring) */
-cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, int grid, int block,
+cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool off16, int grid, int block,
                          size_t smem, cudaStream_t st);
-int align_occupancy(bool two_p, bool full, int mode, int block, size_t smem);
+int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size_t smem);
 size_t block_reduce_smem_bytes();
 
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the

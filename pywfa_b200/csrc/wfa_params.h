@@ -27,10 +27,19 @@ inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
   int scope_indel = k.o1 + k.e1;
   if (two_p) scope_indel = std::max(scope_indel, k.o2 + k.e2);
   k.max_scope = std::max(scope_indel, k.x) + 1;
-  k.rm = k.max_scope;
-  k.r1 = k.e1 + 1;
-  k.r2 = two_p ? k.e2 + 1 : 1;
   if (!two_p) { k.o2 = 0; k.e2 = 1; }
+  /* every reachable score is a sum of x, o+e and e terms: step in units of their gcd */
+  auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+  int g = gcd(gcd(k.x, k.o1 + k.e1), k.e1);
+  if (two_p) g = gcd(gcd(g, k.o2 + k.e2), k.e2);
+  k.g = g;
+  k.dx = k.x / g; k.doe1 = (k.o1 + k.e1) / g; k.de1 = k.e1 / g;
+  k.doe2 = two_p ? (k.o2 + k.e2) / g : 1; k.de2 = two_p ? k.e2 / g : 1;
+  k.rm = std::max(k.dx, std::max(k.doe1, two_p ? k.doe2 : 0)) + 1;
+  k.r1 = k.de1 + 1;
+  k.r2 = two_p ? k.de2 + 1 : 1;
+  k.mr = 1;
+  while (k.mr < k.rm) k.mr <<= 1;
   k.endsfree = c.span == WFAGPU_SPAN_ENDSFREE;
   k.pbf = c.pattern_begin_free; k.pef = c.pattern_end_free;
   k.tbf = c.text_begin_free; k.tef = c.text_end_free;

@@ -70,7 +70,9 @@ struct Tier {
   int threads = 128;
   int groups_per_block = 4;
   int wcap = 64;
+  bool off16 = false;      /* int16 offset rings + history */
   int seq_words_cap = 0;
+  int group_bytes = 0;
   size_t smem = 0;
   int blocks_per_sm = 1;
   long long hcap = 0;
@@ -142,59 +144,78 @@ long long score_bound(const KParams& k, long long p, long long t) {
   return std::min(b, gaps);
 }
 
+int pow2_floor(long long v) { int p = 1; while (2ll * p <= v) p <<= 1; return p; }
+int pow2_ceil(long long v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+size_t group_bytes_of(const KParams& k, bool two_p, int seqw, int wcap, int elem) {
+  const int ns = k.rm + 2 * k.r1 + (two_p ? 2 * k.r2 : 0);
+  const int nc = two_p ? 5 : 3;
+  const size_t bytes = (size_t)k.mr * nc * 16 + 4ull * seqw + (size_t)ns * wcap * elem;
+  return (bytes + 15) & ~(size_t)15;
+}
+
 void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const KParams& k = b->kp;
-  const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
   const int seqw = (b->maxp + 15) / 16 + (b->maxt + 15) / 16 + 2;
   const long long wmax = (long long)b->maxp + b->maxt + 1;
-  const int wmax32 = (int)std::min<long long>((wmax + 31) & ~31ll, INT_MAX / 2);
-  const int meta = k.rm * META_INTS;
+  const int wmax2 = pow2_ceil(std::max<long long>(wmax, 32));
   const long long sb = std::min<long long>(score_bound(k, b->maxp, b->maxt), k.max_steps);
-  const long long scap_bound = std::min<long long>(sb + k.max_scope + 4, INT_MAX / 4);
+  const long long scap_bound = std::min<long long>(sb / k.g + k.rm + 4, INT_MAX / 4);
   const long long cells_bound = std::min<long long>(scap_bound * wmax, (long long)4e18 / 8);
   const int smem_max = ctx->smem_optin;
+  /* int16 rings hold offsets up to ~tlen + width and nulls that drift by one per step */
+  const bool short_reads = 2ll * ((long long)b->maxp + b->maxt) + 4096 < 30000;
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
-    wcap = std::min(wcap, wmax32);
+    wcap = std::min(wcap, wmax2);
     if (wcap <= last_wcap) return;
-    const size_t bytes = 4ull * (seqw + (size_t)ns * wcap + meta);
-    if (bytes > 40 * 1024) return;
     Tier t;
     t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = wcap; t.seq_words_cap = seqw;
-    t.smem = bytes * 4;
-    t.hcap = std::min(hcap, cells_bound); t.scap = (int)std::min<long long>(scap, scap_bound);
+    t.scap = (int)std::min<long long>(scap, scap_bound);
+    t.off16 = short_reads && t.scap <= 16384 && wcap <= 2048;
+    t.group_bytes = (int)group_bytes_of(k, b->two_p, seqw, wcap, t.off16 ? 2 : 4);
+    if (t.group_bytes > 48 * 1024) return;
+    t.smem = (size_t)t.group_bytes * 4;
+    t.hcap = std::min(hcap, cells_bound);
     b->tiers.push_back(t);
     last_wcap = wcap;
   };
-  add_warp(64, 4096, 512);
-  add_warp(256, 65536, 4096);
+  /* first warp tier: the widest power of two that still leaves >= 32 resident warps per SM */
+  int w0 = 32;
+  while (w0 < 1024 && group_bytes_of(k, b->two_p, seqw, w0 * 2, short_reads ? 2 : 4) <= 6912) w0 *= 2;
+  add_warp(w0, 16384, 1024);
+  add_warp(w0 * 4, 131072, 8192);
   {
-    const long long avail = (long long)smem_max - 1024 - (long long)block_reduce_smem_bytes() - 4ll * (seqw + meta);
-    long long wcap = avail > 0 ? (avail / (4ll * ns)) & ~31ll : 0;
-    wcap = std::min<long long>(wcap, wmax32);
-    if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax32)) {
+    const long long avail = (long long)smem_max - 1024 - (long long)block_reduce_smem_bytes() -
+                            (long long)group_bytes_of(k, b->two_p, seqw, 0, 4);
+    const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+    int wcap = avail > 4ll * ns * 32 ? pow2_floor(avail / (4ll * ns)) : 0;
+    wcap = std::min(wcap, wmax2);
+    if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2)) {
       Tier t;
-      t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = (int)wcap;
+      t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
       t.seq_words_cap = seqw;
-      t.smem = 4ull * (seqw + (size_t)ns * wcap + meta) + block_reduce_smem_bytes();
+      t.group_bytes = (int)group_bytes_of(k, b->two_p, seqw, wcap, 4);
+      t.smem = (size_t)t.group_bytes + block_reduce_smem_bytes();
       t.hcap = std::min<long long>(8ll << 20, cells_bound);
       t.scap = (int)std::min<long long>(1 << 16, scap_bound);
       b->tiers.push_back(t);
-      last_wcap = (int)wcap;
+      last_wcap = wcap;
     }
   }
   {
     /* widest tier: ring in HBM, history sized at run time from free memory */
     Tier t;
-    t.mode = 2; t.threads = 512; t.groups_per_block = 1; t.wcap = wmax32;
+    t.mode = 2; t.threads = 512; t.groups_per_block = 1; t.wcap = wmax2;
     t.seq_words_cap = (4ll * seqw <= 160 * 1024) ? seqw : 0;
-    t.smem = 4ull * (t.seq_words_cap + meta) + block_reduce_smem_bytes();
+    t.group_bytes = (int)group_bytes_of(k, b->two_p, t.seq_words_cap, 0, 4);
+    t.smem = (size_t)t.group_bytes + block_reduce_smem_bytes();
     t.hcap = cells_bound;
     t.scap = (int)std::min<long long>(2 * scap_bound, INT_MAX / 4);
     b->tiers.push_back(t);
   }
   for (auto& t : b->tiers) {
-    int bps = align_occupancy(b->two_p, b->full, t.mode, t.threads, t.smem);
+    int bps = align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
     t.blocks_per_sm = std::max(1, bps);
   }
 }
@@ -465,12 +486,13 @@ extern "C" int wfagpu_batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, void* stream) 
       blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
       groups = blocks;
     }
-    k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap;
+    k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
     k.hcap = t.hcap; k.scap = t.scap;
+    const size_t elem = t.off16 ? 2 : 4;
     if (t.mode == 2) {
       const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
-      k.gring_ints = (long long)ns * t.wcap;
-      CK(ctx->gring.ensure(4ull * (size_t)k.gring_ints * (size_t)groups));
+      k.gring_elems = (long long)ns * t.wcap;
+      CK(ctx->gring.ensure(4ull * (size_t)k.gring_elems * (size_t)groups));
       k.gring = ctx->gring.as<int>();
     }
     if (b->full) {
@@ -482,11 +504,11 @@ extern "C" int wfagpu_batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, void* stream) 
         const long long per_group = (long long)((double)free_b * 0.8 / 5.0 / (double)groups);
         k.hcap = std::max<long long>(1024, std::min<long long>(t.hcap, per_group));
       }
-      CK(ctx->hist_m0.ensure(4ull * (size_t)k.hcap * (size_t)groups));
+      CK(ctx->hist_m0.ensure(elem * (size_t)k.hcap * (size_t)groups));
       CK(ctx->hist_code.ensure((size_t)k.hcap * (size_t)groups));
       CK(ctx->hmeta.ensure(8ull * (size_t)k.scap * (size_t)groups));
       CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
-      k.hist_m0 = ctx->hist_m0.as<int>(); k.hist_code = ctx->hist_code.as<uint8_t>();
+      k.hist_m0 = ctx->hist_m0.p; k.hist_code = ctx->hist_code.as<uint8_t>();
       k.hmeta = ctx->hmeta.as<int2>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
     }
     k.worklist = cur_list;
@@ -494,7 +516,7 @@ extern "C" int wfagpu_batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, void* stream) 
     k.work_counter = &dc->work[ti];
     k.retry_list = lists[ti & 1];
     k.retry_count = &dc->retry[ti];
-    CK(launch_align(k, b->two_p, b->full, t.mode, blocks, t.threads, t.smem, st));
+    CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
     b->stats.kernel_launches++;
     CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

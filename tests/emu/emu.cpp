@@ -24,15 +24,35 @@ struct EmuGroup {
   template <int N> void allmin(int (&)[N]) {}
 };
 
-template <bool TWO_P, bool FULL>
-static int run_one(const KParams& P, const GroupMem& gm, int plen, int tlen, PairResult& res) {
+struct EmuBuffers {      /* allocated once per batch */
+  std::vector<unsigned char> ring, h_m0;
+  std::vector<int4> meta;
+  std::vector<uint8_t> h_code;
+  std::vector<int2> hmeta;
+};
+
+template <class OffT, bool TWO_P, bool FULL>
+static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t* tw, int plen, int tlen,
+                   std::vector<uint32_t>& stage, PairResult& res) {
+  const int wcap = P.wcap;
+  GroupMem<OffT> gm;
+  gm.pw = pw; gm.tw = tw;
+  gm.ring[CM] = reinterpret_cast<OffT*>(B.ring.data());
+  gm.ring[CI1] = gm.ring[CM] + P.rm * wcap;
+  gm.ring[CD1] = gm.ring[CI1] + P.r1 * wcap;
+  gm.ring[CI2] = gm.ring[CD1] + P.r1 * wcap;
+  gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * wcap : 0);
+  gm.meta = B.meta.data();
+  gm.h_m0 = reinterpret_cast<OffT*>(B.h_m0.data()); gm.h_code = B.h_code.data(); gm.hmeta = B.hmeta.data();
+  gm.runs_stage = stage.data();
   EmuGroup g;
-  return align_pair<EmuGroup, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+  return align_pair<EmuGroup, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
 }
 
+/* off16 != 0 selects the int16 offset rings of the short-read tiers */
 extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
                                const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
-                               int wcap, long long hcap, int scap, int32_t* score, int32_t* status,
+                               int wcap, long long hcap, int scap, int off16, int32_t* score, int32_t* status,
                                int32_t* locs, int64_t* cig_off, uint32_t* runs, int64_t runs_cap,
                                int32_t* overflow, int64_t* cells) {
   KParams P;
@@ -40,12 +60,17 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
   fill_kparams(*cfg, P);
   const bool two_p = cfg->distance == WFAGPU_DISTANCE_AFFINE2P;
   const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
+  if (wcap & (wcap - 1)) return -3;            /* power of two */
   P.wcap = wcap; P.hcap = hcap; P.scap = scap;
-  const int ns = P.rm + 2 * P.r1 + (two_p ? 2 * P.r2 : 0);
-  std::vector<int> ring((size_t)ns * wcap), meta((size_t)P.rm * META_INTS);
-  std::vector<int> h_m0(full ? (size_t)hcap : 1);
-  std::vector<uint8_t> h_code(full ? (size_t)hcap : 1);
-  std::vector<int2> hmeta(full ? (size_t)scap : 1);
+  EmuBuffers B;
+  {
+    const int ns = P.rm + 2 * P.r1 + (two_p ? 2 * P.r2 : 0);
+    B.ring.resize((size_t)ns * wcap * 4);
+    B.meta.resize((size_t)P.mr * 5);
+    B.h_m0.resize(full ? (size_t)hcap * 4 : 4);
+    B.h_code.resize(full ? (size_t)hcap : 1);
+    B.hmeta.resize(full ? (size_t)scap : 1);
+  }
   int64_t used = 0;
   for (int64_t i = 0; i < n; ++i) {
     const int plen = p_len[i], tlen = t_len[i];
@@ -54,20 +79,16 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
     if (!pack_sequence(seq + t_off[i], tlen, tw.data())) return -2;
     std::vector<uint32_t> stage((size_t)plen + tlen + 2);
     P.runcap = (int)stage.size();
-    GroupMem gm;
-    gm.pw = pw.data(); gm.tw = tw.data();
-    gm.ring[CM] = ring.data();
-    gm.ring[CI1] = gm.ring[CM] + P.rm * wcap;
-    gm.ring[CD1] = gm.ring[CI1] + P.r1 * wcap;
-    gm.ring[CI2] = gm.ring[CD1] + P.r1 * wcap;
-    gm.ring[CD2] = gm.ring[CI2] + (two_p ? P.r2 * wcap : 0);
-    gm.meta = meta.data();
-    gm.h_m0 = h_m0.data(); gm.h_code = h_code.data(); gm.hmeta = hmeta.data(); gm.runs_stage = stage.data();
     PairResult res;
     memset(&res, 0, sizeof res);
     int rc;
-    if (two_p) rc = full ? run_one<true, true>(P, gm, plen, tlen, res) : run_one<true, false>(P, gm, plen, tlen, res);
-    else rc = full ? run_one<false, true>(P, gm, plen, tlen, res) : run_one<false, false>(P, gm, plen, tlen, res);
+#define EMU_RUN(T)                                                                                          \
+    (two_p ? (full ? run_one<T, true, true>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)   \
+                   : run_one<T, true, false>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)) \
+           : (full ? run_one<T, false, true>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)  \
+                   : run_one<T, false, false>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)))
+    if (off16) rc = EMU_RUN(int16_t); else rc = EMU_RUN(int32_t);
+#undef EMU_RUN
     cig_off[i] = used;
     overflow[i] = (rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) { score[i] = 0; status[i] = 0; cells[i] = 0; memset(locs + 4 * i, 0, 16); continue; }

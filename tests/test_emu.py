@@ -25,20 +25,20 @@ def emu():
     subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, stdout=subprocess.DEVNULL)
     lib = C.CDLL(os.path.join(HERE, "emu", "libwfaemu.so"))
     lib.emu_align_batch.argtypes = [C.c_void_p, _u8p, _i64p, _i32p, _i64p, _i32p, C.c_int64, C.c_int,
-                                    C.c_longlong, C.c_int, _i32p, _i32p, _i32p, _i64p, _u32p, C.c_int64,
-                                    _i32p, _i64p]
+                                    C.c_longlong, C.c_int, C.c_int, _i32p, _i32p, _i32p, _i64p, _u32p,
+                                    C.c_int64, _i32p, _i64p]
     lib.emu_align_batch.restype = C.c_int
     lib.emu_pack.argtypes = [_u8p, C.c_int, _u32p]
     lib.emu_pack.restype = C.c_int
 
-    def run(cfg, batch, wcap=1 << 15, hcap=1 << 25, scap=1 << 18):
+    def run(cfg, batch, wcap=1 << 15, hcap=1 << 25, scap=1 << 18, off16=0):
         seq, po, pl, to, tl = batch
         n = len(pl)
         out = dict(score=np.zeros(n, np.int32), status=np.zeros(n, np.int32), locs=np.zeros((n, 4), np.int32),
                    cig_off=np.zeros(n + 1, np.int64), ovf=np.zeros(n, np.int32), cells=np.zeros(n, np.int64))
         cap = int(pl.sum() + tl.sum()) + 16
         runs = np.zeros(cap, np.uint32)
-        rc = lib.emu_align_batch(C.addressof(cfg), np.ascontiguousarray(seq), po, pl, to, tl, n, wcap, hcap, scap,
+        rc = lib.emu_align_batch(C.addressof(cfg), np.ascontiguousarray(seq), po, pl, to, tl, n, wcap, hcap, scap, off16,
                                  out["score"], out["status"], out["locs"], out["cig_off"], runs, cap,
                                  out["ovf"], out["cells"])
         assert rc == 0, rc
@@ -61,6 +61,40 @@ def test_device_source_matches_golden(emu, oracle, case):
     assert r["locs"].tolist() == case["locations"]
     if case["config"].get("scope", "full") == "full":
         assert r["cells"].tolist() == case["cells"]
+
+
+@pytest.mark.parametrize("case", [c for c in SYN if c["length"] <= 2000], ids=[c["name"] for c in SYN if c["length"] <= 2000])
+def test_device_source_int16_rings_match_golden(emu, oracle, case):
+    """the short-read tiers keep offsets as int16 (nulls = any negative value)"""
+    batch = generate_pairs(case["n"], case["length"], case["div"], case["seed"], text_flank=case["flank"])
+    cfg = oracle.make_config(**case["config"])
+    r = emu(cfg, batch, wcap=4096, off16=1)
+    assert not r["ovf"].any()
+    assert r["score"].tolist() == case["score"] and r["status"].tolist() == case["status"]
+    cig = [oracle.runs_to_cigarstring(r["runs"][r["cig_off"][j]:r["cig_off"][j + 1]]) for j in range(case["n"])]
+    assert cig == case["cigars"] and r["locs"].tolist() == case["locations"]
+
+
+GCD_CASES = [
+    dict(span="end-to-end", max_steps=11), dict(span="end-to-end", max_steps=12), dict(span="end-to-end", max_steps=37),
+    dict(heuristic="X-drop", xdrop=10, max_steps=13), dict(heuristic="X-drop", xdrop=15, scope="score"),
+    dict(span="end-to-end", mismatch=6, gap_opening=9, gap_extension=3),
+    dict(mismatch=6, gap_opening=9, gap_extension=3, heuristic="X-drop", xdrop=12, max_steps=100),
+    dict(distance="affine2p", gap_extension2=2), dict(span="end-to-end", mismatch=3, gap_opening=1, gap_extension=1),
+]
+
+
+@pytest.mark.parametrize("kw", GCD_CASES, ids=[str(i) for i in range(len(GCD_CASES))])
+def test_score_unit_gcd_edge_cases(emu, oracle, kw):
+    """scores advance in units of gcd(penalties); step limits and the unreachable test are
+    decided in original units (odd max_steps, drops between two multiples of g, ...)"""
+    batch = generate_pairs(300, 150, 0.15, seed=23)
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    for off16 in (0, 1):
+        got = emu(cfg, batch, wcap=512, off16=off16)
+        for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
+            assert np.array_equal(got[k], want[k]), (kw, off16, k)
 
 
 def test_device_source_matches_oracle_ragged(emu, oracle):
