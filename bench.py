@@ -326,19 +326,22 @@ def main():
     # ---- e2e: host buffers -> results, every step ----
     e2e = None
     if not args.no_e2e:
-        ctx.align_batch(cfg, *batch)        # warm the pinned staging buffers
+        for _ in range(2):
+            ctx.align_batch(cfg, *batch, copy_runs=False, check=False)   # warm staging / buffer pools
         sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            ctx.align_batch(cfg, *batch)
+            r = ctx.align_batch(cfg, *batch, copy_runs=False, check=False)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        d2h_e2e = 8 * n_pairs + (16 * n_pairs + 8 * (n_pairs + 1) + 4 * int(r["cig_off"][-1]) if full else 0)
+        e2e_launches = ctx.last_launches()
         if world > 1:
             tdt = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
             dt = float(tdt.item())
         e2e = {"value": world * n_pairs * args.steps / dt, "unit": "pairs/s",
-               "h2d_bytes_per_step": stats["h2d_bytes"], "d2h_bytes_per_step": 8 * n_pairs if not full else stats["d2h_bytes"],
+               "h2d_bytes_per_step": stats["h2d_bytes"], "d2h_bytes_per_step": d2h_e2e, "gpu_launches_per_step": e2e_launches,
                "ms_per_step": 1e3 * dt / args.steps, "timing": "wall clock around wfagpu_align_batch (host pack + H2D + kernels + D2H), max over ranks"}
         log(f"[rank {rank}] e2e: {1e3 * dt / args.steps:.1f} ms/step -> {e2e['value']:,.0f} pairs/s")
     b.free()

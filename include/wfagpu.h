@@ -126,6 +126,10 @@ const char* wfagpu_strerror(int code);
  * (length<<4 | op) words; pair i owns runs [cig_off[i], cig_off[i+1]).
  * cig_off must have n+1 entries.  The memory stays valid until the next
  * align call on this ctx or wfagpu_destroy.
+ *
+ * Large batches are processed in chunks: the calling thread packs chunk c+1
+ * (2 bits per base, all host cores) into pinned staging while a second host
+ * thread drives upload, kernels and download of chunk c.
  */
 int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
                        const uint8_t* seq,
@@ -165,6 +169,8 @@ typedef struct wfagpu_batch_stats {
   int64_t retried_pairs;       /* pairs re-run on a larger tier               */
 } wfagpu_batch_stats_t;
 int wfagpu_batch_get_stats(const wfagpu_batch* b, wfagpu_batch_stats_t* out);
+/* Kernel launches issued by the last wfagpu_align_batch call on this context. */
+int64_t wfagpu_last_launches(const wfagpu_ctx* ctx);
 
 #ifdef __cplusplus
 }

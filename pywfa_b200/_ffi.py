@@ -87,6 +87,8 @@ def lib():
     L.wfagpu_batch_free.restype = None
     L.wfagpu_batch_get_stats.argtypes = [vp, C.POINTER(BatchStats)]
     L.wfagpu_batch_get_stats.restype = C.c_int
+    L.wfagpu_last_launches.argtypes = [vp]
+    L.wfagpu_last_launches.restype = C.c_int64
     _lib = L
     return L
 
@@ -124,7 +126,7 @@ class Context:
             raise WfaGpuError(rc, lib().wfagpu_last_error(self._h).decode())
 
     @staticmethod
-    def _inputs(seq, p_off, p_len, t_off, t_len):
+    def _inputs(seq, p_off, p_len, t_off, t_len, check=True):
         seq = np.ascontiguousarray(seq, np.uint8)
         p_off = np.ascontiguousarray(p_off, np.int64)
         t_off = np.ascontiguousarray(t_off, np.int64)
@@ -133,15 +135,17 @@ class Context:
         n = len(p_len)
         if not (len(p_off) == len(t_off) == len(t_len) == n):
             raise ValueError("offset/length arrays differ in length")
-        if n:
+        if n and check:
             if (p_off < 0).any() or (t_off < 0).any() or int((p_off + p_len).max()) > len(seq) \
                     or int((t_off + t_len).max()) > len(seq):
                 raise ValueError("a pair lies outside the sequence buffer")
         return seq, p_off, p_len, t_off, t_len, n
 
-    def align_batch(self, cfg: Config, seq, p_off, p_len, t_off, t_len):
-        """``wfagpu_align_batch`` on host arrays; returns a dict of numpy arrays."""
-        seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len)
+    def align_batch(self, cfg: Config, seq, p_off, p_len, t_off, t_len, copy_runs=True, check=True):
+        """``wfagpu_align_batch`` on host arrays; returns a dict of numpy arrays.  With
+        ``copy_runs=False`` the CIGAR run array is a view of library-owned pinned memory that
+        stays valid until the next align call on this context."""
+        seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len, check)
         score = np.empty(n, np.int32)
         status = np.empty(n, np.int32)
         locs = np.empty((n, 4), np.int32)
@@ -153,10 +157,15 @@ class Context:
         self._check(rc)
         total = int(cig_off[n])
         if total:
-            runs = np.ctypeslib.as_array(C.cast(runs_p, C.POINTER(C.c_uint32)), shape=(total,)).copy()
+            runs = np.ctypeslib.as_array(C.cast(runs_p, C.POINTER(C.c_uint32)), shape=(total,))
+            if copy_runs:
+                runs = runs.copy()
         else:
             runs = np.zeros(0, np.uint32)
         return dict(score=score, status=status, locs=locs, cig_off=cig_off, runs=runs)
+
+    def last_launches(self) -> int:
+        return int(lib().wfagpu_last_launches(self._h))
 
     def prepare(self, cfg: Config, seq, p_off, p_len, t_off, t_len) -> "Batch":
         seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len)

@@ -239,6 +239,18 @@ class BatchResult:
 _contexts = {}
 
 
+def _run(ctx, *args, **kw):
+    """Map library error codes onto the exception types of the pywfa surface."""
+    try:
+        return ctx.align_batch(*args, **kw)
+    except _ffi.WfaGpuError as e:
+        if e.code == _ffi.EUNSUPPORTED:
+            raise NotImplementedError(str(e)) from None
+        if e.code == _ffi.EINVAL:
+            raise ValueError(str(e)) from None
+        raise
+
+
 def _context(device):
     ctx = _contexts.get(device)
     if ctx is None:
@@ -476,7 +488,7 @@ class WavefrontAligner:
         self.text_len = len(tb)
         self._validate(len(pb), len(tb))
         seq = np.frombuffer(pb + tb + b"\0", np.uint8)
-        r = _context(self._device).align_batch(
+        r = _run(_context(self._device),
             self._cfg, seq, np.array([0], np.int64), np.array([len(pb)], np.int32),
             np.array([len(pb)], np.int64), np.array([len(tb)], np.int32))
         self._score = int(r["score"][0])
@@ -545,7 +557,7 @@ class WavefrontAligner:
         t_len = np.ascontiguousarray(t_len, np.int32)
         if self._cfg.span == 1 and len(p_len):
             self._validate(int(p_len.min()), int(t_len.min()))
-        d = _context(self._device).align_batch(self._cfg, seq, p_off, p_len, t_off, t_len)
+        d = _run(_context(self._device), self._cfg, seq, p_off, p_len, t_off, t_len)
         return BatchResult(d, p_len, t_len)
 
     def align_batch(self, texts, patterns=None) -> BatchResult:

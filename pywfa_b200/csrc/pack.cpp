@@ -14,6 +14,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -50,8 +53,45 @@ bool pack_sequence(const uint8_t* s, int len, uint32_t* out) {
   }
   ok = (_mm256_movemask_epi8(good) == -1);
 #endif
-  uint32_t acc = 0;
-  int nb = 0;
+  /* 8 bases at a time: SWAR validity test + one pext; `cur` collects up to two 16-bit halves */
+  uint32_t cur = 0;
+  int half = 0;
+#if defined(__BMI2__)
+  for (; i + 8 <= len; i += 8) {
+    uint64_t q;
+    memcpy(&q, s + i, 8);
+    const uint64_t u = q & 0xDFDFDFDFDFDFDFDFull;
+    /* per byte: zero iff equal to the letter; OR the four "is non-zero" masks together */
+    auto nz = [](uint64_t v) { return ((v & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | v; };
+    const uint64_t miss = nz(u ^ 0x4141414141414141ull) & nz(u ^ 0x4343434343434343ull) &
+                          nz(u ^ 0x4747474747474747ull) & nz(u ^ 0x5454545454545454ull);
+    ok &= (miss & 0x8080808080808080ull) == 0;
+    cur |= (uint32_t)_pext_u64(q, 0x0606060606060606ull) << (16 * half);
+    if (++half == 2) { out[w++] = cur; cur = 0; half = 0; }
+  }
+#endif
+  uint32_t acc = cur;
+  int nb = 16 * half;       /* bits already in acc */
+#if defined(__BMI2__)
+  if (i < len && len >= 8) {
+    /* last 1..7 bases: re-read the final 8 bytes of the sequence and shift the tail down */
+    const int rem = len - i;
+    uint64_t q;
+    memcpy(&q, s + len - 8, 8);
+    q >>= 8 * (8 - rem);
+    const uint64_t u = q & 0xDFDFDFDFDFDFDFDFull;
+    auto nz = [](uint64_t v) { return ((v & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | v; };
+    const uint64_t miss = nz(u ^ 0x4141414141414141ull) & nz(u ^ 0x4343434343434343ull) &
+                          nz(u ^ 0x4747474747474747ull) & nz(u ^ 0x5454545454545454ull);
+    const uint64_t live = (~0ull) >> (8 * (8 - rem));
+    ok &= (miss & live & 0x8080808080808080ull) == 0;
+    acc |= (uint32_t)_pext_u64(q, 0x0606060606060606ull) << nb;
+    nb += 2 * rem;           /* nb counts bits here */
+    out[w++] = acc;
+    return ok;
+  }
+#endif
+  nb /= 2;                   /* bases */
   for (; i < len; ++i) {
     const uint8_t c = s[i];
     ok &= is_acgt(c);
@@ -72,16 +112,71 @@ int pack_threads(int64_t n_items, int64_t bytes) {
   return (int)std::min<int64_t>(hw, std::max<int64_t>(1, bytes >> 19));
 }
 
+/* A small persistent pool: chunked batches call parallel_for dozens of times per second, so
+ * threads are created once per process instead of once per call. */
+namespace {
+class Pool {
+ public:
+  static Pool& get() { static Pool p; return p; }
+  void run(int nthreads, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> guard(call_mu_);       /* one parallel region at a time */
+    ensure(nthreads - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn; want_ = nthreads - 1; next_ = 0; done_ = 0; ++epoch_;
+    }
+    cv_.notify_all();
+    fn(nthreads - 1);                                  /* the caller works too */
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return done_ == want_; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void ensure(int n) {
+    while ((int)th_.size() < n) th_.emplace_back([this] { loop(); });
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      int idx;
+      const std::function<void(int)>* fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && next_ < want_); });
+        if (stop_) return;
+        idx = next_++;
+        if (next_ >= want_) seen = epoch_;
+        fn = fn_;
+      }
+      (*fn)(idx);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (++done_ == want_) cv_done_.notify_all();
+    }
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_, cv_done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int want_ = 0, next_ = 0, done_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+};
+}  // namespace
+
 template <class F>
 static void parallel_for(int nthreads, int64_t n, F&& fn) {
   if (nthreads <= 1) { fn(0, (int64_t)0, n); return; }
-  std::vector<std::thread> th;
-  th.reserve(nthreads);
-  for (int t = 0; t < nthreads; ++t) {
+  const std::function<void(int)> body = [&](int t) {
     const int64_t a = n * t / nthreads, b = n * (t + 1) / nthreads;
-    th.emplace_back([&fn, t, a, b] { fn(t, a, b); });
-  }
-  for (auto& x : th) x.join();
+    fn(t, a, b);
+  };
+  Pool::get().run(nthreads, body);
 }
 
 int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, PairMetaHost* meta,

@@ -231,7 +231,8 @@ __global__ void cigar_scan_kernel(long long* tile_sums, int ntiles) {
 __global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long long* __restrict__ runs_base,
                                     long long n, const long long* __restrict__ tile_sums,
                                     const uint32_t* __restrict__ runs_tmp,
-                                    long long* __restrict__ cig_off, uint32_t* __restrict__ runs_out) {
+                                    long long* __restrict__ cig_off, uint32_t* __restrict__ runs_out,
+                                    long long cig_base) {
   __shared__ long long wtot[SCAN_THREADS / 32];
   __shared__ long long carry_s;
   const long long t0 = (long long)blockIdx.x * SCAN_TILE;
@@ -251,7 +252,7 @@ __global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long lo
     for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
     const long long excl = carry_s + woff + inc - v;
     if (i < n) {
-      cig_off[i] = excl;
+      cig_off[i] = excl + cig_base;
       const long long src = runs_base[i];
       for (int r = 0; r < v; ++r) runs_out[excl + r] = runs_tmp[src + r];
     }
@@ -259,7 +260,7 @@ __global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long lo
     if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl + v;
     __syncthreads();
   }
-  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cig_off[n] = tile_sums[gridDim.x];
+  if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) cig_off[n] = tile_sums[gridDim.x] + cig_base;
 }
 
 /* ---- launch wrappers (C++ linkage, used by wfagpu_api.cpp) -------------------------- */
@@ -322,13 +323,13 @@ size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }
 
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,
                                long long* tile_sums, const uint32_t* runs_tmp, long long* cig_off,
-                               uint32_t* runs_out, cudaStream_t st) {
+                               uint32_t* runs_out, long long cig_base, cudaStream_t st) {
   const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
   if (runs_out == nullptr) {   /* phase 1: counts + scan (total lands in tile_sums[ntiles]) */
     cigar_count_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nruns, n, tile_sums);
     cigar_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, ntiles);
   } else {
-    cigar_gather_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nruns, runs_base, n, tile_sums, runs_tmp, cig_off, runs_out);
+    cigar_gather_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(nruns, runs_base, n, tile_sums, runs_tmp, cig_off, runs_out, cig_base);
   }
   return cudaGetLastError();
 }

@@ -15,10 +15,10 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
 size_t block_reduce_smem_bytes();
 
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
- * last one); otherwise gather into cig_off[n+1] / runs_out. */
+ * last one); otherwise gather into cig_off[n+1] (values offset by cig_base) / runs_out. */
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,
                                long long* tile_sums, const uint32_t* runs_tmp, long long* cig_off,
-                               uint32_t* runs_out, cudaStream_t st);
+                               uint32_t* runs_out, long long cig_base, cudaStream_t st);
 int cigar_order_tiles(long long n);
 
 }  // namespace wfagpu

@@ -11,9 +11,14 @@
 #include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -65,6 +70,8 @@ struct DevCounters {       /* one per batch, in HBM */
   unsigned long long cells_total;
 };
 
+struct Staging { PinBuf words, meta; };
+
 struct Tier {
   int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
   int threads = 128;
@@ -84,11 +91,16 @@ struct Tier {
 struct wfagpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   /* uploads of the next chunk overlap the kernels of this one */
+  cudaEvent_t uploaded[2] = {nullptr, nullptr};
   int sms = 0;
   int smem_optin = 0;
   std::string err;
-  /* pinned staging (grow-only) */
-  PinBuf pin_words, pin_meta, pin_runs, pin_small;
+  /* pinned staging (grow-only): two slots so that packing overlaps the GPU */
+  Staging staging[2];
+  PinBuf pin_runs, pin_small;
+  std::vector<wfagpu_batch*> spare;
+  int64_t last_launches = 0;
   /* per-run scratch shared by all batches of this context (grow-only) */
   DevBuf hist_m0, hist_code, hmeta, runs_stage, gring;
 };
@@ -103,13 +115,17 @@ struct wfagpu_batch {
   std::vector<Tier> tiers;
   DevBuf pairs, words, score, status, locs, nruns, runs_base, runs_tmp, retry_a, retry_b, counters,
       cig_off, tile_sums, runs_out;
-  unsigned long long runs_tmp_cap = 0;
+  unsigned long long runs_tmp_cap = 0, runs_bound = 0;
+  int64_t seq_bytes = 0;
   long long total_runs = 0;
+  long long cig_base = 0;       /* added to this batch's cig_off values (chunked calls) */
   bool ran = false;
   wfagpu_batch_stats_t stats;
 };
 
 namespace {
+
+void batch_release(wfagpu_batch* b);
 
 int fail(wfagpu_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -320,7 +336,10 @@ extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t err
   ctx->device = device;
   cudaDeviceProp prop;
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
-      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->uploaded[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->uploaded[1], cudaEventDisableTiming)) != cudaSuccess) {
     set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
     delete ctx;
     return WFAGPU_ECUDA;
@@ -341,104 +360,121 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ctx->pin_words.release(); ctx->pin_meta.release(); ctx->pin_runs.release(); ctx->pin_small.release();
+  for (auto& sg : ctx->staging) { sg.words.release(); sg.meta.release(); }
+  ctx->pin_runs.release(); ctx->pin_small.release();
+  for (wfagpu_batch* b : ctx->spare) batch_release(b);
+  ctx->spare.clear();
   ctx->hist_m0.release(); ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
   cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  cudaEventDestroy(ctx->uploaded[0]); cudaEventDestroy(ctx->uploaded[1]);
   delete ctx;
 }
 
 extern "C" const char* wfagpu_last_error(const wfagpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static bool trace_on() {
+  static const bool t = getenv("WFAGPU_TRACE") != nullptr;
+  return t;
+}
+
 /* ---- batches ------------------------------------------------------------------------- */
-extern "C" void wfagpu_batch_free(wfagpu_ctx* ctx, wfagpu_batch* b) {
-  if (!b) return;
-  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+namespace {
+
+void batch_release(wfagpu_batch* b) {
   for (DevBuf* d : {&b->pairs, &b->words, &b->score, &b->status, &b->locs, &b->nruns, &b->runs_base, &b->runs_tmp,
                     &b->retry_a, &b->retry_b, &b->counters, &b->cig_off, &b->tile_sums, &b->runs_out})
     d->release();
   delete b;
 }
 
-extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq,
-                                    const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
-                                    const int32_t* t_len, int64_t n, wfagpu_batch** out) {
-  if (!ctx || !cfg || !out || n < 0 || (n > 0 && (!seq || !p_off || !p_len || !t_off || !t_len)))
-    return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_prepare");
-  *out = nullptr;
-  if (n > INT_MAX / 2) return fail(ctx, WFAGPU_EINVAL, "at most %d pairs per batch", INT_MAX / 2);
-  char msg[400];
-  int rc = wfagpu_config_check(cfg, -1, -1, msg, sizeof msg);
-  if (rc != WFAGPU_OK) return fail(ctx, rc, "%s", msg);
-  CK(cudaSetDevice(ctx->device));
-  wfagpu_batch* b = new wfagpu_batch();
+/* batch shells keep their device buffers (grow-only) and are recycled through the context */
+wfagpu_batch* batch_acquire(wfagpu_ctx* ctx) {
+  wfagpu_batch* b;
+  if (!ctx->spare.empty()) { b = ctx->spare.back(); ctx->spare.pop_back(); }
+  else b = new wfagpu_batch();
+  b->tiers.clear();
+  b->ran = false; b->total_runs = 0; b->runs_tmp_cap = 0;
+  memset(&b->stats, 0, sizeof b->stats);
+  memset(&b->kp, 0, sizeof b->kp);
+  return b;
+}
+void batch_recycle(wfagpu_ctx* ctx, wfagpu_batch* b) {
+  if (ctx && ctx->spare.size() < 4) ctx->spare.push_back(b);
+  else batch_release(b);
+}
+
+/* host stage: checks, word layout and 2-bit packing into pinned staging (no CUDA stream work) */
+int batch_pack(wfagpu_ctx* ctx, wfagpu_batch* b, Staging& sg, const wfagpu_config_t* cfg, const uint8_t* seq,
+               const int64_t* p_off, const int32_t* p_len, const int64_t* t_off, const int32_t* t_len,
+               int64_t n, int64_t first_pair) {
   b->cfg = *cfg; b->n = n;
   b->two_p = cfg->distance == WFAGPU_DISTANCE_AFFINE2P;
   b->full = cfg->scope == WFAGPU_SCOPE_FULL;
-  memset(&b->stats, 0, sizeof b->stats);
-  memset(&b->kp, 0, sizeof b->kp);
   b->stats.n_pairs = n;
-#define CKB(call)                                                                           \
-  do {                                                                                      \
-    cudaError_t e_ = (call);                                                                \
-    if (e_ != cudaSuccess) {                                                                \
-      wfagpu_batch_free(ctx, b);                                                            \
-      return fail(ctx, e_ == cudaErrorMemoryAllocation ? WFAGPU_ENOMEM : WFAGPU_ECUDA,      \
-                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    }                                                                                       \
-  } while (0)
-  /* layout + per-pair checks */
-  CKB(ctx->pin_meta.ensure(sizeof(PairMetaHost) * (size_t)std::max<int64_t>(n, 1)));
-  PairMetaHost* meta = ctx->pin_meta.as<PairMetaHost>();
+  char msg[400];
+  CK(sg.meta.ensure(sizeof(PairMetaHost) * (size_t)std::max<int64_t>(n, 1)));
+  PairMetaHost* meta = sg.meta.as<PairMetaHost>();
   int64_t seq_bytes = 0;
   for (int64_t i = 0; i < n; ++i) {
-    if (p_len[i] < 0 || t_len[i] < 0) { wfagpu_batch_free(ctx, b); return fail(ctx, WFAGPU_EINVAL, "negative length at pair %lld", (long long)i); }
+    if (p_len[i] < 0 || t_len[i] < 0) return fail(ctx, WFAGPU_EINVAL, "negative length at pair %lld", (long long)(first_pair + i));
     seq_bytes += (int64_t)p_len[i] + t_len[i];
   }
+  b->seq_bytes = seq_bytes;
   if (cfg->span == WFAGPU_SPAN_ENDSFREE &&
       (cfg->pattern_begin_free | cfg->pattern_end_free | cfg->text_begin_free | cfg->text_end_free)) {
     for (int64_t i = 0; i < n; ++i) {
-      rc = wfagpu_config_check(cfg, p_len[i], t_len[i], msg, sizeof msg);
-      if (rc != WFAGPU_OK) { wfagpu_batch_free(ctx, b); return fail(ctx, rc, "pair %lld: %s", (long long)i, msg); }
+      const int rc = wfagpu_config_check(cfg, p_len[i], t_len[i], msg, sizeof msg);
+      if (rc != WFAGPU_OK) return fail(ctx, rc, "pair %lld: %s", (long long)(first_pair + i), msg);
     }
   }
   b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt);
-  if ((long long)b->maxp + b->maxt > (1ll << 27)) { wfagpu_batch_free(ctx, b); return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases"); }
-  CKB(ctx->pin_words.ensure(4 * (size_t)(b->total_words + 1)));
-  uint32_t* words = ctx->pin_words.as<uint32_t>();
+  if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
+  CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
+  uint32_t* words = sg.words.as<uint32_t>();
   const int64_t bad = pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes);
-  if (bad >= 0) {
-    wfagpu_batch_free(ctx, b);
-    return fail(ctx, WFAGPU_EUNSUPPORTED, "pair %lld holds a base other than A/C/G/T: the 2-bit accelerated path cannot represent it", (long long)bad);
-  }
+  if (bad >= 0)
+    return fail(ctx, WFAGPU_EUNSUPPORTED, "pair %lld holds a base other than A/C/G/T: the 2-bit accelerated path cannot represent it",
+                (long long)(first_pair + bad));
   words[b->total_words] = 0;
-  /* upload */
-  CKB(b->pairs.ensure(sizeof(PairMetaHost) * (size_t)std::max<int64_t>(n, 1)));
-  CKB(b->words.ensure(4 * (size_t)(b->total_words + 1)));
-  CKB(cudaMemcpyAsync(b->pairs.p, meta, sizeof(PairMetaHost) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  CKB(cudaMemcpyAsync(b->words.p, words, 4 * (size_t)(b->total_words + 1), cudaMemcpyHostToDevice, ctx->stream));
+  return WFAGPU_OK;
+}
+
+/* device stage: buffers, H2D (async on st), kernel parameters, tier plan */
+int batch_upload(wfagpu_ctx* ctx, wfagpu_batch* b, const Staging& sg, cudaStream_t st) {
+  const int64_t n = b->n;
+  const size_t n1 = (size_t)std::max<int64_t>(n, 1);
+  CK(b->pairs.ensure(sizeof(PairMetaHost) * n1));
+  CK(b->words.ensure(4 * (size_t)(b->total_words + 1)));
+  CK(cudaMemcpyAsync(b->pairs.p, sg.meta.p, sizeof(PairMetaHost) * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(b->words.p, sg.words.p, 4 * (size_t)(b->total_words + 1), cudaMemcpyHostToDevice, st));
   b->stats.packed_bytes = 4 * b->total_words;
   b->stats.h2d_bytes = (int64_t)(sizeof(PairMetaHost) * (size_t)n + 4 * (size_t)(b->total_words + 1));
-  /* results */
-  const size_t n1 = (size_t)std::max<int64_t>(n, 1);
-  CKB(b->score.ensure(4 * n1));
-  CKB(b->status.ensure(4 * n1));
-  CKB(b->retry_a.ensure(4 * n1));
-  CKB(b->retry_b.ensure(4 * n1));
-  CKB(b->counters.ensure(sizeof(DevCounters)));
+  CK(b->score.ensure(4 * n1));
+  CK(b->status.ensure(4 * n1));
+  CK(b->retry_a.ensure(4 * n1));
+  CK(b->retry_b.ensure(4 * n1));
+  CK(b->counters.ensure(sizeof(DevCounters)));
   if (b->full) {
-    CKB(b->locs.ensure(16 * n1));
-    CKB(b->nruns.ensure(4 * n1));
-    CKB(b->runs_base.ensure(8 * n1));
-    CKB(b->cig_off.ensure(8 * (n1 + 1)));
-    CKB(b->tile_sums.ensure(8 * (size_t)(cigar_order_tiles(n) + 2)));
-    unsigned long long cap = (unsigned long long)seq_bytes + 2ull * (unsigned long long)n;
-    cap = std::min<unsigned long long>(cap, 4ull << 30);      /* 16 GiB of run words at most */
-    CKB(b->runs_tmp.ensure(4 * (size_t)std::max<unsigned long long>(cap, 1)));
+    CK(b->locs.ensure(16 * n1));
+    CK(b->nruns.ensure(4 * n1));
+    CK(b->runs_base.ensure(8 * n1));
+    CK(b->cig_off.ensure(8 * (n1 + 1)));
+    CK(b->tile_sums.ensure(8 * (size_t)(cigar_order_tiles(n) + 2)));
+    /* staging for the un-ordered runs: sized for typical CIGARs, regrown (and the batch re-run)
+     * in wfagpu_batch_run if a batch needs more; the hard bound is one run per base */
+    const unsigned long long bound = (unsigned long long)b->seq_bytes + 2ull * (unsigned long long)n;
+    unsigned long long cap = std::max<unsigned long long>(b->runs_tmp.cap / 4, std::min<unsigned long long>(bound, 40ull * n + 4096));
+    cap = std::min(cap, bound);
+    CK(b->runs_tmp.ensure(4 * (size_t)std::max<unsigned long long>(cap, 1)));
     b->runs_tmp_cap = cap;
+    b->runs_bound = bound;
   }
-  /* kernel parameters */
   KParams& k = b->kp;
-  fill_kparams(*cfg, k);
+  fill_kparams(b->cfg, k);
   k.pairs = b->pairs.as<PairMeta>();
   k.words = b->words.as<uint32_t>();
   k.score = b->score.as<int>(); k.status = b->status.as<int>();
@@ -449,8 +485,180 @@ extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
   k.runs_cursor = &dc->runs_cursor;
   k.cells_total = &dc->cells_total;
   plan_tiers(ctx, b);
-  CKB(cudaStreamSynchronize(ctx->stream));   /* pinned staging is reusable after this */
-#undef CKB
+  return WFAGPU_OK;
+}
+
+/* kernels of one batch on stream st; blocks the calling host thread between tiers */
+int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc) {
+  DevCounters* dc = b->counters.as<DevCounters>();
+  b->stats.kernel_launches = 0;
+  b->stats.retried_pairs = 0;
+  b->stats.history_bytes = 0;
+  b->total_runs = 0;
+  if (b->n == 0) { b->ran = true; return WFAGPU_OK; }
+  for (int attempt = 0;; ++attempt) {
+    memset(hc, 0, sizeof *hc);
+    hc->nwork0 = (int)b->n;
+    CK(cudaMemcpyAsync(dc, hc, sizeof *hc, cudaMemcpyHostToDevice, st));
+    long long nwork = b->n;
+    int* lists[2] = {b->retry_a.as<int>(), b->retry_b.as<int>()};
+    const int* cur_list = nullptr;
+    int last_tier = -1;
+    for (size_t ti = 0; ti < b->tiers.size() && nwork > 0; ++ti) {
+      Tier t = b->tiers[ti];
+      KParams k = b->kp;
+      long long groups;
+      int blocks;
+      if (t.mode == 0) {
+        blocks = (int)std::min<long long>((nwork + t.groups_per_block - 1) / t.groups_per_block, (long long)ctx->sms * t.blocks_per_sm);
+        groups = (long long)blocks * t.groups_per_block;
+      } else {
+        blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
+        groups = blocks;
+      }
+      k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
+      k.hcap = t.hcap; k.scap = t.scap;
+      const size_t elem = t.off16 ? 2 : 4;
+      if (t.mode == 2) {
+        const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+        k.gring_elems = (long long)ns * t.wcap;
+        CK(ctx->gring.ensure(4ull * (size_t)k.gring_elems * (size_t)groups));
+        k.gring = ctx->gring.as<int>();
+      }
+      if (b->full) {
+        if (t.mode == 2) {
+          /* history arena of the widest tier: what is free now, split over the groups */
+          size_t free_b = 0, total_b = 0;
+          CK(cudaMemGetInfo(&free_b, &total_b));
+          free_b += ctx->hist_m0.cap + ctx->hist_code.cap;
+          const long long per_group = (long long)((double)free_b * 0.8 / 5.0 / (double)groups);
+          k.hcap = std::max<long long>(1024, std::min<long long>(t.hcap, per_group));
+        }
+        CK(ctx->hist_m0.ensure(elem * (size_t)k.hcap * (size_t)groups));
+        CK(ctx->hist_code.ensure((size_t)k.hcap * (size_t)groups));
+        CK(ctx->hmeta.ensure(8ull * (size_t)k.scap * (size_t)groups));
+        CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
+        k.hist_m0 = ctx->hist_m0.p; k.hist_code = ctx->hist_code.as<uint8_t>();
+        k.hmeta = ctx->hmeta.as<int2>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
+        b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)((elem + 1) * (size_t)k.hcap * (size_t)groups));
+      }
+      k.worklist = cur_list;
+      k.n_work = (last_tier < 0) ? &dc->nwork0 : &dc->retry[last_tier];
+      k.work_counter = &dc->work[ti];
+      k.retry_list = lists[ti & 1];
+      k.retry_count = &dc->retry[ti];
+      CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
+      b->stats.kernel_launches++;
+      CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      nwork = hc->retry[ti];
+      if (ti == 0) b->stats.retried_pairs = nwork;
+      cur_list = lists[ti & 1];
+      last_tier = (int)ti;
+    }
+    b->stats.cells = (int64_t)hc->cells_total;
+    if (b->full && hc->runs_cursor > b->runs_tmp_cap && b->runs_tmp_cap < b->runs_bound && attempt == 0) {
+      /* CIGARs longer than the staging estimate: regrow to what this batch asked for and redo it */
+      const unsigned long long cap = std::min<unsigned long long>(b->runs_bound, hc->runs_cursor + hc->runs_cursor / 8 + 4096);
+      CK(b->runs_tmp.ensure(4 * (size_t)cap));
+      b->runs_tmp_cap = cap;
+      b->kp.runs_tmp = b->runs_tmp.as<uint32_t>(); b->kp.runs_tmp_cap = cap;
+      continue;
+    }
+    if (nwork > 0) {
+      /* capacity exhausted even on the widest tier: WF_STATUS_OOM (W/wavefront/wfa.h:50) */
+      std::vector<int> ids((size_t)nwork);
+      CK(cudaMemcpyAsync(ids.data(), cur_list, 4 * (size_t)nwork, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      const int oom = WFAGPU_STATUS_OOM, sc = INT_MIN, zero = 0;
+      for (int id : ids) {
+        CK(cudaMemcpyAsync(b->score.as<int>() + id, &sc, 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->status.as<int>() + id, &oom, 4, cudaMemcpyHostToDevice, st));
+        if (b->full) {
+          CK(cudaMemcpyAsync(b->nruns.as<int>() + id, &zero, 4, cudaMemcpyHostToDevice, st));
+          CK(cudaMemsetAsync(b->locs.as<int>() + 4 * (size_t)id, 0, 16, st));
+        }
+      }
+      CK(cudaStreamSynchronize(st));
+    }
+    break;
+  }
+  if (b->full) {
+    b->total_runs = (long long)std::min<unsigned long long>(hc->runs_cursor, b->runs_tmp_cap);
+    CK(b->runs_out.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
+    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
+                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), nullptr, 0, st));
+    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
+                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), b->runs_out.as<uint32_t>(), b->cig_base, st));
+    b->stats.kernel_launches += 3;
+  }
+  b->ran = true;
+  return WFAGPU_OK;
+}
+
+/* download into host arrays; runs go to runs_dst (pinned, library-owned) */
+int batch_download(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, int32_t* score, int32_t* status, int32_t* locs,
+                   int64_t* cig_off, bool last_offset, uint32_t* runs_dst) {
+  const size_t n = (size_t)b->n;
+  int64_t d2h = 0;
+  if (n) {
+    if (score) { CK(cudaMemcpyAsync(score, b->score.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
+    if (status) { CK(cudaMemcpyAsync(status, b->status.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
+  }
+  if (b->full && n) {
+    if (locs) { CK(cudaMemcpyAsync(locs, b->locs.p, 16 * n, cudaMemcpyDeviceToHost, st)); d2h += 16 * n; }
+    if (cig_off) {
+      const size_t cnt = n + (last_offset ? 1 : 0);
+      CK(cudaMemcpyAsync(cig_off, b->cig_off.p, 8 * cnt, cudaMemcpyDeviceToHost, st)); d2h += 8 * cnt;
+    }
+    if (runs_dst && b->total_runs) {
+      CK(cudaMemcpyAsync(runs_dst, b->runs_out.p, 4 * (size_t)b->total_runs, cudaMemcpyDeviceToHost, st));
+      d2h += 4 * b->total_runs;
+    }
+  } else {
+    if (locs && n) memset(locs, 0, 16 * n);
+    if (cig_off) for (size_t i = 0; i < n + (last_offset ? 1 : 0); ++i) cig_off[i] = b->cig_base;
+  }
+  CK(cudaStreamSynchronize(st));
+  b->stats.d2h_bytes = d2h;
+  return WFAGPU_OK;
+}
+
+int check_args(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
+               const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n) {
+  if (!ctx || !cfg || n < 0 || (n > 0 && (!seq || !p_off || !p_len || !t_off || !t_len)))
+    return fail(ctx, WFAGPU_EINVAL, "bad arguments");
+  if (n > INT_MAX / 2) return fail(ctx, WFAGPU_EINVAL, "at most %d pairs per batch", INT_MAX / 2);
+  char msg[400];
+  const int rc = wfagpu_config_check(cfg, -1, -1, msg, sizeof msg);
+  if (rc != WFAGPU_OK) return fail(ctx, rc, "%s", msg);
+  return WFAGPU_OK;
+}
+
+}  // namespace
+
+extern "C" void wfagpu_batch_free(wfagpu_ctx* ctx, wfagpu_batch* b) {
+  if (!b) return;
+  if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  batch_recycle(ctx, b);
+}
+
+extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq,
+                                    const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
+                                    const int32_t* t_len, int64_t n, wfagpu_batch** out) {
+  if (!out) return fail(ctx, WFAGPU_EINVAL, "bad arguments");
+  *out = nullptr;
+  int rc = check_args(ctx, cfg, seq, p_off, p_len, t_off, t_len, n);
+  if (rc != WFAGPU_OK) return rc;
+  CK(cudaSetDevice(ctx->device));
+  wfagpu_batch* b = batch_acquire(ctx);
+  const double t0 = now_ms();
+  rc = batch_pack(ctx, b, ctx->staging[0], cfg, seq, p_off, p_len, t_off, t_len, n, 0);
+  const double t1 = now_ms();
+  if (rc == WFAGPU_OK) rc = batch_upload(ctx, b, ctx->staging[0], ctx->stream);
+  if (rc == WFAGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, WFAGPU_ECUDA, "upload failed");
+  if (trace_on()) fprintf(stderr, "[wfagpu]   prepare n=%lld: pack %.2f ms, upload+plan %.2f ms\n", (long long)n, t1 - t0, now_ms() - t1);
+  if (rc != WFAGPU_OK) { batch_recycle(ctx, b); return rc; }
   *out = b;
   return WFAGPU_OK;
 }
@@ -458,101 +666,9 @@ extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
 extern "C" int wfagpu_batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, void* stream) {
   if (!ctx || !b) return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_run");
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  DevCounters* dc = b->counters.as<DevCounters>();
-  b->stats.kernel_launches = 0;
-  b->stats.retried_pairs = 0;
-  b->stats.history_bytes = 0;
-  b->total_runs = 0;
-  if (b->n == 0) { b->ran = true; return WFAGPU_OK; }
-  CK(ctx->pin_small.ensure(256));
-  DevCounters* hc = ctx->pin_small.as<DevCounters>();
-  memset(hc, 0, sizeof *hc);
-  hc->nwork0 = (int)b->n;
-  CK(cudaMemcpyAsync(dc, hc, sizeof *hc, cudaMemcpyHostToDevice, st));
-  long long nwork = b->n;
-  int* lists[2] = {b->retry_a.as<int>(), b->retry_b.as<int>()};
-  const int* cur_list = nullptr;
-  int last_tier = -1;
-  for (size_t ti = 0; ti < b->tiers.size() && nwork > 0; ++ti) {
-    Tier t = b->tiers[ti];
-    KParams k = b->kp;
-    long long groups;
-    int blocks;
-    if (t.mode == 0) {
-      blocks = (int)std::min<long long>((nwork + t.groups_per_block - 1) / t.groups_per_block, (long long)ctx->sms * t.blocks_per_sm);
-      groups = (long long)blocks * t.groups_per_block;
-    } else {
-      blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
-      groups = blocks;
-    }
-    k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
-    k.hcap = t.hcap; k.scap = t.scap;
-    const size_t elem = t.off16 ? 2 : 4;
-    if (t.mode == 2) {
-      const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
-      k.gring_elems = (long long)ns * t.wcap;
-      CK(ctx->gring.ensure(4ull * (size_t)k.gring_elems * (size_t)groups));
-      k.gring = ctx->gring.as<int>();
-    }
-    if (b->full) {
-      if (t.mode == 2) {
-        /* history arena of the widest tier: what is free now, split over the groups */
-        size_t free_b = 0, total_b = 0;
-        CK(cudaMemGetInfo(&free_b, &total_b));
-        free_b += ctx->hist_m0.cap + ctx->hist_code.cap;
-        const long long per_group = (long long)((double)free_b * 0.8 / 5.0 / (double)groups);
-        k.hcap = std::max<long long>(1024, std::min<long long>(t.hcap, per_group));
-      }
-      CK(ctx->hist_m0.ensure(elem * (size_t)k.hcap * (size_t)groups));
-      CK(ctx->hist_code.ensure((size_t)k.hcap * (size_t)groups));
-      CK(ctx->hmeta.ensure(8ull * (size_t)k.scap * (size_t)groups));
-      CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
-      k.hist_m0 = ctx->hist_m0.p; k.hist_code = ctx->hist_code.as<uint8_t>();
-      k.hmeta = ctx->hmeta.as<int2>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
-    }
-    k.worklist = cur_list;
-    k.n_work = (ti == 0 || last_tier < 0) ? &dc->nwork0 : &dc->retry[last_tier];
-    k.work_counter = &dc->work[ti];
-    k.retry_list = lists[ti & 1];
-    k.retry_count = &dc->retry[ti];
-    CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
-    b->stats.kernel_launches++;
-    CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    nwork = hc->retry[ti];
-    if (ti == 0) b->stats.retried_pairs = nwork;
-    cur_list = lists[ti & 1];
-    last_tier = (int)ti;
-  }
-  b->stats.cells = (int64_t)hc->cells_total;
-  if (nwork > 0) {
-    /* capacity exhausted even on the widest tier: WF_STATUS_OOM (W/wavefront/wfa.h:50) */
-    std::vector<int> ids((size_t)nwork);
-    CK(cudaMemcpyAsync(ids.data(), cur_list, 4 * (size_t)nwork, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const int oom = WFAGPU_STATUS_OOM, sc = INT_MIN, zero = 0;
-    for (int id : ids) {
-      CK(cudaMemcpyAsync(b->score.as<int>() + id, &sc, 4, cudaMemcpyHostToDevice, st));
-      CK(cudaMemcpyAsync(b->status.as<int>() + id, &oom, 4, cudaMemcpyHostToDevice, st));
-      if (b->full) {
-        CK(cudaMemcpyAsync(b->nruns.as<int>() + id, &zero, 4, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(b->locs.as<int>() + 4 * (size_t)id, 0, 16, st));
-      }
-    }
-    CK(cudaStreamSynchronize(st));
-  }
-  if (b->full) {
-    b->total_runs = (long long)std::min<unsigned long long>(hc->runs_cursor, b->runs_tmp_cap);
-    CK(b->runs_out.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
-    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
-                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), nullptr, st));
-    CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
-                          b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), b->runs_out.as<uint32_t>(), st));
-    b->stats.kernel_launches += 3;
-  }
-  b->ran = true;
-  return WFAGPU_OK;
+  CK(ctx->pin_small.ensure(512));
+  b->cig_base = 0;
+  return batch_run(ctx, b, stream ? (cudaStream_t)stream : ctx->stream, ctx->pin_small.as<DevCounters>());
 }
 
 extern "C" int wfagpu_batch_fetch(wfagpu_ctx* ctx, wfagpu_batch* b, int32_t* score, int32_t* status, int32_t* locs,
@@ -560,32 +676,14 @@ extern "C" int wfagpu_batch_fetch(wfagpu_ctx* ctx, wfagpu_batch* b, int32_t* sco
   if (!ctx || !b) return fail(ctx, WFAGPU_EINVAL, "bad arguments to wfagpu_batch_fetch");
   if (!b->ran) return fail(ctx, WFAGPU_EINVAL, "wfagpu_batch_fetch before wfagpu_batch_run");
   CK(cudaSetDevice(ctx->device));
-  cudaStream_t st = ctx->stream;
   CK(cudaDeviceSynchronize());
-  const size_t n = (size_t)b->n;
-  int64_t d2h = 0;
-  if (cig_runs) *cig_runs = nullptr;
-  if (n) {
-    if (score) { CK(cudaMemcpyAsync(score, b->score.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
-    if (status) { CK(cudaMemcpyAsync(status, b->status.p, 4 * n, cudaMemcpyDeviceToHost, st)); d2h += 4 * n; }
+  uint32_t* runs_dst = nullptr;
+  if (cig_runs) {
+    CK(ctx->pin_runs.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
+    runs_dst = ctx->pin_runs.as<uint32_t>();
+    *cig_runs = runs_dst;
   }
-  if (b->full && n) {
-    if (locs) { CK(cudaMemcpyAsync(locs, b->locs.p, 16 * n, cudaMemcpyDeviceToHost, st)); d2h += 16 * n; }
-    if (cig_off) { CK(cudaMemcpyAsync(cig_off, b->cig_off.p, 8 * (n + 1), cudaMemcpyDeviceToHost, st)); d2h += 8 * (n + 1); }
-    if (cig_runs) {
-      CK(ctx->pin_runs.ensure(4 * (size_t)std::max<long long>(b->total_runs, 1)));
-      if (b->total_runs) CK(cudaMemcpyAsync(ctx->pin_runs.p, b->runs_out.p, 4 * (size_t)b->total_runs, cudaMemcpyDeviceToHost, st));
-      d2h += 4 * b->total_runs;
-      *cig_runs = ctx->pin_runs.as<uint32_t>();
-    }
-  } else {
-    if (locs && n) memset(locs, 0, 16 * n);
-    if (cig_off) memset(cig_off, 0, 8 * (n + 1));
-    if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->pin_runs.as<uint32_t>(); }
-  }
-  CK(cudaStreamSynchronize(st));
-  b->stats.d2h_bytes = d2h;
-  return WFAGPU_OK;
+  return batch_download(ctx, b, ctx->stream, score, status, locs, cig_off, true, runs_dst);
 }
 
 extern "C" int wfagpu_batch_get_stats(const wfagpu_batch* b, wfagpu_batch_stats_t* out) {
@@ -594,15 +692,132 @@ extern "C" int wfagpu_batch_get_stats(const wfagpu_batch* b, wfagpu_batch_stats_
   return WFAGPU_OK;
 }
 
+/*
+ * The one-call path.  Large batches are cut into chunks and pipelined: the calling thread packs
+ * chunk c+1 into pinned staging (all host cores) while a second host thread drives upload,
+ * kernels and download of chunk c.  Results land directly in the caller's arrays.
+ */
 extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq,
                                   const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
                                   const int32_t* t_len, int64_t n, int32_t* score, int32_t* status,
                                   int32_t* locs, int64_t* cig_off, const uint32_t** cig_runs) {
-  wfagpu_batch* b = nullptr;
-  int rc = wfagpu_batch_prepare(ctx, cfg, seq, p_off, p_len, t_off, t_len, n, &b);
+  int rc = check_args(ctx, cfg, seq, p_off, p_len, t_off, t_len, n);
   if (rc != WFAGPU_OK) return rc;
-  rc = wfagpu_batch_run(ctx, b, nullptr);
-  if (rc == WFAGPU_OK) rc = wfagpu_batch_fetch(ctx, b, score, status, locs, cig_off, cig_runs);
-  wfagpu_batch_free(ctx, b);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->pin_small.ensure(512));
+  if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->pin_runs.as<uint32_t>(); }
+  const double t_start = now_ms();
+  /* chunking: enough chunks to overlap packing with the GPU, big enough to fill it */
+  int64_t chunk = n;
+  {
+    const char* e = getenv("WFAGPU_CHUNK");
+    const int64_t want = e ? atoll(e) : 0;
+    if (want > 0) chunk = want;
+    else if (n >= 262144) chunk = std::max<int64_t>(131072, (n + 7) / 8);
+  }
+  const int64_t nchunks = n == 0 ? 1 : (n + chunk - 1) / chunk;
+  wfagpu_batch* shells[2] = {batch_acquire(ctx), nchunks > 1 ? batch_acquire(ctx) : nullptr};
+  std::mutex mu;
+  std::condition_variable cv;
+  int64_t packed = 0, consumed = 0;     /* chunks packed by the producer / finished by the GPU thread */
+  int err = WFAGPU_OK;
+  long long run_base = 0;
+  int64_t launches = 0;
+  double gpu_busy = 0, t_run = 0, t_down = 0;
+
+  auto upload_side = [&](int64_t c) -> int {     /* runs on the packing thread */
+    const int r = batch_upload(ctx, shells[c & 1], ctx->staging[c & 1], ctx->copy_stream);
+    if (r != WFAGPU_OK) return r;
+    CK(cudaEventRecord(ctx->uploaded[c & 1], ctx->copy_stream));
+    return WFAGPU_OK;
+  };
+  auto gpu_side = [&](int64_t c) -> int {
+    wfagpu_batch* b = shells[c & 1];
+    const int64_t off = c * chunk;
+    int r;
+    const double g0 = now_ms();
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[c & 1], 0));
+    b->cig_base = run_base;
+    r = batch_run(ctx, b, ctx->stream, ctx->pin_small.as<DevCounters>());
+    if (r != WFAGPU_OK) return r;
+    const double g1 = now_ms();
+    uint32_t* runs_dst = nullptr;
+    if (cig_runs && b->full) {
+      const size_t need = 4 * (size_t)(run_base + std::max<long long>(b->total_runs, 1));
+      if (need > ctx->pin_runs.cap) {
+        /* grow the library-owned run buffer, keeping what earlier chunks wrote */
+        PinBuf bigger;
+        const size_t remaining = (size_t)(nchunks - c);
+        CK(bigger.ensure(std::max(need, 4 * (size_t)run_base + 4 * (size_t)b->total_runs * remaining)));
+        if (run_base) memcpy(bigger.p, ctx->pin_runs.p, 4 * (size_t)run_base);
+        ctx->pin_runs.release();
+        ctx->pin_runs = bigger;
+      }
+      runs_dst = ctx->pin_runs.as<uint32_t>() + run_base;
+    }
+    r = batch_download(ctx, b, ctx->stream, score ? score + off : nullptr, status ? status + off : nullptr,
+                       locs ? locs + 4 * off : nullptr, cig_off ? cig_off + off : nullptr, c == nchunks - 1, runs_dst);
+    if (r != WFAGPU_OK) return r;
+    if (b->full) run_base += b->total_runs;
+    launches += b->stats.kernel_launches;
+    t_run += g1 - g0; t_down += now_ms() - g1;
+    return WFAGPU_OK;
+  };
+
+  if (nchunks == 1) {
+    rc = batch_pack(ctx, shells[0], ctx->staging[0], cfg, seq, p_off, p_len, t_off, t_len, n, 0);
+    const double t1 = now_ms();
+    if (rc == WFAGPU_OK) rc = upload_side(0);
+    if (rc == WFAGPU_OK) rc = gpu_side(0);
+    if (trace_on()) fprintf(stderr, "[wfagpu] n=%lld single chunk: pack %.2f ms, gpu side %.2f ms\n", (long long)n, t1 - t_start, now_ms() - t1);
+  } else {
+    std::thread gpu_thread([&] {
+      cudaSetDevice(ctx->device);
+      for (int64_t c = 0; c < nchunks; ++c) {
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return packed > c || err != WFAGPU_OK; });
+          if (err != WFAGPU_OK) return;
+        }
+        const double t0 = now_ms();
+        const int r = gpu_side(c);
+        gpu_busy += now_ms() - t0;
+        std::lock_guard<std::mutex> lk(mu);
+        if (r != WFAGPU_OK) err = r;
+        consumed = c + 1;
+        cv.notify_all();
+        if (r != WFAGPU_OK) return;
+      }
+    });
+    double pack_ms = 0;
+    for (int64_t c = 0; c < nchunks; ++c) {
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return consumed + 2 > c || err != WFAGPU_OK; });   /* staging slot c&1 is free */
+        if (err != WFAGPU_OK) break;
+      }
+      const int64_t off = c * chunk, m = std::min(chunk, n - off);
+      const double t0 = now_ms();
+      int r = batch_pack(ctx, shells[c & 1], ctx->staging[c & 1], cfg, seq, p_off + off, p_len + off,
+                         t_off + off, t_len + off, m, off);
+      if (r == WFAGPU_OK) r = upload_side(c);
+      pack_ms += now_ms() - t0;
+      std::lock_guard<std::mutex> lk(mu);
+      if (r != WFAGPU_OK) { err = r; cv.notify_all(); break; }
+      packed = c + 1;
+      cv.notify_all();
+    }
+    gpu_thread.join();
+    rc = err;
+    if (trace_on())
+      fprintf(stderr, "[wfagpu] n=%lld in %lld chunks: total %.2f ms (pack+upload %.2f ms on the caller; gpu side %.2f ms = kernels %.2f + download %.2f)\n",
+              (long long)n, (long long)nchunks, now_ms() - t_start, pack_ms, gpu_busy, t_run, t_down);
+  }
+  if (cig_runs) *cig_runs = ctx->pin_runs.as<uint32_t>();
+  ctx->last_launches = launches;
+  batch_recycle(ctx, shells[0]);
+  if (shells[1]) batch_recycle(ctx, shells[1]);
   return rc;
 }
+
+extern "C" int64_t wfagpu_last_launches(const wfagpu_ctx* ctx) { return ctx ? ctx->last_launches : 0; }

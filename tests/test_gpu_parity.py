@@ -84,3 +84,48 @@ def test_reference_agrees_when_present(gpu_ctx, oracle):
     want = oracle.align_batch(cfg, *batch, kind="reference")
     got = gpu_ctx.align_batch(cfg, *batch)
     assert_same(got, want, what="reference cfg1")
+
+
+def test_chunked_pipeline_equals_single_call(gpu_ctx, oracle, monkeypatch):
+    """wfagpu_align_batch cuts large batches into chunks (pack of chunk c+1 overlaps the GPU work
+    of chunk c); the concatenated result must equal the oracle's, incl. CIGAR offsets."""
+    batch = generate_pairs(30000, 150, 0.06, seed=77)
+    for kw in (dict(span="end-to-end"), dict(scope="score", span="end-to-end")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        for chunk in ("7000", "4096", "29999"):
+            monkeypatch.setenv("WFAGPU_CHUNK", chunk)
+            got = gpu_ctx.align_batch(cfg, *batch)
+            assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"chunk={chunk} {kw}")
+    monkeypatch.delenv("WFAGPU_CHUNK")
+
+
+def test_python_api_single_and_batch(gpu_ctx):
+    """WavefrontAligner: the reference's own known-answer tests (pywfa/tests/test.py) through the
+    pywfa-compatible Python surface, single calls and the batched entry point."""
+    import json
+    import os
+
+    import pywfa_b200
+    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kat.json")))
+    for case in kat:
+        a = pywfa_b200.WavefrontAligner(**case["ctor"])
+        res = a(case["text"], case["pattern"], **case["call"])
+        e = case["expect"]
+        assert (res.score, res.status, res.cigarstring) == (e["score"], e["status"], e["cigarstring"]), case["name"]
+        assert [res.pattern_start, res.pattern_end, res.text_start, res.text_end] == e["locations"], case["name"]
+        assert (a.score, a.status, a.cigarstring) == (e["aligner_score"], e["aligner_status"], e["aligner_cigarstring"])
+        try:
+            ap, at = res.aligned_pattern, res.aligned_text
+            same = (ap == at) if ap is not None else None
+        except Exception:
+            same = None
+        assert same == e["aligned_equal"], case["name"]
+    # batched entry point on the README pair + friends
+    a = pywfa_b200.WavefrontAligner("TCTTTACTCGCGCGTTGGAGAAATACAATAGT")
+    br = a.align_batch(["TCTATACTGCGCGTTTGGAGAAATAAAATAGT", "TCTTTACTCGCGCGTTGGAGAAATACAATAGT", "tctttactcg"])
+    assert br.score.tolist()[:2] == [-24, 0] and br.cigarstring(0) == "3M1X4M1D7M1I9M1X6M" and br.cigarstring(1) == "32M"
+    r0 = br.result(0)
+    assert (r0.pattern_start, r0.pattern_end, r0.text_start, r0.text_end) == (0, 32, 0, 32)
+    with pytest.raises(NotImplementedError):
+        a.align_batch(["ACGTNNNN"])
