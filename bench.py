@@ -89,7 +89,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True); self.t.start()
         except Exception:
@@ -97,7 +97,11 @@ class ClockSampler:
 
     def _pump(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def mark(self):
+        """Start of the window whose samples count (the timed region)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -108,7 +112,9 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], 0, set()
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < getattr(self, "t_mark", 0.0):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -296,12 +302,13 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()              # nvidia-smi needs ~0.2 s before its first line: start it early
     for _ in range(max(args.warmup, 3)):
         b.run(stream)
     sync_all()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -309,7 +316,18 @@ def main():
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        if not any(ts >= sampler.t_mark for ts, _ in sampler.lines):
+            # timed region shorter than one nvidia-smi period: sample an identical untimed replay
+            t_end = time.perf_counter() + 0.6
+            while time.perf_counter() < t_end:
+                b.run(stream)
+                torch.cuda.synchronize()
+            clocks = sampler.stop()
+            clocks["note"] = "timed region < 50 ms: clocks sampled over an identical untimed replay right after it"
+        else:
+            clocks = sampler.stop()
     if world > 1:
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)

@@ -266,17 +266,20 @@ __global__ void cigar_gather_kernel(const int* __restrict__ nruns, const long lo
 /* ---- launch wrappers (C++ linkage, used by wfagpu_api.cpp) -------------------------- */
 template <bool TWO_P, bool FULL, int MODE, class OffT>
 static cudaError_t launch_one(const KParams& P, int grid, int block, size_t smem, cudaStream_t st) {
-  auto kern = wfa_align_kernel<TWO_P, FULL, MODE, OffT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, block, smem, st>>>(P);
+  /* the dynamic shared-memory limit was raised once per device by init_kernels() */
+  wfa_align_kernel<TWO_P, FULL, MODE, OffT><<<grid, block, smem, st>>>(P);
   return cudaGetLastError();
+}
+
+template <bool TWO_P, bool FULL, int MODE, class OffT>
+static cudaError_t init_one(int smem_optin) {
+  return cudaFuncSetAttribute(wfa_align_kernel<TWO_P, FULL, MODE, OffT>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
 }
 
 template <bool TWO_P, bool FULL, int MODE, class OffT>
 static int occupancy_one(int block, size_t smem) {
   auto kern = wfa_align_kernel<TWO_P, FULL, MODE, OffT>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, block, smem) != cudaSuccess) return 0;
   return nb;
@@ -317,6 +320,23 @@ cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool
 
 int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size_t smem) {
   WFA_DISPATCH(occupancy_one, block, smem);
+}
+
+/* Raise the dynamic shared-memory limit of every instantiation on the CURRENT device, once, at
+ * context creation: the attribute is per function and device, and changing it per launch would
+ * race between the packing thread (occupancy queries) and the launching thread. */
+static cudaError_t init_dispatch(bool two_p, bool full, int mode, bool off16, int smem_optin) {
+  WFA_DISPATCH(init_one, smem_optin);
+}
+cudaError_t init_kernels(int smem_optin) {
+  for (int two_p = 0; two_p < 2; ++two_p)
+    for (int full = 0; full < 2; ++full)
+      for (int mode = 0; mode < 3; ++mode)
+        for (int off16 = 0; off16 < (mode == 0 ? 2 : 1); ++off16) {
+          const cudaError_t e = init_dispatch(two_p, full, mode, off16, smem_optin);
+          if (e != cudaSuccess) return e;
+        }
+  return cudaSuccess;
 }
 
 size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }

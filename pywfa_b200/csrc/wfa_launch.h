@@ -11,6 +11,7 @@ struct KParams;
 /* mode 0: warp-per-pair (smem ring), 1: block-per-pair (smem ring), 2: block-per-pair (HBM ring) */
 cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool off16, int grid, int block,
                          size_t smem, cudaStream_t st);
+cudaError_t init_kernels(int smem_optin);   /* once per device, at context creation */
 int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size_t smem);
 size_t block_reduce_smem_bytes();
 

@@ -352,6 +352,12 @@ extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t err
   }
   ctx->sms = prop.multiProcessorCount;
   ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = init_kernels(ctx->smem_optin)) != cudaSuccess) {
+    set_err(err, errlen, "kernel setup failed: %s", cudaGetErrorString(e));
+    cudaStreamDestroy(ctx->stream); cudaStreamDestroy(ctx->copy_stream);
+    delete ctx;
+    return WFAGPU_ECUDA;
+  }
   *out = ctx;
   return WFAGPU_OK;
 }
