@@ -1,0 +1,88 @@
+/*
+ * lanevec.cuh -- the per-lane value types and warp primitives the register-resident wavefront
+ * tier (wfa_reg.cuh) is written against.
+ *
+ * On the device a `vi`/`vu`/`vb` is simply the calling thread's int / uint32_t / bool and every
+ * primitive is one sm_100a instruction: VIMNMX.S16x2 / VIMNMX3.S16x2 / VIADD.16x2 (the DPX
+ * packed-halfword integer ops), PRMT, SHFL, VOTE, LDS.  tests/emu/ supplies a 32-lane host
+ * model of the same names (test infrastructure; the warp code is then executed lane-vector by
+ * lane-vector on the CPU by the CPU test-suite), which is why wfa_reg.cuh contains no
+ * per-lane control flow: every branch is warp-uniform, lanes differ only through selects.
+ */
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(WFA_LANEVEC_HOST)
+
+namespace wfagpu {
+namespace lv {
+
+typedef int vi;
+typedef uint32_t vu;
+typedef bool vb;
+
+__device__ __forceinline__ vi lane_id() { return (int)(threadIdx.x & 31); }
+
+/* ---- packed s16x2 (DPX) ---- */
+__device__ __forceinline__ vu vimax2(vu a, vu b) { return __vmaxs2(a, b); }
+__device__ __forceinline__ vu vimax3(vu a, vu b, vu c) { return __vimax3_s16x2(a, b, c); }
+__device__ __forceinline__ vu vadd2(vu a, vu b) { return __vadd2(a, b); }
+/* max with "a >= b" predicates per half */
+__device__ __forceinline__ vu vimax2p(vu a, vu b, vb& hi, vb& lo) { return __vibmax_s16x2(a, b, &hi, &lo); }
+/* 0xFFFF in every half whose sign bit is set (PRMT with sign replication) */
+/* (inline PTX: __byte_perm masks the selector to 3 bits per nibble and loses the replication flag) */
+__device__ __forceinline__ vu signmask2(vu a) {
+  vu d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(0u), "r"(0xbb99u));
+  return d;
+}
+__device__ __forceinline__ vu bitsel(vu mask, vu a, vu b) { return (a & mask) | (b & ~mask); }
+__device__ __forceinline__ vu prmt(vu a, vu b, vu sel) { return __byte_perm(a, b, sel); }
+__device__ __forceinline__ vi sx_lo(vu a) { return (int)(short)(a & 0xffffu); }
+__device__ __forceinline__ vi sx_hi(vu a) { return ((int)a) >> 16; }
+__device__ __forceinline__ vu pack2(vi lo, vi hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+
+/* ---- lane exchange ---- */
+__device__ __forceinline__ vu from_prev_lane(vu a) { return __shfl_sync(0xffffffffu, a, (threadIdx.x + 31) & 31); }
+__device__ __forceinline__ vu from_next_lane(vu a) { return __shfl_sync(0xffffffffu, a, (threadIdx.x + 1) & 31); }
+__device__ __forceinline__ int lane_value(vi a, int lane) { return __shfl_sync(0xffffffffu, a, lane); }
+__device__ __forceinline__ uint32_t ballot(vb p) { return __ballot_sync(0xffffffffu, p); }
+__device__ __forceinline__ bool any(vb p) { return __any_sync(0xffffffffu, p); }
+
+/* ---- per-lane integer helpers ---- */
+__device__ __forceinline__ vi vsel(vb p, vi a, vi b) { return p ? a : b; }
+__device__ __forceinline__ vu vselu(vb p, vu a, vu b) { return p ? a : b; }
+__device__ __forceinline__ vi vmin(vi a, vi b) { return a < b ? a : b; }
+__device__ __forceinline__ vi vmax(vi a, vi b) { return a > b ? a : b; }
+__device__ __forceinline__ vi vffs0(vu x) { return __ffs((int)x) - 1; }
+__device__ __forceinline__ vu vfunnel_r(vu lo, vu hi, vi sh) { return __funnelshift_r(lo, hi, sh); }
+__device__ __forceinline__ vi as_vi(vu a) { return (int)a; }
+__device__ __forceinline__ vu as_vu(vi a) { return (uint32_t)a; }
+__device__ __forceinline__ vb vnot(vb a) { return !a; }
+__device__ __forceinline__ vb vfalse() { return false; }
+__device__ __forceinline__ vu splat(uint32_t x) { return x; }
+__device__ __forceinline__ vi splati(int x) { return x; }
+
+__device__ __forceinline__ vi vclz(vu x) { return __clz((int)x); }
+__device__ __forceinline__ vu vbrev(vu x) { return __brev(x); }
+
+/* ---- memory ---- */
+/* a window array in shared memory: its 32-bit shared-window address */
+typedef uint32_t seqref;
+__device__ __forceinline__ seqref make_seqref(const uint32_t* smem_ptr) { return (uint32_t)__cvta_generic_to_shared(smem_ptr); }
+/* predicated LDS: lanes with p == false read nothing and get 0 (no branch, no reconvergence) */
+__device__ __forceinline__ vu load_win(seqref base, vi idx, vb p) {
+  vu r;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, 0;\n\t@q ld.shared.u32 %0, [%1];\n\t}"
+               : "=r"(r) : "r"(base + 4u * (uint32_t)idx), "r"((uint32_t)p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void scatter_u32(uint32_t* base, vi idx, vu val, vb p) { if (p) base[idx] = val; }
+/* word gather from (shared) memory; lanes with p == false read nothing and get 0 */
+__device__ __forceinline__ vu gather_u32(const uint32_t* base, vi idx, vb p) { return p ? base[idx] : 0u; }
+__device__ __forceinline__ void scatter_u8(uint8_t* base, vi idx, vi val, vb p) { if (p) base[idx] = (uint8_t)val; }
+
+}  // namespace lv
+}  // namespace wfagpu
+
+#endif

@@ -43,6 +43,7 @@ namespace wfagpu {
 
 constexpr int OFFNULL = INT32_MIN / 2;      /* W/wavefront/wavefront_offset.h:44 */
 constexpr int KNONE = INT_MAX;
+constexpr int REG_MAX_LEN = 8000;            /* register tier (wfa_reg.cuh): longest sequence its int16 offsets are sized for */
 
 enum { CM = 0, CI1 = 1, CD1 = 2, CI2 = 3, CD2 = 4 };
 /* backtrace_type priorities, W/wavefront/wavefront_backtrace.c:49-59 */
@@ -108,6 +109,9 @@ struct KParams {
   /* global ring arena for the widest tier (elements per group = gring_elems) */
   int* gring; long long gring_elems;
   unsigned long long* cells_total;
+  /* register-resident tier (wfa_reg.cuh): per-warp origin-byte arena and edit-operation stack */
+  uint8_t* rhist; long long rhist_bytes; int rhrows;
+  uint8_t* rops; int ropcap;
 };
 
 /* pointers a group works with for the current pair */
@@ -130,12 +134,14 @@ struct PairResult {
 #ifdef __CUDACC__
 WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }
 WFA_DEV int first_set(uint32_t x) { return __ffs((int)x) - 1; }
+WFA_DEV int last_set(uint32_t x) { return 31 - __clz((int)x); }
 #else
 WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
   const uint64_t v = ((uint64_t)hi << 32) | lo;
   return (uint32_t)(v >> (sh & 31));
 }
 WFA_DEV int first_set(uint32_t x) { return __builtin_ctz(x); }
+WFA_DEV int last_set(uint32_t x) { return 31 - __builtin_clz(x); }
 #endif
 WFA_DEV int imax(int a, int b) { return a > b ? a : b; }
 WFA_DEV int imin(int a, int b) { return a < b ? a : b; }

@@ -18,6 +18,7 @@
 #include <type_traits>
 
 #include "wfa_core.cuh"
+#include "wfa_reg.cuh"
 #include "wfa_launch.h"
 
 namespace wfagpu {
@@ -177,6 +178,78 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
   if (g.rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
 }
 
+/* ---- the register-resident tier (wfa_reg.cuh): warp-per-pair, wavefronts in registers ---- */
+/* shared memory of one warp: the sequence windows of the pair (seq_words_cap words, one per base + 2) */
+template <int P, int DX, int DOE, bool FULL>
+__global__ void __launch_bounds__(128) wfa_reg_kernel(const __grid_constant__ KParams K) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp_id = blockIdx.x * (blockDim.x >> 5) + wib;
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wib * K.seq_words_cap;
+
+  RegParams R;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
+  R.hrows = K.rhrows; R.opcap = K.ropcap; R.runcap = K.runcap;
+  uint8_t* const hist = FULL ? K.rhist + (long long)warp_id * K.rhist_bytes : nullptr;
+  uint8_t* const ops = FULL ? K.rops + (long long)warp_id * K.ropcap : nullptr;
+  uint32_t* const stage = FULL ? K.runs_stage + (long long)warp_id * K.runcap : nullptr;
+
+  const int n_work = *K.n_work;
+  long long cells_acc = 0;
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(K.work_counter, 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= n_work) break;
+    const int pid = K.worklist ? K.worklist[w] : w;
+    const PairMeta pm = K.pairs[pid];
+    const int plen = pm.plen, tlen = pm.tlen;
+    const int pwn = (plen + 15) >> 4;
+    int rc = PAIR_OVERFLOW;
+    PairResult res;
+    if (plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN) {
+      /* packed words in HBM (the batch buffer carries one pad word) -> per-base windows in smem */
+      const uint32_t* gp = K.words + pm.woff;
+      const uint32_t* gt = gp + pwn;
+      uint32_t* sp = sm_seq; uint32_t* st = sm_seq + plen + 1;
+      build_windows(gp, plen, sp);
+      build_windows(gt, tlen, st);
+      __syncwarp();
+      rc = align_pair_reg<P, DX, DOE, FULL>(R, gp, gt, lv::make_seqref(sp), lv::make_seqref(st), plen, tlen, hist, ops,
+                                            stage, lane == 0, res);
+    }
+    if (rc == PAIR_OVERFLOW) {
+      if (lane == 0) { const int idx = atomicAdd(K.retry_count, 1); K.retry_list[idx] = pid; }
+    } else {
+      cells_acc += res.cells;
+      if (FULL) {
+        int nr = __shfl_sync(0xffffffffu, res.nruns, 0);
+        long long rbase = 0;
+        int stt = res.status;
+        if (nr > 0) {
+          if (lane == 0) rbase = (long long)atomicAdd(K.runs_cursor, (unsigned long long)nr);
+          rbase = __shfl_sync(0xffffffffu, rbase, 0);
+          if (nr > K.runcap || (unsigned long long)(rbase + nr) > K.runs_tmp_cap) { stt = ST_OOM; nr = 0; }
+          __syncwarp();
+          for (int i = lane; i < nr; i += 32) K.runs_tmp[rbase + i] = stage[i];
+        } else if (nr < 0) { stt = ST_OOM; nr = 0; }
+        if (lane == 0) {
+          K.score[pid] = res.score; K.status[pid] = stt;
+          int4 l = make_int4(res.locs[0], res.locs[1], res.locs[2], res.locs[3]);
+          if (nr == 0) l = make_int4(0, 0, 0, 0);
+          reinterpret_cast<int4*>(K.locs)[pid] = l;
+          K.nruns[pid] = nr; K.runs_base[pid] = rbase;
+        }
+      } else if (lane == 0) {
+        K.score[pid] = res.score; K.status[pid] = res.status;
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0 && cells_acc) atomicAdd(K.cells_total, (unsigned long long)cells_acc);
+}
+
 /* ---- CIGAR ordering ------------------------------------------------------------------ */
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
@@ -322,6 +395,50 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
   WFA_DISPATCH(occupancy_one, block, smem);
 }
 
+/* register tier: instantiated for the penalty shapes (x, o+e, e)/gcd = (2, 4, 1) -- pywfa's
+ * default 4/6/2 -- and windows of 128 / 256 diagonals */
+#define WFA_REG_DISPATCH(STMT)                                  \
+  do {                                                          \
+    if (regs == 2) {                                            \
+      if (full) { STMT(2, 2, 4, true); } else { STMT(2, 2, 4, false); } \
+    } else {                                                    \
+      if (full) { STMT(4, 2, 4, true); } else { STMT(4, 2, 4, false); } \
+    }                                                           \
+  } while (0)
+
+bool reg_tier_supported(int dx, int doe, int de, int regs) {
+  return dx == 2 && doe == 4 && de == 1 && (regs == 2 || regs == 4);
+}
+
+cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st) {
+#define WFA_REG_LAUNCH(PP, DX, DOE, FULL) wfa_reg_kernel<PP, DX, DOE, FULL><<<grid, block, smem, st>>>(P)
+  WFA_REG_DISPATCH(WFA_REG_LAUNCH);
+#undef WFA_REG_LAUNCH
+  return cudaGetLastError();
+}
+
+int reg_occupancy(int regs, bool full, int block, size_t smem) {
+  int nb = 0;
+#define WFA_REG_OCC(PP, DX, DOE, FULL) \
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfa_reg_kernel<PP, DX, DOE, FULL>, block, smem) != cudaSuccess) nb = 0
+  WFA_REG_DISPATCH(WFA_REG_OCC);
+#undef WFA_REG_OCC
+  return nb;
+}
+
+static cudaError_t init_reg(int smem_optin) {
+  cudaError_t e = cudaSuccess;
+  for (int regs = 2; regs <= 4; regs += 2)
+    for (int full = 0; full < 2; ++full) {
+#define WFA_REG_INIT(PP, DX, DOE, FULL) \
+  e = cudaFuncSetAttribute(wfa_reg_kernel<PP, DX, DOE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)
+      WFA_REG_DISPATCH(WFA_REG_INIT);
+#undef WFA_REG_INIT
+      if (e != cudaSuccess) return e;
+    }
+  return e;
+}
+
 /* Raise the dynamic shared-memory limit of every instantiation on the CURRENT device, once, at
  * context creation: the attribute is per function and device, and changing it per launch would
  * race between the packing thread (occupancy queries) and the launching thread. */
@@ -336,7 +453,7 @@ cudaError_t init_kernels(int smem_optin) {
           const cudaError_t e = init_dispatch(two_p, full, mode, off16, smem_optin);
           if (e != cudaSuccess) return e;
         }
-  return cudaSuccess;
+  return init_reg(smem_optin);
 }
 
 size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }

@@ -15,6 +15,11 @@ cudaError_t init_kernels(int smem_optin);   /* once per device, at context creat
 int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size_t smem);
 size_t block_reduce_smem_bytes();
 
+/* register-resident tier (wfa_reg.cuh): regs = packed registers per wavefront (window 64*regs) */
+bool reg_tier_supported(int dx, int doe, int de, int regs);
+cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st);
+int reg_occupancy(int regs, bool full, int block, size_t smem);
+
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
  * last one); otherwise gather into cig_off[n+1] (values offset by cig_base) / runs_out. */
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,

@@ -61,9 +61,10 @@ struct PinBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+constexpr int MAX_TIERS = 8;
 struct DevCounters {       /* one per batch, in HBM */
-  int work[4];
-  int retry[4];
+  int work[MAX_TIERS];
+  int retry[MAX_TIERS];
   int nwork0;
   int pad;
   unsigned long long runs_cursor;
@@ -73,6 +74,7 @@ struct DevCounters {       /* one per batch, in HBM */
 struct Staging { PinBuf words, meta; };
 
 struct Tier {
+  int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
   int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
   int threads = 128;
   int groups_per_block = 4;
@@ -102,7 +104,7 @@ struct wfagpu_ctx {
   std::vector<wfagpu_batch*> spare;
   int64_t last_launches = 0;
   /* per-run scratch shared by all batches of this context (grow-only) */
-  DevBuf hist_m0, hist_code, hmeta, runs_stage, gring;
+  DevBuf hist_m0, hist_code, hmeta, runs_stage, gring, rhist, rops;
 };
 
 struct wfagpu_batch {
@@ -181,6 +183,20 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const int smem_max = ctx->smem_optin;
   /* int16 rings hold offsets up to ~tlen + width and nulls that drift by one per step */
   const bool short_reads = 2ll * ((long long)b->maxp + b->maxt) + 4096 < 30000;
+  /* register-resident tiers first: gap-affine, no heuristic, instantiated penalty shape, short reads */
+  static const bool no_reg = getenv("WFAGPU_NO_REG_TIER") != nullptr;     /* debugging aid */
+  const int winw = b->maxp + b->maxt + 2;       /* sequence windows: one word per base */
+  if (!no_reg && !b->two_p && k.heuristic == 0 && std::max(b->maxp, b->maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
+    const int first = std::max(b->maxp, b->maxt) <= 192 ? 2 : 4;
+    for (int regs = first; regs <= 4; regs += 2) {
+      if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs)) continue;
+      Tier t;
+      t.regs = regs; t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = 64 * regs;
+      t.seq_words_cap = winw; t.group_bytes = 4 * winw; t.smem = (size_t)t.group_bytes * 4;
+      t.scap = 32 * regs + k.doe1 + 1;          /* origin rows: scores the window can hold */
+      b->tiers.push_back(t);
+    }
+  }
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
     wcap = std::min(wcap, wmax2);
@@ -231,7 +247,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     b->tiers.push_back(t);
   }
   for (auto& t : b->tiers) {
-    int bps = align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
+    int bps = t.regs ? reg_occupancy(t.regs, b->full, t.threads, t.smem)
+                     : align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
     t.blocks_per_sm = std::max(1, bps);
   }
 }
@@ -371,6 +388,7 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   for (wfagpu_batch* b : ctx->spare) batch_release(b);
   ctx->spare.clear();
   ctx->hist_m0.release(); ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
+  ctx->rhist.release(); ctx->rops.release();
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaEventDestroy(ctx->uploaded[0]); cudaEventDestroy(ctx->uploaded[1]);
@@ -525,13 +543,24 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
       k.hcap = t.hcap; k.scap = t.scap;
       const size_t elem = t.off16 ? 2 : 4;
-      if (t.mode == 2) {
+      if (t.regs) {
+        if (b->full) {
+          k.rhrows = t.scap; k.rhist_bytes = (long long)t.scap * 64 * t.regs;
+          k.ropcap = (int)(((long long)b->maxp + b->maxt + 8 + 15) & ~15ll);
+          CK(ctx->rhist.ensure((size_t)k.rhist_bytes * (size_t)groups));
+          CK(ctx->rops.ensure((size_t)k.ropcap * (size_t)groups));
+          CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
+          k.rhist = ctx->rhist.as<uint8_t>(); k.rops = ctx->rops.as<uint8_t>();
+          k.runs_stage = ctx->runs_stage.as<uint32_t>();
+          b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)k.rhist_bytes * groups);
+        }
+      } else if (t.mode == 2) {
         const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
         k.gring_elems = (long long)ns * t.wcap;
         CK(ctx->gring.ensure(4ull * (size_t)k.gring_elems * (size_t)groups));
         k.gring = ctx->gring.as<int>();
       }
-      if (b->full) {
+      if (b->full && !t.regs) {
         if (t.mode == 2) {
           /* history arena of the widest tier: what is free now, split over the groups */
           size_t free_b = 0, total_b = 0;
@@ -553,7 +582,8 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.work_counter = &dc->work[ti];
       k.retry_list = lists[ti & 1];
       k.retry_count = &dc->retry[ti];
-      CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
+      if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
+      else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
       b->stats.kernel_launches++;
       CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));

@@ -1,0 +1,76 @@
+/*
+ * emu_reg.cpp -- TEST INFRASTRUCTURE ONLY (tests/).  Runs the warp code of the register-resident
+ * tier (pywfa_b200/csrc/wfa_reg.cuh) on the CPU through the 32-lane host model lanevec_host.h,
+ * so that `pytest -m "not gpu"` can compare it with the oracle.  Never linked into the product.
+ */
+#include "lanevec_host.h"
+
+#include <cuda_runtime.h>   /* int2 / int4 types only; nothing is linked */
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/wfagpu.h"
+#include "../../pywfa_b200/csrc/pack.h"
+#include "../../pywfa_b200/csrc/wfa_params.h"
+#include "../../pywfa_b200/csrc/wfa_reg.cuh"
+
+using namespace wfagpu;
+
+template <int P, int DX, int DOE>
+static int run_pair(bool full, const RegParams& R, const uint32_t* pw, const uint32_t* tw, int plen, int tlen,
+                    uint8_t* hist, uint8_t* ops, uint32_t* stage, PairResult& res) {
+  std::vector<uint32_t> pwin((size_t)plen + 1), twin((size_t)tlen + 1);
+  build_windows(pw, plen, pwin.data());
+  build_windows(tw, tlen, twin.data());
+  if (full) return align_pair_reg<P, DX, DOE, true>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, hist, ops, stage, true, res);
+  return align_pair_reg<P, DX, DOE, false>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, hist, ops, stage, true, res);
+}
+
+/* regs = packed registers per wavefront (window = 64 * regs diagonals); hrows = origin rows */
+extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
+                                   const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
+                                   int regs, int hrows, int32_t* score, int32_t* status, int32_t* locs,
+                                   int64_t* cig_off, uint32_t* runs, int64_t runs_cap, int32_t* overflow,
+                                   int64_t* cells) {
+  KParams K;
+  memset(&K, 0, sizeof K);
+  fill_kparams(*cfg, K);
+  if (cfg->distance != WFAGPU_DISTANCE_AFFINE || cfg->heuristic != WFAGPU_HEURISTIC_NONE) return -4;
+  if (!(K.dx == 2 && K.doe1 == 4 && K.de1 == 1)) return -4;
+  const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
+  RegParams R;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
+  R.hrows = hrows;
+  std::vector<uint8_t> hist((size_t)hrows * 64 * regs + 64);
+  int64_t used = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int plen = p_len[i], tlen = t_len[i];
+    std::vector<uint32_t> pw((plen + 15) / 16 + 1, 0), tw((tlen + 15) / 16 + 1, 0);
+    if (!pack_sequence(seq + p_off[i], plen, pw.data())) return -2;
+    if (!pack_sequence(seq + t_off[i], tlen, tw.data())) return -2;
+    std::vector<uint32_t> stage((size_t)plen + tlen + 2);
+    std::vector<uint8_t> ops((size_t)plen + tlen + 8);
+    R.runcap = (int)stage.size(); R.opcap = (int)ops.size();
+    PairResult res;
+    memset(&res, 0, sizeof res);
+    int rc;
+    if (plen > REG_MAX_LEN || tlen > REG_MAX_LEN) rc = PAIR_OVERFLOW;
+    else if (regs == 1) rc = run_pair<1, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
+    else if (regs == 2) rc = run_pair<2, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
+    else if (regs == 4) rc = run_pair<4, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
+    else return -3;
+    cig_off[i] = used;
+    overflow[i] = (rc == PAIR_OVERFLOW);
+    if (rc == PAIR_OVERFLOW) { score[i] = 0; status[i] = 0; cells[i] = 0; memset(locs + 4 * i, 0, 16); continue; }
+    score[i] = res.score; status[i] = res.status; cells[i] = res.cells;
+    memcpy(locs + 4 * i, res.locs, 16);
+    if (res.nruns < 0 || used + res.nruns > runs_cap) return -1;
+    for (int r = 0; r < res.nruns; ++r) runs[used + r] = stage[r];
+    used += res.nruns;
+  }
+  cig_off[n] = used;
+  return 0;
+}

@@ -1,0 +1,116 @@
+"""CPU check of the register-resident tier: pywfa_b200/csrc/wfa_reg.cuh (the warp code the GPU
+runs for short reads) executed on the 32-lane host model tests/emu/lanevec_host.h must reproduce
+the oracle bit-exactly -- score, status, CIGAR runs, coordinates and the wavefront cell count --
+or report a window overflow (the pair is then retried on a wider tier), never a wrong answer."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from pywfa_b200.synth import generate_pairs, pairs_from_strings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+
+
+@pytest.fixture(scope="module")
+def emu_reg():
+    subprocess.run(["make", "-C", os.path.join(HERE, "emu")], check=True, stdout=subprocess.DEVNULL)
+    lib = C.CDLL(os.path.join(HERE, "emu", "libwfaemu_reg.so"))
+    lib.emu_reg_align_batch.argtypes = [C.c_void_p, _u8p, _i64p, _i32p, _i64p, _i32p, C.c_int64, C.c_int, C.c_int,
+                                        _i32p, _i32p, _i32p, _i64p, _u32p, C.c_int64, _i32p, _i64p]
+    lib.emu_reg_align_batch.restype = C.c_int
+
+    def run(cfg, batch, regs, hrows=None):
+        seq, po, pl, to, tl = batch
+        n = len(pl)
+        out = dict(score=np.zeros(n, np.int32), status=np.zeros(n, np.int32), locs=np.zeros((n, 4), np.int32),
+                   cig_off=np.zeros(n + 1, np.int64), ovf=np.zeros(n, np.int32), cells=np.zeros(n, np.int64))
+        cap = int(pl.sum() + tl.sum()) + 16
+        runs = np.zeros(cap, np.uint32)
+        rc = lib.emu_reg_align_batch(C.addressof(cfg), np.ascontiguousarray(seq), po, pl, to, tl, n, regs,
+                                     hrows or 32 * regs + 5, out["score"], out["status"], out["locs"],
+                                     out["cig_off"], runs, cap, out["ovf"], out["cells"])
+        assert rc == 0, rc
+        out["runs"] = runs[:out["cig_off"][-1]]
+        return out
+    return run
+
+
+def compare(got, want, full):
+    """Every pair the tier finished must equal the oracle; returns the number of overflows."""
+    done = np.flatnonzero(got["ovf"] == 0)
+    for key in ("score", "status", "cells"):
+        bad = done[got[key][done] != want[key][done]]
+        assert bad.size == 0, f"{key} differs at pairs {bad[:5]}"
+    if full:
+        for i in done:
+            a = got["runs"][got["cig_off"][i]:got["cig_off"][i + 1]]
+            b = want["runs"][want["cig_off"][i]:want["cig_off"][i + 1]]
+            assert np.array_equal(a, b), f"CIGAR differs at pair {i}"
+        assert np.array_equal(got["locs"][done], want["locs"][done])
+    return len(got["ovf"]) - len(done)
+
+
+CASES = [
+    # name, config, n, length, divergence, flank, registers, max overflow fraction
+    ("cfg1-e2e-full-128", dict(span="end-to-end"), 1500, 150, 0.05, 0, 2, 0.0),
+    ("cfg1-e2e-full-64", dict(span="end-to-end"), 1500, 150, 0.05, 0, 1, 0.2),
+    ("cfg1-endsfree-default-128", dict(), 1000, 150, 0.05, 0, 2, 0.0),
+    ("cfg2-score-256", dict(span="end-to-end", scope="score"), 800, 250, 0.10, 0, 4, 0.0),
+    ("cfg2-full-256", dict(span="end-to-end"), 500, 250, 0.10, 0, 4, 0.0),
+    ("cfg2-score-128-overflows", dict(span="end-to-end", scope="score"), 300, 250, 0.10, 0, 2, 1.0),
+    ("endsfree-all-four", dict(pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7),
+     1000, 150, 0.10, 4, 4, 0.0),
+    ("high-divergence", dict(span="end-to-end"), 800, 100, 0.5, 0, 4, 0.05),
+    ("max-steps", dict(span="end-to-end", max_steps=10), 600, 150, 0.1, 0, 2, 0.0),
+    ("max-steps-odd", dict(span="end-to-end", max_steps=11, scope="score"), 600, 150, 0.1, 0, 2, 0.0),
+    ("long-low-divergence", dict(span="end-to-end"), 60, 2000, 0.01, 0, 4, 0.2),
+]
+
+
+@pytest.mark.parametrize("name,kw,n,length,div,flank,regs,max_ovf", CASES, ids=[c[0] for c in CASES])
+def test_register_tier_matches_oracle(emu_reg, oracle, name, kw, n, length, div, flank, regs, max_ovf):
+    batch = generate_pairs(n, length, div, seed=hash(name) % 9973, text_flank=flank)
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu_reg(cfg, batch, regs)
+    novf = compare(got, want, kw.get("scope", "full") == "full")
+    assert novf <= max_ovf * n, f"{novf} of {n} pairs overflowed the window"
+
+
+def test_register_tier_ragged_and_empty(emu_reg, oracle):
+    rng = np.random.default_rng(5)
+    acgt = "ACGT"
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C"), ("ACGT" * 40, "ACGT" * 40)]
+    for _ in range(500):
+        lp, lt = int(rng.integers(0, 120)), int(rng.integers(0, 120))
+        p = "".join(acgt[i] for i in rng.integers(0, 4, lp))
+        if rng.random() < 0.5 and lp:
+            cut = int(rng.integers(0, lp))
+            t = p[:cut] + "".join(acgt[i] for i in rng.integers(0, 4, int(rng.integers(0, 9)))) + p[cut + int(rng.integers(0, 5)):]
+        else:
+            t = "".join(acgt[i] for i in rng.integers(0, 4, lt))
+        pairs.append((p, t))
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(span="end-to-end"), dict(), dict(scope="score", span="end-to-end")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = emu_reg(cfg, batch, 4)
+        # unrelated random pairs score beyond what a 256-diagonal window reaches: they overflow
+        assert compare(got, want, kw.get("scope", "full") == "full") < len(pairs) // 4
+
+
+def test_register_tier_origin_rows_overflow(emu_reg, oracle):
+    """Too few origin rows for the score: the pair must be handed on, not mis-aligned."""
+    batch = generate_pairs(200, 150, 0.10, seed=11)
+    cfg = oracle.make_config(span="end-to-end")
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu_reg(cfg, batch, 4, hrows=20)
+    novf = compare(got, want, True)
+    assert 0 < novf < 200
