@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwfagpu.so")
+LIB_PATH = os.environ.get("WFAGPU_LIB") or os.path.join(HERE, "libwfagpu.so")   # env: tuning experiments
 
 CONFIG_FIELDS = [
     "distance", "scope", "span",
@@ -141,15 +141,23 @@ class Context:
                 raise ValueError("a pair lies outside the sequence buffer")
         return seq, p_off, p_len, t_off, t_len, n
 
-    def align_batch(self, cfg: Config, seq, p_off, p_len, t_off, t_len, copy_runs=True, check=True):
+    def align_batch(self, cfg: Config, seq, p_off, p_len, t_off, t_len, copy_runs=True, check=True, out=None):
         """``wfagpu_align_batch`` on host arrays; returns a dict of numpy arrays.  With
         ``copy_runs=False`` the CIGAR run array is a view of library-owned pinned memory that
-        stays valid until the next align call on this context."""
+        stays valid until the next align call on this context.  ``out`` may hold preallocated
+        ``score``/``status``/``locs``/``cig_off`` arrays of the right shape to be filled in place."""
         seq, p_off, p_len, t_off, t_len, n = self._inputs(seq, p_off, p_len, t_off, t_len, check)
-        score = np.empty(n, np.int32)
-        status = np.empty(n, np.int32)
-        locs = np.empty((n, 4), np.int32)
-        cig_off = np.empty(n + 1, np.int64)
+        if out is not None:
+            score, status, locs, cig_off = out["score"], out["status"], out["locs"], out["cig_off"]
+            if not (score.shape == (n,) and status.shape == (n,) and locs.shape == (n, 4) and cig_off.shape == (n + 1,)
+                    and score.dtype == np.int32 and status.dtype == np.int32 and locs.dtype == np.int32
+                    and cig_off.dtype == np.int64 and all(a.flags.c_contiguous for a in (score, status, locs, cig_off))):
+                raise ValueError("out arrays have the wrong shape or dtype")
+        else:
+            score = np.empty(n, np.int32)
+            status = np.empty(n, np.int32)
+            locs = np.empty((n, 4), np.int32)
+            cig_off = np.empty(n + 1, np.int64)
         runs_p = C.c_void_p()
         rc = lib().wfagpu_align_batch(self._h, C.addressof(cfg), _ptr(seq), _ptr(p_off), _ptr(p_len),
                                       _ptr(t_off), _ptr(t_len), n, _ptr(score), _ptr(status),

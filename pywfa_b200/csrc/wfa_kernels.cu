@@ -178,10 +178,14 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
   if (g.rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
 }
 
+#ifndef WFA_REG_MINB
+#define WFA_REG_MINB 6      /* resident CTAs per SM the register tier is compiled for (register budget;
+                               measured r01: 5 -> 41.6, 6 -> 42.8, 7 -> 37.3, 8 -> 35.2 M pairs/s on cfg2) */
+#endif
 /* ---- the register-resident tier (wfa_reg.cuh): warp-per-pair, wavefronts in registers ---- */
 /* shared memory of one warp: the sequence windows of the pair (seq_words_cap words, one per base + 2) */
 template <int P, int DX, int DOE, bool FULL>
-__global__ void __launch_bounds__(128) wfa_reg_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp_id = blockIdx.x * (blockDim.x >> 5) + wib;

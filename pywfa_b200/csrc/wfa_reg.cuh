@@ -352,7 +352,6 @@ struct RegAligner {
       }
       /* phase B: the recurrence (compute_affine.c:44-86), 64 diagonals per instruction */
       uint8_t* const hrow = FULL ? hist + s * WIN : nullptr;
-      vu over = splat(0x80008000u);                 /* max over new I/D of (offset - ub - 1), per half */
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const vu L = prmt(p > 0 ? rl[p > 0 ? p - 1 : 0] : splat(REG_NULL2), rl[p], selL);
@@ -375,17 +374,22 @@ struct RegAligner {
           m = vimax3(mis, ins, del);
         }
         /* offsets beyond the matrix are nulled: M > ub  <=>  M + ~ub >= 0 */
-        const vu nub = ~ub2[p];
-        Mn[p] = bitsel(signmask2(vadd2(m, nub)), m, splat(REG_NULL2));
+        Mn[p] = bitsel(signmask2(vadd2(m, ~ub2[p])), m, splat(REG_NULL2));
         I[p] = ins; D[p] = del;
-        over = vimax3(over, vadd2(ins, nub), vadd2(del, nub));
       }
       bool exIn = ex_o | exI, exDn = ex_o | exD;
-      if (any((over & 0x80008000u) != 0x80008000u)) {
-        /* some new I/D offset lies beyond the matrix: trim_ends decides which of them survive */
-        exact = true;
-        trim_component(I, exIn);
-        trim_component(D, exDn);
+      if (exact) {
+        /* An I/D offset can only leave the matrix after some offset has touched its edge, and the
+         * first offset to do so is an M offset (M >= I, D on every diagonal), which raised `exact`
+         * in after_extend.  From then on look for such offsets (offset - ub - 1 >= 0, per half);
+         * trim_ends (compute.c:571-605) decides which of them survive. */
+        vu over = splat(0x80008000u);
+#pragma unroll
+        for (int p = 0; p < P; ++p) over = vimax3(over, vadd2(I[p], ~ub2[p]), vadd2(D[p], ~ub2[p]));
+        if (any((over & 0x80008000u) != 0x80008000u)) {
+          trim_component(I, exIn);
+          trim_component(D, exDn);
+        }
       }
       exI = exIn; exD = exDn;
       rotate();

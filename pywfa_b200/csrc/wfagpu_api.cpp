@@ -95,6 +95,10 @@ struct wfagpu_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   /* uploads of the next chunk overlap the kernels of this one */
   cudaEvent_t uploaded[2] = {nullptr, nullptr};
+  cudaStream_t d2h_stream = nullptr;    /* result downloads of chunk c overlap the kernels of chunk c+1 */
+  cudaEvent_t d2h_done[2] = {nullptr, nullptr};
+  cudaEvent_t run_done = nullptr;       /* all kernels of a chunk (incl. CIGAR ordering) finished */
+  PinBuf out_stage[2];                  /* pinned landing zone of one chunk's result arrays */
   int sms = 0;
   int smem_optin = 0;
   std::string err;
@@ -355,8 +359,12 @@ extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t err
   if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->uploaded[0], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->uploaded[1], cudaEventDisableTiming)) != cudaSuccess) {
+      (e = cudaEventCreateWithFlags(&ctx->uploaded[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->d2h_done[0], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->d2h_done[1], cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->run_done, cudaEventDisableTiming)) != cudaSuccess) {
     set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
     delete ctx;
     return WFAGPU_ECUDA;
@@ -391,7 +399,11 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   ctx->rhist.release(); ctx->rops.release();
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->d2h_stream);
   cudaEventDestroy(ctx->uploaded[0]); cudaEventDestroy(ctx->uploaded[1]);
+  cudaEventDestroy(ctx->d2h_done[0]); cudaEventDestroy(ctx->d2h_done[1]);
+  cudaEventDestroy(ctx->run_done);
+  ctx->out_stage[0].release(); ctx->out_stage[1].release();
   delete ctx;
 }
 
@@ -807,6 +819,109 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     if (rc == WFAGPU_OK) rc = gpu_side(0);
     if (trace_on()) fprintf(stderr, "[wfagpu] n=%lld single chunk: pack %.2f ms, gpu side %.2f ms\n", (long long)n, t1 - t_start, now_ms() - t1);
   } else {
+    /*
+     * Three host threads: the caller packs chunk c+1 (all cores) and starts its upload; the GPU
+     * thread runs the kernels of chunk c and queues its result download on a third stream into
+     * pinned staging; the drain thread copies finished downloads into the caller's arrays.  So
+     * pack(c+1), kernels(c) and download(c-1) overlap.
+     */
+    struct Drain { int64_t off, m; bool last; long long runs; long long run_base; bool full; };
+    Drain drains[2];
+    int64_t queued = 0, drained = 0;     /* chunks whose download was queued / copied out */
+    auto out_bytes = [&](int64_t m, bool full) { return (size_t)(full ? 8 * (m + 1) + 24 * m : 8 * m) + 64; };
+    auto gpu_side_async = [&](int64_t c) -> int {
+      wfagpu_batch* b = shells[c & 1];
+      const int64_t off = c * chunk;
+      const double g0 = now_ms();
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[c & 1], 0));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->d2h_done[c & 1], 0));   /* chunk c-2 left this shell's result buffers */
+      b->cig_base = run_base;
+      int r = batch_run(ctx, b, ctx->stream, ctx->pin_small.as<DevCounters>());
+      if (r != WFAGPU_OK) return r;
+      const double g1 = now_ms();
+      {
+        std::unique_lock<std::mutex> lk(mu);                          /* landing zone c&1 free again? */
+        cv.wait(lk, [&] { return drained + 2 > c || err != WFAGPU_OK; });
+        if (err != WFAGPU_OK) return err;
+      }
+      const size_t m = (size_t)b->n;
+      PinBuf& st = ctx->out_stage[c & 1];
+      CK(st.ensure(out_bytes((int64_t)m, b->full)));
+      unsigned char* base = st.as<unsigned char>();
+      cudaStream_t ds = ctx->d2h_stream;
+      CK(cudaEventRecord(ctx->run_done, ctx->stream));       /* the CIGAR ordering kernels are still in flight */
+      CK(cudaStreamWaitEvent(ds, ctx->run_done, 0));
+      if (b->full) {
+        /* layout: cig_off[m+1] | locs[4m] | score[m] | status[m] */
+        CK(cudaMemcpyAsync(base, b->cig_off.p, 8 * (m + 1), cudaMemcpyDeviceToHost, ds));
+        CK(cudaMemcpyAsync(base + 8 * (m + 1), b->locs.p, 16 * m, cudaMemcpyDeviceToHost, ds));
+        CK(cudaMemcpyAsync(base + 8 * (m + 1) + 16 * m, b->score.p, 4 * m, cudaMemcpyDeviceToHost, ds));
+        CK(cudaMemcpyAsync(base + 8 * (m + 1) + 20 * m, b->status.p, 4 * m, cudaMemcpyDeviceToHost, ds));
+        if (cig_runs && b->total_runs) {
+          const size_t need = 4 * (size_t)(run_base + b->total_runs);
+          if (need > ctx->pin_runs.cap) {
+            /* grow the library-owned run buffer (sized from this chunk for all remaining ones),
+             * keeping what earlier chunks wrote; their downloads must have landed first */
+            CK(cudaStreamSynchronize(ds));
+            PinBuf bigger;
+            CK(bigger.ensure(std::max(need, 4 * (size_t)run_base + 4 * (size_t)(b->total_runs + b->total_runs / 8) * (size_t)(nchunks - c))));
+            if (run_base) memcpy(bigger.p, ctx->pin_runs.p, 4 * (size_t)run_base);
+            ctx->pin_runs.release();
+            ctx->pin_runs = bigger;
+          }
+          CK(cudaMemcpyAsync(ctx->pin_runs.as<uint32_t>() + run_base, b->runs_out.p, 4 * (size_t)b->total_runs,
+                             cudaMemcpyDeviceToHost, ds));
+        }
+      } else {
+        CK(cudaMemcpyAsync(base, b->score.p, 4 * m, cudaMemcpyDeviceToHost, ds));
+        CK(cudaMemcpyAsync(base + 4 * m, b->status.p, 4 * m, cudaMemcpyDeviceToHost, ds));
+      }
+      CK(cudaEventRecord(ctx->d2h_done[c & 1], ds));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        drains[c & 1] = Drain{off, (int64_t)m, c == nchunks - 1, b->total_runs, run_base, b->full};
+        queued = c + 1;
+        cv.notify_all();
+      }
+      if (b->full) run_base += b->total_runs;
+      launches += b->stats.kernel_launches;
+      t_run += g1 - g0; t_down += now_ms() - g1;
+      return WFAGPU_OK;
+    };
+    std::thread drain_thread([&] {
+      cudaSetDevice(ctx->device);
+      for (int64_t c = 0; c < nchunks; ++c) {
+        Drain d;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return queued > c || err != WFAGPU_OK; });
+          if (queued <= c) return;
+          d = drains[c & 1];
+        }
+        if (cudaEventSynchronize(ctx->d2h_done[c & 1]) != cudaSuccess) {
+          std::lock_guard<std::mutex> lk(mu);
+          if (err == WFAGPU_OK) { err = WFAGPU_ECUDA; ctx->err = "result download failed"; }
+          cv.notify_all();
+          return;
+        }
+        const unsigned char* base = ctx->out_stage[c & 1].as<unsigned char>();
+        const size_t m = (size_t)d.m;
+        if (d.full) {
+          if (cig_off) memcpy(cig_off + d.off, base, 8 * (m + (d.last ? 1 : 0)));
+          if (locs) memcpy(locs + 4 * d.off, base + 8 * (m + 1), 16 * m);
+          if (score) memcpy(score + d.off, base + 8 * (m + 1) + 16 * m, 4 * m);
+          if (status) memcpy(status + d.off, base + 8 * (m + 1) + 20 * m, 4 * m);
+        } else {
+          if (score) memcpy(score + d.off, base, 4 * m);
+          if (status) memcpy(status + d.off, base + 4 * m, 4 * m);
+          if (locs && m) memset(locs + 4 * d.off, 0, 16 * m);
+          if (cig_off) for (size_t i = 0; i < m + (d.last ? 1 : 0); ++i) cig_off[d.off + i] = d.run_base;
+        }
+        std::lock_guard<std::mutex> lk(mu);
+        drained = c + 1;
+        cv.notify_all();
+      }
+    });
     std::thread gpu_thread([&] {
       cudaSetDevice(ctx->device);
       for (int64_t c = 0; c < nchunks; ++c) {
@@ -816,10 +931,10 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
           if (err != WFAGPU_OK) return;
         }
         const double t0 = now_ms();
-        const int r = gpu_side(c);
+        const int r = gpu_side_async(c);
         gpu_busy += now_ms() - t0;
         std::lock_guard<std::mutex> lk(mu);
-        if (r != WFAGPU_OK) err = r;
+        if (r != WFAGPU_OK && err == WFAGPU_OK) err = r;
         consumed = c + 1;
         cv.notify_all();
         if (r != WFAGPU_OK) return;
@@ -839,14 +954,17 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
       if (r == WFAGPU_OK) r = upload_side(c);
       pack_ms += now_ms() - t0;
       std::lock_guard<std::mutex> lk(mu);
-      if (r != WFAGPU_OK) { err = r; cv.notify_all(); break; }
+      if (r != WFAGPU_OK) { if (err == WFAGPU_OK) err = r; cv.notify_all(); break; }
       packed = c + 1;
       cv.notify_all();
     }
     gpu_thread.join();
+    { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
+    drain_thread.join();
+    cudaStreamSynchronize(ctx->d2h_stream);
     rc = err;
     if (trace_on())
-      fprintf(stderr, "[wfagpu] n=%lld in %lld chunks: total %.2f ms (pack+upload %.2f ms on the caller; gpu side %.2f ms = kernels %.2f + download %.2f)\n",
+      fprintf(stderr, "[wfagpu] n=%lld in %lld chunks: total %.2f ms (pack+upload %.2f ms on the caller; gpu side %.2f ms = kernels %.2f + queueing downloads %.2f)\n",
               (long long)n, (long long)nchunks, now_ms() - t_start, pack_ms, gpu_busy, t_run, t_down);
   }
   if (cig_runs) *cig_runs = ctx->pin_runs.as<uint32_t>();
