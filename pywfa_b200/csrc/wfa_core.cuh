@@ -20,11 +20,13 @@
  *   - trim_ends (W/wavefront/wavefront_compute.c:571-605), end-to-end / ends-free termination
  *     (W/wavefront/wavefront_termination.c:37-162) and the WF-adaptive / X-drop cut-offs
  *     (W/wavefront/wavefront_heuristic.c:257-383,509-567) are min-reductions over the group;
- *   - scope=full spills one (pre-extension M offset, origin code) record per cell to a
- *     per-group HBM arena with coalesced stores; the backtrace
- *     (W/wavefront/wavefront_backtrace.c:320-529) then follows the recorded origin codes,
- *     which hold the winner of the reference's (offset<<4 | type) max and one ext/open bit
- *     per gap component, and emits run-length encoded CIGAR words directly.
+ *   - scope=full spills ONE origin byte per cell to a per-group HBM arena with coalesced
+ *     stores: the winner of the reference's (offset<<4 | type) max
+ *     (W/wavefront/wavefront_backtrace.c:366-389) and one ext/open bit per gap component.  The
+ *     backtrace (W/wavefront/wavefront_backtrace.c:320-529) walks these bytes from the end cell
+ *     back to score 0 collecting the edit operations, then replays them forwards re-extending
+ *     the matches from the sequences, which emits the run-length encoded CIGAR in order; no
+ *     offsets are stored (1 byte per cell instead of the reference's 4 x ncomp).
  *
  * The file is also compiled as plain host C++ with a one-thread group by tests/emu/ (test
  * infrastructure for the CPU-only CI; never part of the product library).
@@ -70,6 +72,12 @@ template <class T> WFA_DEV T off_store(int v) {
   return (T)(v > n ? v : n);
 }
 
+struct HistRow {       /* scope=full: where the origin bytes of one score live */
+  long long off;       /* first cell of the score in the group's arena */
+  int lo;              /* diagonal of that cell */
+  int pad;
+};
+
 struct PairMeta {      /* 16 bytes, one per pair, in HBM */
   int64_t woff;        /* first 32-bit word of the packed pattern; text words follow it */
   int32_t plen, tlen;
@@ -104,7 +112,7 @@ struct KParams {
   /* results (SoA) */
   int* score; int* status; int* locs; int* nruns; long long* runs_base;
   /* scope=full scratch */
-  void* hist_m0; uint8_t* hist_code; int2* hmeta; uint32_t* runs_stage;
+  uint8_t* hist_code; HistRow* hmeta; uint32_t* runs_stage;
   uint32_t* runs_tmp; unsigned long long* runs_cursor; unsigned long long runs_tmp_cap;
   /* global ring arena for the widest tier (elements per group = gring_elems) */
   int* gring; long long gring_elems;
@@ -120,7 +128,8 @@ struct GroupMem {
   const uint32_t* pw; const uint32_t* tw;   /* packed sequences, readable one word past the end */
   OffT* ring[5];
   int4* meta;                               /* [mr][NC] : lo, hi, ring slot, exists */
-  OffT* h_m0; uint8_t* h_code; int2* hmeta; uint32_t* runs_stage;
+  uint8_t* h_code; HistRow* hmeta; uint32_t* runs_stage;
+  uint8_t* ops; int opcap;                  /* edit-operation stack of the backtrace */
 };
 
 struct PairResult {
@@ -194,11 +203,11 @@ WFA_DEV int rd(const Src<OffT>& s, int k, int km) {
   return (k >= s.lo && k <= s.hi) ? (int)s.slot[km] : OFFNULL;
 }
 
-/* ---- CIGAR run emitter (rank 0 only); runs are produced end -> start --------------- */
-struct RunEmitter {
+/* ---- CIGAR run emitter (one thread); runs are produced in CIGAR order ----------------- */
+struct FwdEmitter {
   uint32_t* stage; int cap; int n; uint32_t op; int len;
   WFA_DEV void init(uint32_t* s, int c) { stage = s; cap = c; n = 0; op = 0xffu; len = 0; }
-  WFA_DEV void flush() { if (len > 0 && n < cap) stage[n] = ((uint32_t)len << 4) | op; if (len > 0) ++n; len = 0; }
+  WFA_DEV void flush() { if (len > 0) { if (n < cap) stage[n] = ((uint32_t)len << 4) | op; ++n; } len = 0; }
   WFA_DEV void push(uint32_t o, int cnt) {
     if (cnt <= 0) return;
     if (o == op) { len += cnt; return; }
@@ -206,78 +215,101 @@ struct RunEmitter {
   }
 };
 
+/* edit operations collected by the backward walk (one byte each) */
+enum { EOP_X = 0, EOP_I_OPEN = 1, EOP_I_EXT = 2, EOP_D_OPEN = 3, EOP_D_EXT = 4 };
+
 /*
- * Backtrace over the recorded history (W/wavefront/wavefront_backtrace.c:320-529).  One
- * thread.  At an M cell the origin code gives the winning source type and the stored
- * pre-extension offset gives the length of the match run; inside a gap only the ext/open
- * bit of that component is needed.  Scores are in units of g.  Runs are written end -> start.
+ * Forward replay of the edit operations (ops[nops-1] is the first one) from the score-0 seed of
+ * diagonal k: every arrival in the M matrix re-extends the matches from the sequences, exactly
+ * the extension the forward pass made there.  Emits what wavefront_backtrace_affine
+ * (W/wavefront/wavefront_backtrace.c:320-529) produces right-to-left, in CIGAR order: free
+ * prefix, leading matches, operations with their match runs, free suffix.
  */
-template <class OffT>
-WFA_DEV void backtrace(const KParams& P, const GroupMem<OffT>& gm, int plen, int tlen,
-                       int a_score, int a_k, int a_off, RunEmitter& em) {
-  int mt = CM, score = a_score, k = a_k;
-  int off = a_off;
-  int h = a_off, v = a_off - a_k;
-  if (v < plen) em.push(OP_D, plen - v);
-  if (h < tlen) em.push(OP_I, tlen - h);
-  while (v > 0 && h > 0 && score > 0) {
-    const int2 hm = gm.hmeta[score];
-    const long long idx = (long long)hm.x + (k - hm.y);
-    const int code = gm.h_code[idx];
-    int type;
-    if (mt == CM) {
-      type = code & 15;
-      if (type == BT_NONE) break;
-      const int m0 = (int)gm.h_m0[idx];
-      em.push(OP_M, off - m0);
-      off = m0;
-      v = off - k; h = off;
-      if (v <= 0 || h <= 0) break;
-    } else if (mt == CI1) type = (code & 0x10) ? BT_I1_EXT : BT_I1_OPEN;
-    else if (mt == CD1) type = (code & 0x20) ? BT_D1_EXT : BT_D1_OPEN;
-    else if (mt == CI2) type = (code & 0x40) ? BT_I2_EXT : BT_I2_OPEN;
-    else type = (code & 0x80) ? BT_D2_EXT : BT_D2_OPEN;
-    switch (type) {
-      case BT_M: score -= P.dx; mt = CM; break;
-      case BT_I1_OPEN: score -= P.doe1; mt = CM; break;
-      case BT_I1_EXT: score -= P.de1; mt = CI1; break;
-      case BT_I2_OPEN: score -= P.doe2; mt = CM; break;
-      case BT_I2_EXT: score -= P.de2; mt = CI2; break;
-      case BT_D1_OPEN: score -= P.doe1; mt = CM; break;
-      case BT_D1_EXT: score -= P.de1; mt = CD1; break;
-      case BT_D2_OPEN: score -= P.doe2; mt = CM; break;
-      default: score -= P.de2; mt = CD2; break;
-    }
-    if (type == BT_M) { em.push(OP_X, 1); --off; }
-    else if (type <= BT_I2_EXT) { em.push(OP_I, 1); --k; --off; }
-    else { em.push(OP_D, 1); ++k; }
-    v = off - k; h = off;
+WFA_DEV void replay_ops(const uint8_t* ops, int nops, int k, int plen, int tlen, const uint32_t* pw, const uint32_t* tw,
+                        FwdEmitter& em) {
+  int off = k > 0 ? k : 0;
+  em.push(OP_I, k > 0 ? k : 0);            /* free text prefix (ends-free seeds) */
+  em.push(OP_D, k < 0 ? -k : 0);           /* free pattern prefix */
+  {
+    const int e = extend_offset(pw, tw, plen, tlen, k, off);
+    em.push(OP_M, e - off); off = e;
   }
-  if (mt == CM) {
-    if (v > 0 && h > 0) {
-      const int n = imin(v, h);
-      em.push(OP_M, n);
-      v -= n; h -= n;
+  for (int i = nops - 1; i >= 0; --i) {
+    const int op = ops[i];
+    bool at_m = true;
+    if (op == EOP_X) { em.push(OP_X, 1); ++off; }
+    else if (op == EOP_I_OPEN || op == EOP_I_EXT) {
+      em.push(OP_I, 1); ++k; ++off;
+      at_m = !(i > 0 && ops[i - 1] == EOP_I_EXT);
+    } else {
+      em.push(OP_D, 1); --k;
+      at_m = !(i > 0 && ops[i - 1] == EOP_D_EXT);
     }
-    em.push(OP_D, v);
-    em.push(OP_I, h);
+    if (at_m) {
+      const int e = extend_offset(pw, tw, plen, tlen, k, off);
+      em.push(OP_M, e - off); off = e;
+    }
   }
+  em.push(OP_I, tlen - off);                /* free text suffix */
+  em.push(OP_D, plen - (off - k));          /* free pattern suffix */
   em.flush();
 }
 
-/* `locations` of pywfa (pywfa/align.pyx:788-833) from the staged (reversed) runs */
-WFA_DEV void locations_from_stage(const uint32_t* stage, int n, int plen, int tlen, int* locs) {
+/*
+ * Backtrace over the recorded origin bytes (one thread).  Backward walk from the end cell: at an
+ * M cell the byte names the winning source (mismatch / open / extend of which gap), inside a gap
+ * only the ext/open bit of that component is needed; scores are in units of g.  Returns the
+ * number of runs (may exceed em.cap: the CIGAR did not fit) or -1 if the operation stack is full.
+ */
+WFA_DEV int backtrace_codes(const KParams& P, const uint8_t* h_code, const HistRow* hmeta, int a_score, int a_k,
+                            int plen, int tlen, const uint32_t* pw, const uint32_t* tw, uint8_t* ops, int opcap,
+                            FwdEmitter& em) {
+  int mt = CM, score = a_score, k = a_k, nops = 0;
+  while (score > 0) {
+    const HistRow hm = hmeta[score];
+    const int code = h_code[hm.off + (k - hm.lo)];
+    int type;
+    if (mt == CM) type = code & 15;
+    else if (mt == CI1) type = (code & 0x10) ? BT_I1_EXT : BT_I1_OPEN;
+    else if (mt == CD1) type = (code & 0x20) ? BT_D1_EXT : BT_D1_OPEN;
+    else if (mt == CI2) type = (code & 0x40) ? BT_I2_EXT : BT_I2_OPEN;
+    else type = (code & 0x80) ? BT_D2_EXT : BT_D2_OPEN;
+    if (type == BT_NONE) break;
+    int op;
+    switch (type) {
+      case BT_M: score -= P.dx; mt = CM; op = EOP_X; break;
+      case BT_I1_OPEN: score -= P.doe1; mt = CM; op = EOP_I_OPEN; break;
+      case BT_I1_EXT: score -= P.de1; mt = CI1; op = EOP_I_EXT; break;
+      case BT_I2_OPEN: score -= P.doe2; mt = CM; op = EOP_I_OPEN; break;
+      case BT_I2_EXT: score -= P.de2; mt = CI2; op = EOP_I_EXT; break;
+      case BT_D1_OPEN: score -= P.doe1; mt = CM; op = EOP_D_OPEN; break;
+      case BT_D1_EXT: score -= P.de1; mt = CD1; op = EOP_D_EXT; break;
+      case BT_D2_OPEN: score -= P.doe2; mt = CM; op = EOP_D_OPEN; break;
+      default: score -= P.de2; mt = CD2; op = EOP_D_EXT; break;
+    }
+    if (nops < opcap) ops[nops] = (uint8_t)op;
+    ++nops;
+    if (op == EOP_I_OPEN || op == EOP_I_EXT) --k;
+    else if (op == EOP_D_OPEN || op == EOP_D_EXT) ++k;
+  }
+  if (nops > opcap) return -1;
+  replay_ops(ops, nops, k, plen, tlen, pw, tw, em);
+  return em.n;
+}
+
+/* `locations` of pywfa (pywfa/align.pyx:788-833) from runs in CIGAR order */
+WFA_DEV void locations_from_runs(const uint32_t* runs, int n, int plen, int tlen, int* locs) {
   locs[0] = locs[1] = locs[2] = locs[3] = 0;
   if (n == 0 || plen == 0 || tlen == 0) return;
   int ps = 0, ts = 0;
-  for (int i = n - 1; i >= 0; --i) {          /* CIGAR order = reverse staging order */
-    const uint32_t w = stage[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
+  for (int i = 0; i < n; ++i) {
+    const uint32_t w = runs[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
     if (op == OP_M) break;
     if (op == OP_D) ps += ln; else if (op == OP_X) { ps += ln; ts += ln; } else ts += ln;
   }
   int pe = plen, te = tlen;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t w = stage[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
+  for (int i = n - 1; i >= 0; --i) {
+    const uint32_t w = runs[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
     if (op == OP_M) break;
     if (op == OP_D) pe -= ln; else if (op == OP_X) { pe -= ln; te -= ln; } else te -= ln;
   }
@@ -296,7 +328,7 @@ WFA_DEV bool term_cell(const KParams& P, int plen, int tlen, int ak, int k, int 
 /*
  * Align one pair with the thread group `g`.  G provides: rank, size, sync(),
  * template<int N> allmin(int (&v)[N]).
- * Returns PAIR_DONE (res filled; for scope=full the reversed runs are in gm.runs_stage)
+ * Returns PAIR_DONE (res filled; for scope=full the runs are in gm.runs_stage, in CIGAR order)
  * or PAIR_OVERFLOW (a tier capacity was exceeded; retry on a larger tier).
  */
 template <class G, class OffT, bool TWO_P, bool FULL>
@@ -539,7 +571,6 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
               code |= (x2 << 6) | (y2 << 7);
             }
             code |= (best >= 0) ? (best & 15) : 0;
-            gm.h_m0[cell_off + (k - lo)] = off_store<OffT>(mx);
             gm.h_code[cell_off + (k - lo)] = (uint8_t)code;
           }
           if (m_in) {
@@ -576,7 +607,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           mrow[c] = make_int4(l, h, z, 1);
         }
         if (FULL) {
-          if (g.rank == 0) gm.hmeta[s] = make_int2((int)cell_off, lo);
+          if (g.rank == 0) { HistRow hr; hr.off = cell_off; hr.lo = lo; hr.pad = 0; gm.hmeta[s] = hr; }
           cell_off += width;
         }
         g.sync();
@@ -615,10 +646,10 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
   } else {
     if (status == 1) {
       if (g.rank == 0) {
-        RunEmitter em; em.init(gm.runs_stage, P.runcap);
-        backtrace<OffT>(P, gm, plen, tlen, s, end_k, end_off, em);
-        res.nruns = em.n;
-        locations_from_stage(gm.runs_stage, imin(em.n, P.runcap), plen, tlen, res.locs);
+        FwdEmitter em; em.init(gm.runs_stage, P.runcap);
+        const int n = backtrace_codes(P, gm.h_code, gm.hmeta, s, end_k, plen, tlen, gm.pw, gm.tw, gm.ops, gm.opcap, em);
+        res.nruns = n;
+        if (n >= 0) locations_from_runs(gm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }
       res.score = classic_score(P.match, end_off - end_k, end_off, end_score);
       res.status = ST_COMPLETED;

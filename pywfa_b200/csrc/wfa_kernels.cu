@@ -109,12 +109,12 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
   gm.ring[CI2] = gm.ring[CD1] + P.r1 * P.wcap;
   gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * P.wcap : 0);
   if (FULL) {
-    gm.h_m0 = reinterpret_cast<OffT*>(P.hist_m0) + (long long)group_id * P.hcap;
     gm.h_code = P.hist_code + (long long)group_id * P.hcap;
+    gm.ops = P.rops + (long long)group_id * P.ropcap; gm.opcap = P.ropcap;
     gm.hmeta = P.hmeta + (long long)group_id * P.scap;
     gm.runs_stage = P.runs_stage + (long long)group_id * P.runcap;
   } else {
-    gm.h_m0 = nullptr; gm.h_code = nullptr; gm.hmeta = nullptr; gm.runs_stage = nullptr;
+    gm.h_code = nullptr; gm.hmeta = nullptr; gm.runs_stage = nullptr; gm.ops = nullptr; gm.opcap = 0;
   }
 
   const int n_work = *P.n_work;
@@ -160,8 +160,9 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
           if (g.rank == 0) rbase = (long long)atomicAdd(P.runs_cursor, (unsigned long long)nr);
           rbase = g.bcastll(rbase);
           if (nr > P.runcap || (unsigned long long)(rbase + nr) > P.runs_tmp_cap) { st = ST_OOM; nr = 0; }
-          for (int i = g.rank; i < nr; i += g.size) P.runs_tmp[rbase + i] = gm.runs_stage[nr - 1 - i];
-        }
+          g.sync();
+          for (int i = g.rank; i < nr; i += g.size) P.runs_tmp[rbase + i] = gm.runs_stage[i];
+        } else if (nr < 0) { st = ST_OOM; nr = 0; }
         if (g.rank == 0) {
           P.score[pid] = res.score; P.status[pid] = st;
           int4 l = make_int4(res.locs[0], res.locs[1], res.locs[2], res.locs[3]);

@@ -58,9 +58,6 @@ constexpr int REG_NULL16 = -16384;
 constexpr int REG_UB_MIN = -8192;              /* floor of ub[k] for diagonals left of the matrix */
 constexpr uint32_t REG_ONE2 = 0x00010001u;
 
-/* edit operations collected by the backward walk */
-enum { EOP_X = 0, EOP_I_OPEN = 1, EOP_I_EXT = 2, EOP_D_OPEN = 3, EOP_D_EXT = 4 };
-
 struct RegParams {
   int match, g, max_steps;
   int endsfree, pbf, pef, tbf, tef;
@@ -68,37 +65,6 @@ struct RegParams {
   int opcap;          /* edit-operation stack bytes */
   int runcap;         /* CIGAR run staging words */
 };
-
-/* forward CIGAR run emitter (one thread) */
-struct FwdEmitter {
-  uint32_t* stage; int cap; int n; uint32_t op; int len;
-  WFA_DEV void init(uint32_t* s, int c) { stage = s; cap = c; n = 0; op = 0xffu; len = 0; }
-  WFA_DEV void flush() { if (len > 0) { if (n < cap) stage[n] = ((uint32_t)len << 4) | op; ++n; } len = 0; }
-  WFA_DEV void push(uint32_t o, int cnt) {
-    if (cnt <= 0) return;
-    if (o == op) { len += cnt; return; }
-    flush(); op = o; len = cnt;
-  }
-};
-
-/* `locations` of pywfa (pywfa/align.pyx:788-833) from runs in CIGAR order */
-WFA_DEV void locations_from_runs(const uint32_t* runs, int n, int plen, int tlen, int* locs) {
-  locs[0] = locs[1] = locs[2] = locs[3] = 0;
-  if (n == 0 || plen == 0 || tlen == 0) return;
-  int ps = 0, ts = 0;
-  for (int i = 0; i < n; ++i) {
-    const uint32_t w = runs[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
-    if (op == OP_M) break;
-    if (op == OP_D) ps += ln; else if (op == OP_X) { ps += ln; ts += ln; } else ts += ln;
-  }
-  int pe = plen, te = tlen;
-  for (int i = n - 1; i >= 0; --i) {
-    const uint32_t w = runs[i]; const uint32_t op = w & 15; const int ln = (int)(w >> 4);
-    if (op == OP_M) break;
-    if (op == OP_D) pe -= ln; else if (op == OP_X) { pe -= ln; te -= ln; } else te -= ln;
-  }
-  locs[0] = ps; locs[1] = pe; locs[2] = ts; locs[3] = te;
-}
 
 /*
  * Backtrace over origin bytes (one thread): backward walk, then forward replay.
@@ -131,34 +97,7 @@ WFA_DEV int backtrace_origin(const uint8_t* hist, int win, int kbase, int dx, in
     }
   }
   if (nops > opcap) return -1;
-  /* forward replay from the score-0 seed of diagonal k */
-  int k = kbase + d;
-  int off = k > 0 ? k : 0;
-  em.push(OP_I, k > 0 ? k : 0);           /* free text prefix (ends-free seeds) */
-  em.push(OP_D, k < 0 ? -k : 0);          /* free pattern prefix */
-  {
-    const int e = extend_offset(pw, tw, plen, tlen, k, off);
-    em.push(OP_M, e - off); off = e;
-  }
-  for (int i = nops - 1; i >= 0; --i) {
-    const int op = ops[i];
-    bool at_m = true;
-    if (op == EOP_X) { em.push(OP_X, 1); ++off; }
-    else if (op == EOP_I_OPEN || op == EOP_I_EXT) {
-      em.push(OP_I, 1); ++k; ++off;
-      at_m = !(i > 0 && ops[i - 1] == EOP_I_EXT);
-    } else {
-      em.push(OP_D, 1); --k;
-      at_m = !(i > 0 && ops[i - 1] == EOP_D_EXT);
-    }
-    if (at_m) {
-      const int e = extend_offset(pw, tw, plen, tlen, k, off);
-      em.push(OP_M, e - off); off = e;
-    }
-  }
-  em.push(OP_I, tlen - off);               /* free text suffix */
-  em.push(OP_D, plen - (off - k));         /* free pattern suffix */
-  em.flush();
+  replay_ops(ops, nops, kbase + d, plen, tlen, pw, tw, em);
   return em.n;
 }
 

@@ -108,7 +108,7 @@ struct wfagpu_ctx {
   std::vector<wfagpu_batch*> spare;
   int64_t last_launches = 0;
   /* per-run scratch shared by all batches of this context (grow-only) */
-  DevBuf hist_m0, hist_code, hmeta, runs_stage, gring, rhist, rops;
+  DevBuf hist_code, hmeta, runs_stage, gring, rhist, rops;
 };
 
 struct wfagpu_batch {
@@ -395,7 +395,7 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   ctx->pin_runs.release(); ctx->pin_small.release();
   for (wfagpu_batch* b : ctx->spare) batch_release(b);
   ctx->spare.clear();
-  ctx->hist_m0.release(); ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
+  ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
   ctx->rhist.release(); ctx->rops.release();
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -577,17 +577,18 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
           /* history arena of the widest tier: what is free now, split over the groups */
           size_t free_b = 0, total_b = 0;
           CK(cudaMemGetInfo(&free_b, &total_b));
-          free_b += ctx->hist_m0.cap + ctx->hist_code.cap;
-          const long long per_group = (long long)((double)free_b * 0.8 / 5.0 / (double)groups);
+          free_b += ctx->hist_code.cap;
+          const long long per_group = (long long)((double)free_b * 0.85 / (double)groups);     /* 1 byte per cell */
           k.hcap = std::max<long long>(1024, std::min<long long>(t.hcap, per_group));
         }
-        CK(ctx->hist_m0.ensure(elem * (size_t)k.hcap * (size_t)groups));
+        k.ropcap = (int)(((long long)b->maxp + b->maxt + 8 + 15) & ~15ll);
         CK(ctx->hist_code.ensure((size_t)k.hcap * (size_t)groups));
-        CK(ctx->hmeta.ensure(8ull * (size_t)k.scap * (size_t)groups));
+        CK(ctx->hmeta.ensure(sizeof(HistRow) * (size_t)k.scap * (size_t)groups));
+        CK(ctx->rops.ensure((size_t)k.ropcap * (size_t)groups));
         CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
-        k.hist_m0 = ctx->hist_m0.p; k.hist_code = ctx->hist_code.as<uint8_t>();
-        k.hmeta = ctx->hmeta.as<int2>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
-        b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)((elem + 1) * (size_t)k.hcap * (size_t)groups));
+        k.hist_code = ctx->hist_code.as<uint8_t>(); k.rops = ctx->rops.as<uint8_t>();
+        k.hmeta = ctx->hmeta.as<HistRow>(); k.runs_stage = ctx->runs_stage.as<uint32_t>();
+        b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)((size_t)k.hcap * (size_t)groups));
       }
       k.worklist = cur_list;
       k.n_work = (last_tier < 0) ? &dc->nwork0 : &dc->retry[last_tier];
@@ -761,7 +762,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     const char* e = getenv("WFAGPU_CHUNK");
     const int64_t want = e ? atoll(e) : 0;
     if (want > 0) chunk = want;
-    else if (n >= 262144) chunk = std::max<int64_t>(131072, (n + 7) / 8);
+    else if (n >= 524288) chunk = std::max<int64_t>(262144, (n + 7) / 8);
   }
   const int64_t nchunks = n == 0 ? 1 : (n + chunk - 1) / chunk;
   wfagpu_batch* shells[2] = {batch_acquire(ctx), nchunks > 1 ? batch_acquire(ctx) : nullptr};

@@ -25,15 +25,16 @@ struct EmuGroup {
 };
 
 struct EmuBuffers {      /* allocated once per batch */
-  std::vector<unsigned char> ring, h_m0;
+  std::vector<unsigned char> ring;
   std::vector<int4> meta;
   std::vector<uint8_t> h_code;
-  std::vector<int2> hmeta;
+  std::vector<HistRow> hmeta;
 };
 
 template <class OffT, bool TWO_P, bool FULL>
 static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t* tw, int plen, int tlen,
                    std::vector<uint32_t>& stage, PairResult& res) {
+  std::vector<uint8_t> ops((size_t)plen + tlen + 8);
   const int wcap = P.wcap;
   GroupMem<OffT> gm;
   gm.pw = pw; gm.tw = tw;
@@ -43,8 +44,9 @@ static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t
   gm.ring[CI2] = gm.ring[CD1] + P.r1 * wcap;
   gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * wcap : 0);
   gm.meta = B.meta.data();
-  gm.h_m0 = reinterpret_cast<OffT*>(B.h_m0.data()); gm.h_code = B.h_code.data(); gm.hmeta = B.hmeta.data();
+  gm.h_code = B.h_code.data(); gm.hmeta = B.hmeta.data();
   gm.runs_stage = stage.data();
+  gm.ops = ops.data(); gm.opcap = (int)ops.size();
   EmuGroup g;
   return align_pair<EmuGroup, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
 }
@@ -67,7 +69,6 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
     const int ns = P.rm + 2 * P.r1 + (two_p ? 2 * P.r2 : 0);
     B.ring.resize((size_t)ns * wcap * 4);
     B.meta.resize((size_t)P.mr * 5);
-    B.h_m0.resize(full ? (size_t)hcap * 4 : 4);
     B.h_code.resize(full ? (size_t)hcap : 1);
     B.hmeta.resize(full ? (size_t)scap : 1);
   }
@@ -95,7 +96,8 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
     score[i] = res.score; status[i] = res.status; cells[i] = res.cells;
     memcpy(locs + 4 * i, res.locs, 16);
     if (used + res.nruns > runs_cap) return -1;
-    for (int r = 0; r < res.nruns; ++r) runs[used + r] = stage[res.nruns - 1 - r];
+    if (res.nruns < 0) return -1;
+    for (int r = 0; r < res.nruns; ++r) runs[used + r] = stage[r];
     used += res.nruns;
   }
   cig_off[n] = used;
