@@ -363,16 +363,20 @@ static int occupancy_one(int block, size_t smem) {
   return nb;
 }
 
-/* int16 offset rings exist for the warp tiers only */
+/* int16 offset rings exist for the shared-memory tiers (modes 0 and 1) */
 #define WFA_DISPATCH(FN, ...)                                                   \
   do {                                                                          \
     const int key = (two_p ? 1 : 0) | (full ? 2 : 0) | (mode << 2);             \
-    if (off16 && mode == 0) {                                                   \
+    if (off16 && mode <= 1) {                                                   \
       switch (key) {                                                            \
         case 0: return FN<false, false, 0, int16_t>(__VA_ARGS__);               \
         case 1: return FN<true, false, 0, int16_t>(__VA_ARGS__);                \
         case 2: return FN<false, true, 0, int16_t>(__VA_ARGS__);                \
-        default: return FN<true, true, 0, int16_t>(__VA_ARGS__);                \
+        case 3: return FN<true, true, 0, int16_t>(__VA_ARGS__);                 \
+        case 4: return FN<false, false, 1, int16_t>(__VA_ARGS__);               \
+        case 5: return FN<true, false, 1, int16_t>(__VA_ARGS__);                \
+        case 6: return FN<false, true, 1, int16_t>(__VA_ARGS__);                \
+        default: return FN<true, true, 1, int16_t>(__VA_ARGS__);                \
       }                                                                         \
     }                                                                           \
     switch (key) {                                                              \
@@ -454,7 +458,7 @@ cudaError_t init_kernels(int smem_optin) {
   for (int two_p = 0; two_p < 2; ++two_p)
     for (int full = 0; full < 2; ++full)
       for (int mode = 0; mode < 3; ++mode)
-        for (int off16 = 0; off16 < (mode == 0 ? 2 : 1); ++off16) {
+        for (int off16 = 0; off16 < (mode <= 1 ? 2 : 1); ++off16) {
           const cudaError_t e = init_dispatch(two_p, full, mode, off16, smem_optin);
           if (e != cudaSuccess) return e;
         }

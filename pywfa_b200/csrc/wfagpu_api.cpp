@@ -225,16 +225,20 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const long long avail = (long long)smem_max - 1024 - (long long)block_reduce_smem_bytes() -
                             (long long)group_bytes_of(k, b->two_p, seqw, 0, 4);
     const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
-    int wcap = avail > 4ll * ns * 32 ? pow2_floor(avail / (4ll * ns)) : 0;
+    /* int16 rings double the width that fits in shared memory (1 kbp gap-affine-2p pairs need
+     * ~1100 diagonals x 36 ring slots) */
+    const long long elem = short_reads ? 2 : 4;
+    int wcap = avail > elem * ns * 32 ? pow2_floor(avail / (elem * ns)) : 0;
     wcap = std::min(wcap, wmax2);
     if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2)) {
       Tier t;
       t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
       t.seq_words_cap = seqw;
-      t.group_bytes = (int)group_bytes_of(k, b->two_p, seqw, wcap, 4);
+      t.off16 = short_reads;
+      t.group_bytes = (int)group_bytes_of(k, b->two_p, seqw, wcap, (int)elem);
       t.smem = (size_t)t.group_bytes + block_reduce_smem_bytes();
       t.hcap = std::min<long long>(8ll << 20, cells_bound);
-      t.scap = (int)std::min<long long>(1 << 16, scap_bound);
+      t.scap = (int)std::min<long long>(t.off16 ? 16384 : 1 << 16, scap_bound);
       b->tiers.push_back(t);
       last_wcap = wcap;
     }

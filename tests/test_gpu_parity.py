@@ -33,6 +33,9 @@ CASES = [
     ("penalties-odd", dict(span="end-to-end", mismatch=3, gap_opening=1, gap_extension=1), 3000, 120, 0.15, 0),
     ("penalties-2p-odd", dict(distance="affine2p", mismatch=7, gap_opening=2, gap_extension=3, gap_opening2=11, gap_extension2=2), 1500, 200, 0.15, 0),
     ("high-divergence", dict(span="end-to-end"), 2000, 100, 0.5, 0),
+    ("cfg5-proxy-10kbp-2p-e2e", dict(distance="affine2p", span="end-to-end"), 3, 10000, 0.20, 0),
+    ("long-low-divergence-2kbp", dict(span="end-to-end"), 200, 2000, 0.01, 0),
+    ("mixed-lengths-bwa-like-penalties", dict(span="end-to-end", mismatch=4, gap_opening=6, gap_extension=1), 2000, 180, 0.08, 0),
 ]
 
 
@@ -65,6 +68,43 @@ def test_parity_ragged_and_empty(gpu_ctx, oracle):
         want = oracle.align_batch(cfg, *batch, kind="port")
         got = gpu_ctx.align_batch(cfg, *batch)
         assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"ragged {kw}")
+
+
+def _check_cigar(runs, pattern, text, x, o1, e1, o2, e2):
+    """cigar_check_alignment + cigar_score of the reference (W/alignment/cigar.c:277-345, :617-690)
+    restated for RLE runs: the CIGAR must spell the two sequences, and returns its gap-affine-2p cost."""
+    i = j = cost = 0
+    for w in runs.tolist():
+        op, ln = w & 15, w >> 4
+        if op == 0:
+            assert pattern[i:i + ln] == text[j:j + ln], "M run over differing bases"
+            i += ln; j += ln
+        elif op == 8:
+            assert all(pattern[i + t] != text[j + t] for t in range(ln)), "X over equal bases"
+            i += ln; j += ln; cost += x * ln
+        elif op == 1:
+            j += ln; cost += min(o1 + e1 * ln, o2 + e2 * ln)
+        else:
+            i += ln; cost += min(o1 + e1 * ln, o2 + e2 * ln)
+    assert (i, j) == (len(pattern), len(text)), "CIGAR does not span both sequences"
+    return cost
+
+
+def test_long_reads_cigar_consistency(gpu_ctx, oracle):
+    """cfg5-shaped pairs beyond what the CPU checker finishes in seconds (40 kbp, 20 %, affine2p,
+    end-to-end, block-per-pair with the history spilled to HBM): size-independent properties --
+    the CIGAR spells both sequences and its cost equals the reported score; the score-only path
+    (no history) reports the same score."""
+    batch = generate_pairs(2, 40000, 0.20, seed=41)
+    seq, po, pl, to, tl = batch
+    buf = seq.tobytes().decode()
+    got = gpu_ctx.align_batch(oracle.make_config(distance="affine2p", span="end-to-end"), *batch)
+    sc = gpu_ctx.align_batch(oracle.make_config(distance="affine2p", span="end-to-end", scope="score"), *batch)
+    assert got["status"].tolist() == [0, 0] and sc["status"].tolist() == [0, 0]
+    for i in range(2):
+        runs = got["runs"][got["cig_off"][i]:got["cig_off"][i + 1]]
+        cost = _check_cigar(runs, buf[po[i]:po[i] + pl[i]], buf[to[i]:to[i] + tl[i]], 4, 6, 2, 24, 1)
+        assert -cost == got["score"][i] == sc["score"][i]
 
 
 def test_empty_batch(gpu_ctx, oracle):
