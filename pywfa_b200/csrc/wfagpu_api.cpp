@@ -233,6 +233,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2)) {
       Tier t;
       t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
+      if (const char* e = getenv("WFAGPU_BLOCK_THREADS")) t.threads = atoi(e);       /* tuning experiments */
       t.seq_words_cap = seqw;
       t.off16 = short_reads;
       t.group_bytes = (int)group_bytes_of(k, b->two_p, seqw, wcap, (int)elem);
