@@ -45,6 +45,7 @@ namespace wfagpu {
 
 constexpr int OFFNULL = INT32_MIN / 2;      /* W/wavefront/wavefront_offset.h:44 */
 constexpr int KNONE = INT_MAX;
+constexpr int VEC_MAX_LEN = 12000;           /* packed-halfword tier (wfa_vec.cuh): int16 offsets incl. out-of-matrix I offsets */
 constexpr int REG_MAX_LEN = 8000;            /* register tier (wfa_reg.cuh): longest sequence its int16 offsets are sized for */
 
 enum { CM = 0, CI1 = 1, CD1 = 2, CI2 = 3, CD2 = 4 };

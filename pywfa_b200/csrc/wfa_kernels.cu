@@ -19,6 +19,7 @@
 
 #include "wfa_core.cuh"
 #include "wfa_reg.cuh"
+#include "wfa_vec.cuh"
 #include "wfa_launch.h"
 
 namespace wfagpu {
@@ -255,6 +256,103 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
   if (lane == 0 && cells_acc) atomicAdd(K.cells_total, (unsigned long long)cells_acc);
 }
 
+/* ---- the packed-halfword tier (wfa_vec.cuh): NW warps per pair, rings in shared memory ---- */
+/* shared memory of one group: [metadata int4 x mr*3][flags 256 B][packed sequences][offset rings] */
+template <bool TWO_P, bool FULL, int NW>
+__global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32) wfa_vec_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int sh_i;
+  __shared__ long long sh_ll;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int rank = NW == 1 ? lane : (int)threadIdx.x;
+  const int gsize = NW * 32;
+  const int group_id = NW == 1 ? (int)(blockIdx.x * (blockDim.x >> 5) + wib) : (int)blockIdx.x;
+  unsigned char* const base = smem_raw + (NW == 1 ? (size_t)wib * P.group_bytes : 0);
+
+  vec::VMem vm;
+  vm.meta = reinterpret_cast<int4*>(base);
+  vm.flags = reinterpret_cast<int*>(base + (size_t)P.mr * 48);
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * 48 + 256);
+  vm.ring = sm_seq + P.seq_words_cap;
+  if (FULL) {
+    vm.h_code = P.hist_code + (long long)group_id * P.hcap;
+    vm.ops = P.rops + (long long)group_id * P.ropcap; vm.opcap = P.ropcap;
+    vm.hmeta = P.hmeta + (long long)group_id * P.scap;
+    vm.runs_stage = P.runs_stage + (long long)group_id * P.runcap;
+  } else {
+    vm.h_code = nullptr; vm.hmeta = nullptr; vm.runs_stage = nullptr; vm.ops = nullptr; vm.opcap = 0;
+  }
+  auto bcast = [&](int v) -> int {
+    if (NW == 1) return __shfl_sync(0xffffffffu, v, 0);
+    if (rank == 0) sh_i = v;
+    __syncthreads();
+    const int r = sh_i;
+    __syncthreads();
+    return r;
+  };
+  auto bcastll = [&](long long v) -> long long {
+    if (NW == 1) return __shfl_sync(0xffffffffu, v, 0);
+    if (rank == 0) sh_ll = v;
+    __syncthreads();
+    const long long r = sh_ll;
+    __syncthreads();
+    return r;
+  };
+
+  const int n_work = *P.n_work;
+  long long cells_acc = 0;
+  for (;;) {
+    int w = 0;
+    if (rank == 0) w = atomicAdd(P.work_counter, 1);
+    w = bcast(w);
+    if (w >= n_work) break;
+    const int pid = P.worklist ? P.worklist[w] : w;
+    const PairMeta pm = P.pairs[pid];
+    const int plen = pm.plen, tlen = pm.tlen;
+    const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+    int rc = PAIR_OVERFLOW;
+    PairResult res;
+    if (pwn + twn + 2 <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {
+      const uint32_t* gw = P.words + pm.woff;
+      uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
+      for (int i = rank; i < pwn; i += gsize) sp[i] = gw[i];
+      for (int i = rank; i < twn; i += gsize) st[i] = gw[pwn + i];
+      if (rank == 0) { sp[pwn] = 0; st[twn] = 0; }
+      vm.pw = sp; vm.tw = st;
+      vec::gsync<NW>();
+      rc = vec::align_pair_vec<TWO_P, FULL, NW>(P, vm, plen, tlen, res);
+    }
+    if (rc == PAIR_OVERFLOW) {
+      if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
+    } else {
+      cells_acc += res.cells;
+      if (FULL) {
+        int nr = bcast(res.nruns);
+        long long rbase = 0;
+        int stt = res.status;
+        if (nr > 0) {
+          if (rank == 0) rbase = (long long)atomicAdd(P.runs_cursor, (unsigned long long)nr);
+          rbase = bcastll(rbase);
+          if (nr > P.runcap || (unsigned long long)(rbase + nr) > P.runs_tmp_cap) { stt = ST_OOM; nr = 0; }
+          vec::gsync<NW>();
+          for (int i = rank; i < nr; i += gsize) P.runs_tmp[rbase + i] = vm.runs_stage[i];
+        } else if (nr < 0) { stt = ST_OOM; nr = 0; }
+        if (rank == 0) {
+          P.score[pid] = res.score; P.status[pid] = stt;
+          int4 l = make_int4(res.locs[0], res.locs[1], res.locs[2], res.locs[3]);
+          if (nr == 0) l = make_int4(0, 0, 0, 0);
+          reinterpret_cast<int4*>(P.locs)[pid] = l;
+          P.nruns[pid] = nr; P.runs_base[pid] = rbase;
+        }
+      } else if (rank == 0) {
+        P.score[pid] = res.score; P.status[pid] = res.status;
+      }
+    }
+    vec::gsync<NW>();
+  }
+  if (rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
+}
+
 /* ---- CIGAR ordering ------------------------------------------------------------------ */
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;
@@ -448,6 +546,52 @@ static cudaError_t init_reg(int smem_optin) {
   return e;
 }
 
+/* packed-halfword tier: NW = 1 (warp per pair), 8 or 16 warps per pair */
+#define WFA_VEC_DISPATCH(STMT)                                                          \
+  do {                                                                                  \
+    const int key = (two_p ? 1 : 0) | (full ? 2 : 0);                                   \
+    if (nw == 1) {                                                                      \
+      switch (key) { case 0: STMT(false, false, 1); break; case 1: STMT(true, false, 1); break; \
+                     case 2: STMT(false, true, 1); break; default: STMT(true, true, 1); break; } \
+    } else if (nw == 8) {                                                               \
+      switch (key) { case 0: STMT(false, false, 8); break; case 1: STMT(true, false, 8); break; \
+                     case 2: STMT(false, true, 8); break; default: STMT(true, true, 8); break; } \
+    } else {                                                                            \
+      switch (key) { case 0: STMT(false, false, 16); break; case 1: STMT(true, false, 16); break; \
+                     case 2: STMT(false, true, 16); break; default: STMT(true, true, 16); break; } \
+    }                                                                                   \
+  } while (0)
+
+cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int grid, int block, size_t smem, cudaStream_t st) {
+#define WFA_VEC_LAUNCH(TP, FU, NWW) wfa_vec_kernel<TP, FU, NWW><<<grid, block, smem, st>>>(P)
+  WFA_VEC_DISPATCH(WFA_VEC_LAUNCH);
+#undef WFA_VEC_LAUNCH
+  return cudaGetLastError();
+}
+
+int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem) {
+  int nb = 0;
+#define WFA_VEC_OCC(TP, FU, NWW) \
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfa_vec_kernel<TP, FU, NWW>, block, smem) != cudaSuccess) nb = 0
+  WFA_VEC_DISPATCH(WFA_VEC_OCC);
+#undef WFA_VEC_OCC
+  return nb;
+}
+
+static cudaError_t init_vec(int smem_optin) {
+  cudaError_t e = cudaSuccess;
+  for (int nw : {1, 8, 16})
+    for (int k = 0; k < 4; ++k) {
+      const bool two_p = k & 1, full = k & 2;
+#define WFA_VEC_INIT(TP, FU, NWW) \
+  e = cudaFuncSetAttribute(wfa_vec_kernel<TP, FU, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 256)   /* the kernel has a few bytes of static shared memory */
+      WFA_VEC_DISPATCH(WFA_VEC_INIT);
+#undef WFA_VEC_INIT
+      if (e != cudaSuccess) return e;
+    }
+  return e;
+}
+
 /* Raise the dynamic shared-memory limit of every instantiation on the CURRENT device, once, at
  * context creation: the attribute is per function and device, and changing it per launch would
  * race between the packing thread (occupancy queries) and the launching thread. */
@@ -462,7 +606,9 @@ cudaError_t init_kernels(int smem_optin) {
           const cudaError_t e = init_dispatch(two_p, full, mode, off16, smem_optin);
           if (e != cudaSuccess) return e;
         }
-  return init_reg(smem_optin);
+  const cudaError_t e = init_reg(smem_optin);
+  if (e != cudaSuccess) return e;
+  return init_vec(smem_optin);
 }
 
 size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }

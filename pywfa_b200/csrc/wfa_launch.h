@@ -20,6 +20,10 @@ bool reg_tier_supported(int dx, int doe, int de, int regs);
 cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st);
 int reg_occupancy(int regs, bool full, int block, size_t smem);
 
+/* packed-halfword tier (wfa_vec.cuh): nw = warps per pair (1, 8 or 16) */
+cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int grid, int block, size_t smem, cudaStream_t st);
+int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem);
+
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
  * last one); otherwise gather into cig_off[n+1] (values offset by cig_base) / runs_out. */
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,

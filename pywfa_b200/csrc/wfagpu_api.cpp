@@ -75,6 +75,7 @@ struct Staging { PinBuf words, meta; };
 
 struct Tier {
   int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
+  int vec_nw = 0;          /* > 0: packed-halfword tier (wfa_vec.cuh) with vec_nw warps per pair */
   int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
   int threads = 128;
   int groups_per_block = 4;
@@ -201,8 +202,41 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
       b->tiers.push_back(t);
     }
   }
+  /* packed-halfword tiers (wfa_vec.cuh): everything the register tier does not take, reads up to
+   * VEC_MAX_LEN; warp per pair first, then 8 and 16 warps per pair with the widest rings that
+   * leave two / one CTA per SM */
+  static const bool no_vec = getenv("WFAGPU_NO_VEC_TIER") != nullptr;     /* debugging aid */
+  bool vec_covers_smem = false;
+  if (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN) {
+    const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+    const long long fixed = (long long)k.mr * 48 + 256 + 4ll * seqw;
+    const long long nblk_max = (wmax + 63) / 64 + 1;
+    long long last_nblk = 0;
+    auto add_vec = [&](int nw, long long budget, long long hcap, long long scap) {
+      long long nblk = (budget - fixed) / ((long long)nslots * 128);
+      nblk = std::min(nblk, nblk_max);
+      if (nblk < 2 || nblk <= last_nblk) return;
+      Tier t;
+      t.vec_nw = nw; t.mode = nw == 1 ? 0 : 1;
+      t.threads = nw == 1 ? 128 : nw * 32; t.groups_per_block = nw == 1 ? 4 : 1;
+      t.wcap = (int)(64 * nblk); t.seq_words_cap = seqw;
+      t.group_bytes = (int)((fixed + nblk * nslots * 128 + 15) & ~15ll);
+      t.smem = (size_t)t.group_bytes * t.groups_per_block;
+      t.scap = (int)std::min<long long>(scap, scap_bound);
+      t.hcap = std::min<long long>(hcap, (long long)t.scap * (t.wcap + 64));
+      t.hcap = (t.hcap + 63) & ~63ll;
+      b->tiers.push_back(t);
+      last_nblk = nblk;
+      if (nblk == nblk_max) vec_covers_smem = true;
+    };
+    add_vec(1, 11264, 2ll << 20, 16384);
+    if (last_nblk == 0) add_vec(1, 22528, 2ll << 20, 16384);
+    add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768);
+    add_vec(16, smem_max - 1024, 64ll << 20, 65536);
+  }
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
+    if (vec_covers_smem || (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN)) return;   /* the vec tiers replace the scalar shared-memory tiers */
     wcap = std::min(wcap, wmax2);
     if (wcap <= last_wcap) return;
     Tier t;
@@ -230,7 +264,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const long long elem = short_reads ? 2 : 4;
     int wcap = avail > elem * ns * 32 ? pow2_floor(avail / (elem * ns)) : 0;
     wcap = std::min(wcap, wmax2);
-    if (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2)) {
+    const bool vec_has = !no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN;
+    if (!vec_has && (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2))) {
       Tier t;
       t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
       if (const char* e = getenv("WFAGPU_BLOCK_THREADS")) t.threads = atoi(e);       /* tuning experiments */
@@ -257,7 +292,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   }
   for (auto& t : b->tiers) {
     int bps = t.regs ? reg_occupancy(t.regs, b->full, t.threads, t.smem)
-                     : align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
+              : t.vec_nw ? vec_occupancy(b->two_p, b->full, t.vec_nw, t.threads, t.smem)
+                         : align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
     t.blocks_per_sm = std::max(1, bps);
   }
 }
@@ -600,11 +636,17 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.work_counter = &dc->work[ti];
       k.retry_list = lists[ti & 1];
       k.retry_count = &dc->retry[ti];
+      const double tier_t0 = trace_on() ? now_ms() : 0;
       if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
+      else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, blocks, t.threads, t.smem, st));
       else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
       b->stats.kernel_launches++;
       CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
+      if (trace_on())
+        fprintf(stderr, "[wfagpu]   tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d): %lld pairs in, %d overflowed, %.2f ms\n",
+                ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks, t.threads,
+                nwork, hc->retry[ti], now_ms() - tier_t0);
       nwork = hc->retry[ti];
       if (ti == 0) b->stats.retried_pairs = nwork;
       cur_list = lists[ti & 1];
