@@ -257,9 +257,9 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
 }
 
 /* ---- the packed-halfword tier (wfa_vec.cuh): NW warps per pair, rings in shared memory ---- */
-/* shared memory of one group: [metadata int4 x mr*3][flags 256 B][packed sequences][offset rings] */
+/* shared memory of one group: [metadata int4 x mr*3][flags 256 B][2 step plans 512 B][packed sequences][offset rings] */
 template <bool TWO_P, bool FULL, int NW>
-__global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32) wfa_vec_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8 ? 2 : 1) wfa_vec_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sh_i;
   __shared__ long long sh_ll;
@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32) wfa_vec_kernel(const 
   vec::VMem vm;
   vm.meta = reinterpret_cast<int4*>(base);
   vm.flags = reinterpret_cast<int*>(base + (size_t)P.mr * 48);
-  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * 48 + 256);
+  vm.plan = reinterpret_cast<vec::PlanOut*>(base + (size_t)P.mr * 48 + 256);
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * 48 + (NW == 1 ? 256 : 768));   /* one warp per pair plans for itself */
   vm.ring = sm_seq + P.seq_words_cap;
   if (FULL) {
     vm.h_code = P.hist_code + (long long)group_id * P.hcap;

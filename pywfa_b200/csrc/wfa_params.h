@@ -39,7 +39,7 @@ inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
   k.r1 = k.de1 + 1;
   k.r2 = two_p ? k.de2 + 1 : 1;
   k.mr = 1;
-  while (k.mr < k.rm) k.mr <<= 1;
+  while (k.mr < k.rm + 1) k.mr <<= 1;     /* one spare entry: the planner warp of wfa_vec.cuh publishes score s+1 while score s-rm+1 may still be read */
   k.endsfree = c.span == WFAGPU_SPAN_ENDSFREE;
   k.pbf = c.pattern_begin_free; k.pef = c.pattern_end_free;
   k.tbf = c.text_begin_free; k.tef = c.text_end_free;

@@ -70,26 +70,40 @@ struct VMem {
   int* flags;            /* [3][NFLAG] */
   const uint32_t* pw; const uint32_t* tw;     /* 2-bit packed sequences in shared memory (+1 pad word) */
   uint32_t* ring;        /* slots x capw words */
+  struct PlanOut* plan;  /* [2], NW > 1 only */
   uint8_t* h_code; HistRow* hmeta; uint32_t* runs_stage; uint8_t* ops; int opcap;
 };
 
-struct VSrc { const uint32_t* base; int w0; unsigned span; };
+struct VSrc { int off; int w0; unsigned span; };     /* ring word offset of the slot; written word range [w0, w0 + span] */
 
 template <bool CHECK>
-__device__ __forceinline__ uint32_t vld(const VSrc& s, int pos, int wi) {
-  if (CHECK) return ((unsigned)(wi - s.w0) <= s.span) ? s.base[pos] : NULL2;
-  return s.base[pos];
+__device__ __forceinline__ uint32_t vld(const uint32_t* ring, const VSrc& s, int pos, int wi) {
+  if (CHECK) return ((unsigned)(wi - s.w0) <= s.span) ? ring[s.off + pos] : NULL2;
+  return ring[s.off + pos];
 }
 
-struct VStep {
-  VSrc mx, mo1, i1e, d1e, mo2, i2e, d2e;
-  uint32_t *oM, *oI1, *oD1, *oI2, *oD2;      /* output slots; nullptr: the component does not exist */
+/* everything a step needs that is uniform across the group */
+struct __align__(16) PlanOut {
+  VSrc mx, mo1, i1e, d1e, mo2, i2e, d2e;     /* sources */
+  int oM, oI1, oD1, oI2, oD2;                /* output slots as ring word offsets (-1: component does not exist) */
+  uint8_t* hrow;                             /* scope=full: origin bytes of the score, indexed by biased diagonal */
+  long long cell_off;                        /* history cursor after this score */
+  int nblo, nbhi;                            /* block range written by this score (null step: empty, nblo = tracked block) */
+  int tp;                                    /* ring position (words) of block nblo */
+  int fl, fh;                                /* blocks in [fl, fh] need no range checks */
+  int kind;                                  /* 0 compute, 1 null step, 2 capacity exceeded */
+  int exact;                                 /* ranges must be scanned from this score on */
+  int pad0;
+  int lo[5], hi[5];                          /* ranges of the valid cells (derived; replaced by the scan when exact) */
+};
+static_assert(sizeof(PlanOut) == 192, "PlanOut is copied through shared memory as 12 int4");
+
+/* constants of the pair */
+struct VCtx {
+  uint32_t* ring;
   const uint32_t *pw, *tw;
   int plen, tlen, capw, ak;
   int endsfree, pef, tef;
-  bool exact;
-  int* F;
-  uint8_t* hrow;                              /* scope=full: origin bytes of this score, indexed by biased diagonal */
 };
 
 template <int NW> __device__ __forceinline__ void gsync() {
@@ -120,41 +134,42 @@ __device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int 
  * Extend the two M cells of the lane, detect matrix-edge contact / termination, store the word.
  * k0 = diagonal of the low half, u0 / u1 = ub of the two diagonals.
  */
-__device__ __forceinline__ void finish_m(const VStep& c, uint32_t Mn, int pos, int k0, int u0, int u1, int kblock, int lane) {
+__device__ __forceinline__ void finish_m(const VCtx& c, uint32_t* oM, int* F, bool exact, uint32_t Mn, int pos, int k0, int u0, int u1, int kblock, int lane) {
   using namespace lv;
   int o0 = sx_lo(Mn), o1 = sx_hi(Mn);
   const bool v0 = o0 >= 0, v1 = o1 >= 0;
   o0 += vext(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0);
   o1 += vext(c.pw, c.tw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
-  c.oM[pos] = pack2(o0, o1);
+  oM[pos] = pack2(o0, o1);
   const bool e0 = v0 && o0 == u0, e1 = v1 && o1 == u1;
   if (__any_sync(0xffffffffu, e0 || e1)) {
-    if (e0 || e1) c.F[F_EDGE] = 1;
+    if (e0 || e1) F[F_EDGE] = 1;
     if (c.endsfree) {                              /* termination.c:115-162: lowest terminating diagonal */
       int tk = KNONE;
       if (e1) { const int vv = o1 - k0 - 1; if ((o1 >= c.tlen && c.plen - vv <= c.pef) || (vv >= c.plen && c.tlen - o1 <= c.tef)) tk = k0 + 1; }
       if (e0) { const int vv = o0 - k0; if ((o0 >= c.tlen && c.plen - vv <= c.pef) || (vv >= c.plen && c.tlen - o0 <= c.tef)) tk = k0; }
-      if (tk != KNONE) atomicMin(&c.F[F_TERM], tk);
+      if (tk != KNONE) atomicMin(&F[F_TERM], tk);
     } else {                                       /* termination.c:37-61 */
-      if (k0 == c.ak && e0 && o0 >= c.tlen) c.F[F_TERM] = c.ak;
-      if (k0 + 1 == c.ak && e1 && o1 >= c.tlen) c.F[F_TERM] = c.ak;
+      if (k0 == c.ak && e0 && o0 >= c.tlen) F[F_TERM] = c.ak;
+      if (k0 + 1 == c.ak && e1 && o1 >= c.tlen) F[F_TERM] = c.ak;
     }
   }
-  if (c.exact) report_range(c.F, CM, __ballot_sync(0xffffffffu, o0 >= 0), __ballot_sync(0xffffffffu, o1 >= 0), kblock, lane);
+  if (exact) report_range(F, CM, __ballot_sync(0xffffffffu, o0 >= 0), __ballot_sync(0xffffffffu, o1 >= 0), kblock, lane);
 }
 
 /* exact mode: in-matrix ballots of an I/D word; flags offsets beyond the matrix */
-__device__ __forceinline__ void scan_gap(const VStep& c, int comp, uint32_t x, uint32_t nub, int kblock, int lane) {
+__device__ __forceinline__ void scan_gap(int* F, int comp, uint32_t x, uint32_t nub, int kblock, int lane) {
   using namespace lv;
   const uint32_t t = vadd2(x, nub);                /* sign set: x <= ub */
   const uint32_t ok = t & ~x, bad = ~t & ~x;       /* sign bits: valid / non-negative but beyond the matrix */
-  report_range(c.F, comp, __ballot_sync(0xffffffffu, (ok & 0x8000u) != 0), __ballot_sync(0xffffffffu, (ok & 0x80000000u) != 0), kblock, lane);
-  if (bad & 0x80008000u) c.F[F_POISON] = 1;
+  report_range(F, comp, __ballot_sync(0xffffffffu, (ok & 0x8000u) != 0), __ballot_sync(0xffffffffu, (ok & 0x80000000u) != 0), kblock, lane);
+  if (bad & 0x80008000u) F[F_POISON] = 1;
 }
 
 /* one block of 64 diagonals of the recurrence */
 template <bool TWO_P, bool FULL, bool CHECK>
-__device__ __forceinline__ void vec_block(const VStep& c, int b, int posb, int lane) {
+__device__ __forceinline__ void vec_block(const VCtx& c, const PlanOut& pl, int* F, bool exact, int b, int posb, int lane) {
+  const uint32_t* const ring = c.ring;
   using namespace lv;
   const int wi = 32 * b + lane;
   const int pos = posb + lane;
@@ -165,12 +180,12 @@ __device__ __forceinline__ void vec_block(const VStep& c, int b, int posb, int l
   const int u0 = imax(imin(c.tlen, c.plen + k0), UB_MIN), u1 = imax(imin(c.tlen, c.plen + k0 + 1), UB_MIN);
   const uint32_t nub = ~pack2(u0, u1);
 
-  const uint32_t mx = vld<CHECK>(c.mx, pos, wi);
-  const uint32_t mo1 = vld<CHECK>(c.mo1, pos, wi);
-  const uint32_t MoL = prmt(vld<CHECK>(c.mo1, posl, wi - 1), mo1, 0x5432u);
-  const uint32_t MoR = prmt(mo1, vld<CHECK>(c.mo1, posr, wi + 1), 0x5432u);
-  const uint32_t IeL = prmt(vld<CHECK>(c.i1e, posl, wi - 1), vld<CHECK>(c.i1e, pos, wi), 0x5432u);
-  const uint32_t DeR = prmt(vld<CHECK>(c.d1e, pos, wi), vld<CHECK>(c.d1e, posr, wi + 1), 0x5432u);
+  const uint32_t mx = vld<CHECK>(ring, pl.mx, pos, wi);
+  const uint32_t mo1 = vld<CHECK>(ring, pl.mo1, pos, wi);
+  const uint32_t MoL = prmt(vld<CHECK>(ring, pl.mo1, posl, wi - 1), mo1, 0x5432u);
+  const uint32_t MoR = prmt(mo1, vld<CHECK>(ring, pl.mo1, posr, wi + 1), 0x5432u);
+  const uint32_t IeL = prmt(vld<CHECK>(ring, pl.i1e, posl, wi - 1), vld<CHECK>(ring, pl.i1e, pos, wi), 0x5432u);
+  const uint32_t DeR = prmt(vld<CHECK>(ring, pl.d1e, pos, wi), vld<CHECK>(ring, pl.d1e, posr, wi + 1), 0x5432u);
   const uint32_t mis = vadd2(mx, ONE2);
   uint32_t ins1, del1, ins2 = NULL2, del2 = NULL2, m;
   bool x1h = false, x1l = false, y1h = false, y1l = false, x2h = false, x2l = false, y2h = false, y2l = false;
@@ -182,11 +197,11 @@ __device__ __forceinline__ void vec_block(const VStep& c, int b, int posb, int l
     del1 = vimax2(DeR, MoR);
   }
   if (TWO_P) {
-    const uint32_t mo2 = vld<CHECK>(c.mo2, pos, wi);
-    const uint32_t Mo2L = prmt(vld<CHECK>(c.mo2, posl, wi - 1), mo2, 0x5432u);
-    const uint32_t Mo2R = prmt(mo2, vld<CHECK>(c.mo2, posr, wi + 1), 0x5432u);
-    const uint32_t I2L = prmt(vld<CHECK>(c.i2e, posl, wi - 1), vld<CHECK>(c.i2e, pos, wi), 0x5432u);
-    const uint32_t D2R = prmt(vld<CHECK>(c.d2e, pos, wi), vld<CHECK>(c.d2e, posr, wi + 1), 0x5432u);
+    const uint32_t mo2 = vld<CHECK>(ring, pl.mo2, pos, wi);
+    const uint32_t Mo2L = prmt(vld<CHECK>(ring, pl.mo2, posl, wi - 1), mo2, 0x5432u);
+    const uint32_t Mo2R = prmt(mo2, vld<CHECK>(ring, pl.mo2, posr, wi + 1), 0x5432u);
+    const uint32_t I2L = prmt(vld<CHECK>(ring, pl.i2e, posl, wi - 1), vld<CHECK>(ring, pl.i2e, pos, wi), 0x5432u);
+    const uint32_t D2R = prmt(vld<CHECK>(ring, pl.d2e, pos, wi), vld<CHECK>(ring, pl.d2e, posr, wi + 1), 0x5432u);
     if (FULL) {
       ins2 = vadd2(vimax2p(I2L, Mo2L, x2h, x2l), ONE2);
       del2 = vimax2p(D2R, Mo2R, y2h, y2l);
@@ -207,7 +222,7 @@ __device__ __forceinline__ void vec_block(const VStep& c, int b, int posb, int l
     const uint32_t wh = p4h ? 5u : (p3h ? 4u : (p2h ? 3u : (p1h ? 2u : 1u)));
     const uint32_t cl = wl | (x1l ? 0x10u : 0u) | (y1l ? 0x20u : 0u) | (x2l ? 0x40u : 0u) | (y2l ? 0x80u : 0u);
     const uint32_t ch = wh | (x1h ? 0x10u : 0u) | (y1h ? 0x20u : 0u) | (x2h ? 0x40u : 0u) | (y2h ? 0x80u : 0u);
-    *reinterpret_cast<uint16_t*>(c.hrow + (64 * b + 2 * lane)) = (uint16_t)(cl | (ch << 8));
+    *reinterpret_cast<uint16_t*>(pl.hrow + (64 * b + 2 * lane)) = (uint16_t)(cl | (ch << 8));
   } else if (TWO_P) {
     m = vimax3(vimax3(mis, ins1, ins2), del1, del2);
   } else {
@@ -216,21 +231,21 @@ __device__ __forceinline__ void vec_block(const VStep& c, int b, int posb, int l
   /* keep 0 <= M <= ub, everything else becomes the null (compute_affine.c:80-84) */
   const uint32_t keep = signmask2(vadd2(m, nub) & ~m);
   const uint32_t Mn = (m & keep) | (NULL2 & ~keep);
-  if (c.oI1) c.oI1[pos] = ins1;
-  if (c.oD1) c.oD1[pos] = del1;
+  if (pl.oI1 >= 0) c.ring[pl.oI1 + pos] = ins1;
+  if (pl.oD1 >= 0) c.ring[pl.oD1 + pos] = del1;
   if (TWO_P) {
-    if (c.oI2) c.oI2[pos] = ins2;
-    if (c.oD2) c.oD2[pos] = del2;
+    if (pl.oI2 >= 0) c.ring[pl.oI2 + pos] = ins2;
+    if (pl.oD2 >= 0) c.ring[pl.oD2 + pos] = del2;
   }
-  if (c.exact) {
-    if (c.oI1) scan_gap(c, CI1, ins1, nub, kblock, lane);
-    if (c.oD1) scan_gap(c, CD1, del1, nub, kblock, lane);
+  if (exact) {
+    if (pl.oI1 >= 0) scan_gap(F, CI1, ins1, nub, kblock, lane);
+    if (pl.oD1 >= 0) scan_gap(F, CD1, del1, nub, kblock, lane);
     if (TWO_P) {
-      if (c.oI2) scan_gap(c, CI2, ins2, nub, kblock, lane);
-      if (c.oD2) scan_gap(c, CD2, del2, nub, kblock, lane);
+      if (pl.oI2 >= 0) scan_gap(F, CI2, ins2, nub, kblock, lane);
+      if (pl.oD2 >= 0) scan_gap(F, CD2, del2, nub, kblock, lane);
     }
   }
-  finish_m(c, Mn, pos, k0, u0, u1, kblock, lane);
+  finish_m(c, c.ring + pl.oM, F, exact, Mn, pos, k0, u0, u1, kblock, lane);
 }
 
 /* null the cells of one ring word that lie outside [lo, hi] */
@@ -268,6 +283,117 @@ __device__ inline int backtrace_vcodes(const KParams& P, const uint8_t* h_code, 
 }
 
 /*
+ * Plan score s: fetch_input (compute.c:298-344), limits (compute.c:40-86), allocate_output
+ * (compute.c:401-486) and, while no offset has touched the matrix border, the trimmed ranges
+ * (compute.c:571-605) derived from the source ranges.  A pure function of the metadata ring and
+ * the scalars passed in, so that one warp can run it for score s+1 while the others still work
+ * on score s.  `writer`: this thread publishes the metadata / history row of the score.
+ */
+template <bool TWO_P, bool FULL>
+__device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int plen, int tlen, int s, int cm, int c1, int c2,
+                                          int tp, int tb, long long cell_off, bool exact, bool writer, PlanOut& o) {
+  const int capw = P.wcap >> 1, nblk = P.wcap >> 6, mmask = P.mr - 1;
+  const int4* const meta = vm.meta;
+  const int rI1 = P.rm * capw, rD1 = rI1 + P.r1 * capw, rI2 = rD1 + P.r1 * capw, rD2 = rI2 + (TWO_P ? P.r2 * capw : 0);   /* ring word offsets */
+  const int4 aMx = meta[((s - P.dx) & mmask) * 3];
+  const int4 aMo1 = meta[((s - P.doe1) & mmask) * 3];
+  const int4* const rowe1 = meta + ((s - P.de1) & mmask) * 3;
+  const int4 aE1 = rowe1[0], bE1 = rowe1[1];
+  int4 aMo2 = make_int4(1, -1, 1, -1), aE2 = aMo2, cE2 = aMo2;
+  if (TWO_P) {
+    aMo2 = meta[((s - P.doe2) & mmask) * 3];
+    const int4* const rowe2 = meta + ((s - P.de2) & mmask) * 3;
+    aE2 = rowe2[0]; cE2 = rowe2[2];
+  }
+  const bool n_mx = aMx.x > aMx.y, n_mo1 = aMo1.x > aMo1.y, n_i1 = bE1.x > bE1.y, n_d1 = bE1.z > bE1.w;
+  const bool n_mo2 = TWO_P ? aMo2.x > aMo2.y : true;
+  const bool n_i2 = TWO_P ? cE2.x > cE2.y : true;
+  const bool n_d2 = TWO_P ? cE2.z > cE2.w : true;
+  int4* const mrow = vm.meta + (s & mmask) * 3;
+  o.cell_off = cell_off; o.tp = tp; o.nblo = tb; o.nbhi = tb - 1; o.exact = exact; o.fl = INT_MAX; o.fh = INT_MIN;
+  for (int c = 0; c < 5; ++c) { o.lo[c] = 1; o.hi[c] = -1; }
+  if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
+    /* null step: allocate_output_null, compute.c:374-400 */
+    o.kind = 1;
+    if (writer) { mrow[0] = make_int4(1, -1, 1, -1); mrow[1] = make_int4(1, -1, 1, -1); mrow[2] = make_int4(1, -1, 1, -1); }
+    return;
+  }
+  int lo = INT_MAX, hi = INT_MIN, li1 = INT_MAX, hi1 = INT_MIN, ld1 = INT_MAX, hd1 = INT_MIN;
+  int li2 = INT_MAX, hi2 = INT_MIN, ld2 = INT_MAX, hd2 = INT_MIN;
+  int fl = INT_MIN, fh = INT_MAX;
+  bool all_src = true;
+  auto use = [&](const int4& a, bool null_) {
+    if (null_) { all_src = false; return; }
+    fl = imax(fl, a.z + 1); fh = imin(fh, a.w - 1);
+  };
+  if (!n_mx) { lo = aMx.x; hi = aMx.y; }
+  if (!n_mo1) { li1 = aMo1.x + 1; hi1 = aMo1.y + 1; ld1 = aMo1.x - 1; hd1 = aMo1.y - 1; }
+  if (!n_i1) { li1 = imin(li1, bE1.x + 1); hi1 = imax(hi1, bE1.y + 1); }
+  if (!n_d1) { ld1 = imin(ld1, bE1.z - 1); hd1 = imax(hd1, bE1.w - 1); }
+  lo = imin(lo, imin(li1, ld1)); hi = imax(hi, imax(hi1, hd1));
+  use(aMx, n_mx); use(aMo1, n_mo1); use(aE1, n_i1); use(aE1, n_d1);
+  if (TWO_P) {
+    if (!n_mo2) { li2 = aMo2.x + 1; hi2 = aMo2.y + 1; ld2 = aMo2.x - 1; hd2 = aMo2.y - 1; }
+    if (!n_i2) { li2 = imin(li2, cE2.x + 1); hi2 = imax(hi2, cE2.y + 1); }
+    if (!n_d2) { ld2 = imin(ld2, cE2.z - 1); hd2 = imax(hd2, cE2.w - 1); }
+    lo = imin(lo, imin(li2, ld2)); hi = imax(hi, imax(hi2, hd2));
+    use(aMo2, n_mo2); use(aE2, n_i2); use(aE2, n_d2);
+  }
+  if (!all_src) { fl = INT_MAX; fh = INT_MIN; }
+  if (lo < -plen || hi > tlen) exact = true;
+  const int nblo = (lo + BIAS) >> 6, nbhi = (hi + BIAS) >> 6;
+  const int rowlen = (nbhi - nblo + 1) << 6;
+  if (nbhi - nblo + 1 > nblk || (FULL && (s >= P.scap || cell_off + rowlen > P.hcap))) { o.kind = 2; return; }
+  tp += (nblo - tb) << 5;
+  while (tp >= capw) tp -= capw;
+  while (tp < 0) tp += capw;
+  /* allocate_output, compute.c:401-486 */
+  const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
+  const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
+  auto src = [&](VSrc& v, int off, const int4& a, bool null_) {
+    v.off = off;
+    if (null_) { v.w0 = INT_MAX; v.span = 0; } else { v.w0 = a.z << 5; v.span = (unsigned)(((a.w - a.z) << 5) + 31); }
+  };
+  auto mslot = [&](int d) { int sl = cm - d; if (sl < 0) sl += P.rm; return sl * capw; };
+  const int e1s = (c1 + 1 == P.r1) ? 0 : c1 + 1;           /* slot of score s - e1 */
+  src(o.mx, mslot(P.dx), aMx, n_mx);
+  src(o.mo1, mslot(P.doe1), aMo1, n_mo1);
+  src(o.i1e, rI1 + e1s * capw, aE1, n_i1);
+  src(o.d1e, rD1 + e1s * capw, aE1, n_d1);
+  if (TWO_P) {
+    const int e2s = (c2 + 1 == P.r2) ? 0 : c2 + 1;
+    src(o.mo2, mslot(P.doe2), aMo2, n_mo2);
+    src(o.i2e, rI2 + e2s * capw, aE2, n_i2);
+    src(o.d2e, rD2 + e2s * capw, aE2, n_d2);
+  } else {
+    o.mo2 = o.mo1; o.i2e = o.i1e; o.d2e = o.d1e;
+  }
+  o.oM = cm * capw;
+  o.oI1 = has_i1 ? rI1 + c1 * capw : -1;
+  o.oD1 = has_d1 ? rD1 + c1 * capw : -1;
+  o.oI2 = has_i2 ? rI2 + c2 * capw : -1;
+  o.oD2 = has_d2 ? rD2 + c2 * capw : -1;
+  o.hrow = nullptr;
+  if (FULL) {
+    o.hrow = vm.h_code + cell_off - 64ll * nblo;
+    if (writer) { HistRow hr; hr.off = cell_off; hr.lo = 64 * nblo - BIAS; hr.pad = 0; vm.hmeta[s] = hr; }
+    o.cell_off = cell_off + rowlen;
+  }
+  o.kind = 0; o.exact = exact; o.nblo = nblo; o.nbhi = nbhi; o.tp = tp; o.fl = fl; o.fh = fh;
+  o.lo[CM] = lo; o.hi[CM] = hi;
+  if (has_i1) { o.lo[CI1] = li1; o.hi[CI1] = hi1; }
+  if (has_d1) { o.lo[CD1] = ld1; o.hi[CD1] = hd1; }
+  if (has_i2) { o.lo[CI2] = li2; o.hi[CI2] = hi2; }
+  if (has_d2) { o.lo[CD2] = ld2; o.hi[CD2] = hd2; }
+  if (writer && !exact) {
+    /* derived ranges are final: publish them now (the scan publishes them otherwise) */
+    mrow[0] = make_int4(lo, hi, nblo, nbhi);
+    mrow[1] = make_int4(o.lo[CI1], o.hi[CI1], o.lo[CD1], o.hi[CD1]);
+    mrow[2] = make_int4(o.lo[CI2], o.hi[CI2], o.lo[CD2], o.hi[CD2]);
+  }
+}
+
+/*
  * Align one pair with a group of NW warps.  Returns PAIR_DONE (res filled; scope=full: runs in
  * vm.runs_stage, res.nruns / res.locs valid on rank 0 only) or PAIR_OVERFLOW.
  */
@@ -287,9 +413,9 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
   uint32_t* const rD2 = rI2 + (TWO_P ? P.r2 * capw : 0);
   const int ak = tlen - plen;
 
-  VStep st;
-  st.pw = vm.pw; st.tw = vm.tw; st.plen = plen; st.tlen = tlen; st.capw = capw; st.ak = ak;
-  st.endsfree = P.endsfree; st.pef = P.pef; st.tef = P.tef;
+  VCtx cx;
+  cx.ring = vm.ring; cx.pw = vm.pw; cx.tw = vm.tw; cx.plen = plen; cx.tlen = tlen; cx.capw = capw; cx.ak = ak;
+  cx.endsfree = P.endsfree; cx.pef = P.pef; cx.tef = P.tef;
 
   int s = 0, cm = 0, c1 = 0, c2 = 0, fb = 0;
   int s_exist = 0, steps_wait = P.steps_between, max_sw = 0;
@@ -299,6 +425,8 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
   int end_k = KNONE, end_off = OFFNULL, end_score = 0, status = 0;
   int tb, tp = 0;                               /* ring position tp (words) of block tb */
   int blo, bhi;                                 /* written block range of the current score */
+  bool have_plan = false;                       /* vm.plan[(s+1)&1] holds the plan of the next score */
+  const bool is_writer = NW == 1 ? lane == 0 : (warp == NW - 1 && lane == 0);   /* publishes metadata (the planner's lane 0) */
 
   /* ---- score 0: wavefront_aligner_init_wf_m, W/wavefront/wavefront_aligner.c:251-310 ---- */
   {
@@ -310,15 +438,13 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     for (int i = rank; i < 3 * NFLAG; i += GS) vm.flags[i] = flag_init(i % NFLAG);
     gsync<NW>();
     tb = blo;
-    st.oM = rM; st.oI1 = st.oD1 = st.oI2 = st.oD2 = nullptr;
-    st.exact = false; st.F = vm.flags; st.hrow = nullptr;
     for (int b = blo + warp; b <= bhi; b += NW) {
       const int pos = ((b - blo) << 5) + lane;
       const int kblock = 64 * b - BIAS, k0 = kblock + 2 * lane;
       const int u0 = imax(imin(tlen, plen + k0), UB_MIN), u1 = imax(imin(tlen, plen + k0 + 1), UB_MIN);
       const int s0 = (k0 >= lo0 && k0 <= hi0) ? imax(k0, 0) : NULL16;
       const int s1 = (k0 + 1 >= lo0 && k0 + 1 <= hi0) ? imax(k0 + 1, 0) : NULL16;
-      finish_m(st, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
+      finish_m(cx, rM, vm.flags, false, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
     }
     for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
     clo[CM] = lo0; chi[CM] = hi0;
@@ -498,138 +624,74 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       gsync<NW>();
     }
     {
-      /* fetch_input, compute.c:298-344 */
-      const int4 aMx = meta[((s - P.dx) & mmask) * 3];
-      const int4 aMo1 = meta[((s - P.doe1) & mmask) * 3];
-      const int4* const rowe1 = meta + ((s - P.de1) & mmask) * 3;
-      const int4 aE1 = rowe1[0], bE1 = rowe1[1];
-      int4 aMo2 = make_int4(1, -1, 1, -1), aE2 = aMo2, cE2 = aMo2;
-      if (TWO_P) {
-        aMo2 = meta[((s - P.doe2) & mmask) * 3];
-        const int4* const rowe2 = meta + ((s - P.de2) & mmask) * 3;
-        aE2 = rowe2[0]; cE2 = rowe2[2];
-      }
-      const bool n_mx = aMx.x > aMx.y, n_mo1 = aMo1.x > aMo1.y, n_i1 = bE1.x > bE1.y, n_d1 = bE1.z > bE1.w;
-      const bool n_mo2 = TWO_P ? aMo2.x > aMo2.y : true;
-      const bool n_i2 = TWO_P ? cE2.x > cE2.y : true;
-      const bool n_d2 = TWO_P ? cE2.z > cE2.w : true;
-      int4* const mrow = meta + (s & mmask) * 3;
-      if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
-        /* null step: allocate_output_null, compute.c:374-400 */
-        cur_exists = false;
-        for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
-        if (rank < 3) mrow[rank] = make_int4(1, -1, 1, -1);
-        gsync<NW>();
+      /* plan of this score: precomputed by the planner warp during the previous step, or by everybody now */
+      PlanOut pl;
+      if (NW > 1 && have_plan) {
+        pl = vm.plan[s & 1];
+        if (exact) pl.exact = 1;
       } else {
-        s_exist = s * P.g;
-        /* ranges of the valid cells of every component, from the non-null sources
-         * (limits_input, compute.c:40-86, followed by trim_ends, compute.c:571-605) */
-        int lo = INT_MAX, hi = INT_MIN, li1 = INT_MAX, hi1 = INT_MIN, ld1 = INT_MAX, hd1 = INT_MIN;
-        int li2 = INT_MAX, hi2 = INT_MIN, ld2 = INT_MAX, hd2 = INT_MIN;
-        int fl = INT_MIN, fh = INT_MAX;               /* blocks that need no range checks */
-        bool all_src = true;
-        auto use = [&](const int4& a, bool null_) {
-          if (null_) { all_src = false; return; }
-          fl = imax(fl, a.z + 1); fh = imin(fh, a.w - 1);
-        };
-        if (!n_mx) { lo = imin(lo, aMx.x); hi = imax(hi, aMx.y); }
-        if (!n_mo1) { li1 = aMo1.x + 1; hi1 = aMo1.y + 1; ld1 = aMo1.x - 1; hd1 = aMo1.y - 1; }
-        if (!n_i1) { li1 = imin(li1, bE1.x + 1); hi1 = imax(hi1, bE1.y + 1); }
-        if (!n_d1) { ld1 = imin(ld1, bE1.z - 1); hd1 = imax(hd1, bE1.w - 1); }
-        lo = imin(lo, imin(li1, ld1)); hi = imax(hi, imax(hi1, hd1));
-        use(aMx, n_mx); use(aMo1, n_mo1); use(aE1, n_i1); use(aE1, n_d1);
-        if (TWO_P) {
-          if (!n_mo2) { li2 = aMo2.x + 1; hi2 = aMo2.y + 1; ld2 = aMo2.x - 1; hd2 = aMo2.y - 1; }
-          if (!n_i2) { li2 = imin(li2, cE2.x + 1); hi2 = imax(hi2, cE2.y + 1); }
-          if (!n_d2) { ld2 = imin(ld2, cE2.z - 1); hd2 = imax(hd2, cE2.w - 1); }
-          lo = imin(lo, imin(li2, ld2)); hi = imax(hi, imax(hi2, hd2));
-          use(aMo2, n_mo2); use(aE2, n_i2); use(aE2, n_d2);
-        }
-        if (!all_src) { fl = INT_MAX; fh = INT_MIN; }
-        if (lo < -plen || hi > tlen) exact = true;
-        const int nblo = (lo + BIAS) >> 6, nbhi = (hi + BIAS) >> 6;
-        if (nbhi - nblo + 1 > nblk) return PAIR_OVERFLOW;
-        const int rowlen = (nbhi - nblo + 1) << 6;
-        if (FULL) { if (s >= P.scap || cell_off + rowlen > P.hcap) return PAIR_OVERFLOW; }
-        /* ring position of the first block */
-        tp += (nblo - tb) << 5; tb = nblo;
-        while (tp >= capw) tp -= capw;
-        while (tp < 0) tp += capw;
-        blo = nblo; bhi = nbhi;
-        /* allocate_output, compute.c:401-486 */
-        const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
-        const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
-        auto src = [&](VSrc& v, const uint32_t* base, const int4& a, bool null_) {
-          v.base = base;
-          if (null_) { v.w0 = INT_MAX; v.span = 0; } else { v.w0 = a.z << 5; v.span = (unsigned)(((a.w - a.z) << 5) + 31); }
-        };
-        auto mslot = [&](int d) { int sl = cm - d; if (sl < 0) sl += P.rm; return rM + sl * capw; };
-        const int e1s = (c1 + 1 == P.r1) ? 0 : c1 + 1;           /* slot of score s - e1 */
-        src(st.mx, mslot(P.dx), aMx, n_mx);
-        src(st.mo1, mslot(P.doe1), aMo1, n_mo1);
-        src(st.i1e, rI1 + e1s * capw, aE1, n_i1);
-        src(st.d1e, rD1 + e1s * capw, aE1, n_d1);
-        if (TWO_P) {
-          const int e2s = (c2 + 1 == P.r2) ? 0 : c2 + 1;
-          src(st.mo2, mslot(P.doe2), aMo2, n_mo2);
-          src(st.i2e, rI2 + e2s * capw, aE2, n_i2);
-          src(st.d2e, rD2 + e2s * capw, aE2, n_d2);
-        }
-        st.oM = rM + cm * capw;
-        st.oI1 = has_i1 ? rI1 + c1 * capw : nullptr;
-        st.oD1 = has_d1 ? rD1 + c1 * capw : nullptr;
-        st.oI2 = has_i2 ? rI2 + c2 * capw : nullptr;
-        st.oD2 = has_d2 ? rD2 + c2 * capw : nullptr;
-        st.exact = exact; st.F = Fn;
-        if (FULL) {
-          st.hrow = vm.h_code + cell_off - 64ll * nblo;
-          if (rank == 0) { HistRow hr; hr.off = cell_off; hr.lo = 64 * nblo - BIAS; hr.pad = 0; vm.hmeta[s] = hr; }
-          cell_off += rowlen;
-        }
-        for (int b = nblo + warp; b <= nbhi; b += NW) {
-          int posb = tp + ((b - nblo) << 5); if (posb >= capw) posb -= capw;
-          if (b >= fl && b <= fh) vec_block<TWO_P, FULL, false>(st, b, posb, lane);
-          else vec_block<TWO_P, FULL, true>(st, b, posb, lane);
-        }
+        plan_step<TWO_P, FULL>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
+      }
+      if (pl.kind == 2) return PAIR_OVERFLOW;
+      exact = pl.exact != 0;
+      tp = pl.tp; tb = pl.nblo; cell_off = pl.cell_off;
+      blo = pl.nblo; bhi = pl.nbhi;
+      for (int c = 0; c < 5; ++c) { clo[c] = pl.lo[c]; chi[c] = pl.hi[c]; }
+      /* the planner may run one score ahead while nothing can invalidate derived ranges */
+      const bool pipelined = NW > 1 && P.heuristic == 0 && !exact;
+      if (pl.kind == 1) {
+        cur_exists = false;
+      } else {
         cur_exists = true;
-        clo[CM] = lo; chi[CM] = hi;
-        clo[CI1] = li1; chi[CI1] = hi1; clo[CD1] = ld1; chi[CD1] = hd1;
-        clo[CI2] = li2; chi[CI2] = hi2; clo[CD2] = ld2; chi[CD2] = hd2;
-        if (!has_i1) { clo[CI1] = 1; chi[CI1] = -1; }
-        if (!has_d1) { clo[CD1] = 1; chi[CD1] = -1; }
-        if (!has_i2) { clo[CI2] = 1; chi[CI2] = -1; }
-        if (!has_d2) { clo[CD2] = 1; chi[CD2] = -1; }
-        if (exact) {
-          gsync<NW>();
-          /* trim_ends, compute.c:571-605: [first in-matrix cell, last in-matrix cell] per component */
-          const bool has[5] = {true, has_i1, has_d1, has_i2, has_d2};
-          for (int c = 0; c < 5; ++c) {
-            const int l = Fn[F_LO + c], h = Fn[F_HI + c];
-            if (has[c] && l != INT_MAX) { clo[c] = l; chi[c] = h; } else { clo[c] = 1; chi[c] = -1; }
-          }
-          if (Fn[F_POISON]) {
-            /* offsets beyond the matrix that the trimmed range no longer covers read as NULL */
-            for (int b = nblo + warp; b <= nbhi; b += NW) {
-              int pos = tp + ((b - nblo) << 5); if (pos >= capw) pos -= capw;
-              pos += lane;
-              const int k0 = 64 * b - BIAS + 2 * lane;
-              if (has_i1) clip_word(st.oI1, pos, k0, clo[CI1], chi[CI1]);
-              if (has_d1) clip_word(st.oD1, pos, k0, clo[CD1], chi[CD1]);
-              if (TWO_P) {
-                if (has_i2) clip_word(st.oI2, pos, k0, clo[CI2], chi[CI2]);
-                if (has_d2) clip_word(st.oD2, pos, k0, clo[CD2], chi[CD2]);
-              }
+        s_exist = s * P.g;
+        for (int b = blo + warp; b <= bhi; b += NW) {
+          int posb = tp + ((b - blo) << 5); if (posb >= capw) posb -= capw;
+          if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false>(cx, pl, Fn, exact, b, posb, lane);
+          else vec_block<TWO_P, FULL, true>(cx, pl, Fn, exact, b, posb, lane);
+        }
+      }
+      if (NW > 1) {
+        if (pipelined && warp == NW - 1) {
+          PlanOut nx;
+          const int ncm = (cm + 1 == P.rm) ? 0 : cm + 1, nc1 = (c1 + 1 == P.r1) ? 0 : c1 + 1;
+          const int nc2 = TWO_P ? ((c2 + 1 == P.r2) ? 0 : c2 + 1) : 0;
+          __syncwarp();                                    /* lane 0's metadata of score s is visible to the warp */
+          plan_step<TWO_P, FULL>(P, vm, plen, tlen, s + 1, ncm, nc1, nc2, tp, tb, cell_off, false, lane == 0, nx);
+          if (lane == 0) vm.plan[(s + 1) & 1] = nx;
+        }
+        have_plan = pipelined;
+      }
+      if (exact && pl.kind == 0) {
+        gsync<NW>();
+        /* trim_ends, compute.c:571-605: [first in-matrix cell, last in-matrix cell] per component */
+        const bool has[5] = {true, pl.oI1 >= 0, pl.oD1 >= 0, TWO_P && pl.oI2 >= 0, TWO_P && pl.oD2 >= 0};
+        for (int c = 0; c < 5; ++c) {
+          const int l = Fn[F_LO + c], h = Fn[F_HI + c];
+          if (has[c] && l != INT_MAX) { clo[c] = l; chi[c] = h; } else { clo[c] = 1; chi[c] = -1; }
+        }
+        if (Fn[F_POISON]) {
+          /* offsets beyond the matrix that the trimmed range no longer covers read as NULL */
+          for (int b = blo + warp; b <= bhi; b += NW) {
+            int pos = tp + ((b - blo) << 5); if (pos >= capw) pos -= capw;
+            pos += lane;
+            const int k0 = 64 * b - BIAS + 2 * lane;
+            if (has[CI1]) clip_word(vm.ring + pl.oI1, pos, k0, clo[CI1], chi[CI1]);
+            if (has[CD1]) clip_word(vm.ring + pl.oD1, pos, k0, clo[CD1], chi[CD1]);
+            if (TWO_P) {
+              if (has[CI2]) clip_word(vm.ring + pl.oI2, pos, k0, clo[CI2], chi[CI2]);
+              if (has[CD2]) clip_word(vm.ring + pl.oD2, pos, k0, clo[CD2], chi[CD2]);
             }
           }
         }
-        if (rank == 0) {
+        if (is_writer) {
+          int4* const mrow = meta + (s & mmask) * 3;
           const bool n0 = clo[CM] > chi[CM];
-          mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], nblo, nbhi);
+          mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], blo, bhi);
           mrow[1] = make_int4(clo[CI1], chi[CI1], clo[CD1], chi[CD1]);
           mrow[2] = make_int4(clo[CI2], chi[CI2], clo[CD2], chi[CD2]);
         }
-        gsync<NW>();
       }
+      gsync<NW>();
     }
     /* unreachable (extend.c:99-106) and the step limit (unialign.c:98-109), in ORIGINAL score
      * units: between two multiples of g every score is a null step of the reference */

@@ -61,7 +61,7 @@ struct PinBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int MAX_TIERS = 8;
+constexpr int MAX_TIERS = 12;
 struct DevCounters {       /* one per batch, in HBM */
   int work[MAX_TIERS];
   int retry[MAX_TIERS];
@@ -76,6 +76,7 @@ struct Staging { PinBuf words, meta; };
 struct Tier {
   int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
   int vec_nw = 0;          /* > 0: packed-halfword tier (wfa_vec.cuh) with vec_nw warps per pair */
+  int max_groups = 0;      /* > 0: at most this many pairs in flight (history arena per pair grows accordingly) */
   int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
   int threads = 128;
   int groups_per_block = 4;
@@ -189,7 +190,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   /* int16 rings hold offsets up to ~tlen + width and nulls that drift by one per step */
   const bool short_reads = 2ll * ((long long)b->maxp + b->maxt) + 4096 < 30000;
   /* register-resident tiers first: gap-affine, no heuristic, instantiated penalty shape, short reads */
-  static const bool no_reg = getenv("WFAGPU_NO_REG_TIER") != nullptr;     /* debugging aid */
+  const bool no_reg = getenv("WFAGPU_NO_REG_TIER") != nullptr;            /* tests / debugging */
   const int winw = b->maxp + b->maxt + 2;       /* sequence windows: one word per base */
   if (!no_reg && !b->two_p && k.heuristic == 0 && std::max(b->maxp, b->maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
     const int first = std::max(b->maxp, b->maxt) <= 192 ? 2 : 4;
@@ -205,14 +206,15 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   /* packed-halfword tiers (wfa_vec.cuh): everything the register tier does not take, reads up to
    * VEC_MAX_LEN; warp per pair first, then 8 and 16 warps per pair with the widest rings that
    * leave two / one CTA per SM */
-  static const bool no_vec = getenv("WFAGPU_NO_VEC_TIER") != nullptr;     /* debugging aid */
+  const bool no_vec = getenv("WFAGPU_NO_VEC_TIER") != nullptr;            /* tests / debugging */
   bool vec_covers_smem = false;
   if (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN) {
     const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
-    const long long fixed = (long long)k.mr * 48 + 256 + 4ll * seqw;
+    const long long fixed0 = (long long)k.mr * 48 + 256 + 4ll * seqw;
     const long long nblk_max = (wmax + 63) / 64 + 1;
     long long last_nblk = 0;
     auto add_vec = [&](int nw, long long budget, long long hcap, long long scap) {
+      const long long fixed = fixed0 + (nw > 1 ? 512 : 0);      /* step plans of the planner warp */
       long long nblk = (budget - fixed) / ((long long)nslots * 128);
       nblk = std::min(nblk, nblk_max);
       if (nblk < 2 || nblk <= last_nblk) return;
@@ -229,10 +231,14 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
       last_nblk = nblk;
       if (nblk == nblk_max) vec_covers_smem = true;
     };
-    add_vec(1, 11264, 2ll << 20, 16384);
-    if (last_nblk == 0) add_vec(1, 22528, 2ll << 20, 16384);
-    add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768);
-    add_vec(16, smem_max - 1024, 64ll << 20, 65536);
+    const char* only_e = getenv("WFAGPU_VEC_NW");                          /* tests: push everything through one group size */
+    const int only = only_e ? atoi(only_e) : 0;
+    if (!only || only == 1) {
+      add_vec(1, 11264, 2ll << 20, 16384);
+      if (last_nblk == 0) add_vec(1, 22528, 2ll << 20, 16384);
+    }
+    if (!only || only == 8) add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768);
+    if (!only || only == 16) add_vec(16, smem_max - 1024, 64ll << 20, 65536);
   }
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
@@ -289,6 +295,12 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     t.hcap = cells_bound;
     t.scap = (int)std::min<long long>(2 * scap_bound, INT_MAX / 4);
     b->tiers.push_back(t);
+    if (b->full) {
+      /* scope=full: the origin bytes of a 100 kbp pair need ~10 GB; pairs whose history outgrows
+       * an even split of the free HBM are redone with fewer pairs in flight */
+      t.max_groups = 12; b->tiers.push_back(t);
+      t.max_groups = 2; b->tiers.push_back(t);
+    }
   }
   for (auto& t : b->tiers) {
     int bps = t.regs ? reg_occupancy(t.regs, b->full, t.threads, t.smem)
@@ -591,6 +603,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         groups = (long long)blocks * t.groups_per_block;
       } else {
         blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
+        if (t.max_groups) blocks = std::min(blocks, t.max_groups);
         groups = blocks;
       }
       k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
@@ -803,15 +816,29 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   CK(ctx->pin_small.ensure(512));
   if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->pin_runs.as<uint32_t>(); }
   const double t_start = now_ms();
-  /* chunking: enough chunks to overlap packing with the GPU, big enough to fill it */
-  int64_t chunk = n;
+  /* chunking: enough chunks to overlap packing with the GPU, big enough to fill it; the first
+   * chunk is small so that the GPU starts early (its packing is the only one nothing overlaps) */
+  std::vector<int64_t> starts;           /* chunk c covers pairs [starts[c], starts[c+1]) */
   {
     const char* e = getenv("WFAGPU_CHUNK");
     const int64_t want = e ? atoll(e) : 0;
+    int64_t chunk = n;
     if (want > 0) chunk = want;
     else if (n >= 524288) chunk = std::max<int64_t>(262144, (n + 7) / 8);
+    int64_t first = chunk;
+    if (want <= 0 && n >= 524288) first = std::min<int64_t>(chunk, std::max<int64_t>(131072, n / 40));
+    starts.push_back(0);
+    /* ramp up by 1.5x per chunk: packing chunk c+1 must not take longer than the GPU needs for chunk c */
+    int64_t cur = first;
+    for (int64_t off = std::min(first, n); off < n;) {
+      starts.push_back(off);
+      cur = std::min<int64_t>(chunk, cur + cur / 2);
+      off += cur;
+    }
+    starts.push_back(n);
+    if (n == 0) starts.assign({0, 0});
   }
-  const int64_t nchunks = n == 0 ? 1 : (n + chunk - 1) / chunk;
+  const int64_t nchunks = (int64_t)starts.size() - 1;
   wfagpu_batch* shells[2] = {batch_acquire(ctx), nchunks > 1 ? batch_acquire(ctx) : nullptr};
   std::mutex mu;
   std::condition_variable cv;
@@ -829,7 +856,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   };
   auto gpu_side = [&](int64_t c) -> int {
     wfagpu_batch* b = shells[c & 1];
-    const int64_t off = c * chunk;
+    const int64_t off = starts[c];
     int r;
     const double g0 = now_ms();
     CK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[c & 1], 0));
@@ -879,7 +906,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     auto out_bytes = [&](int64_t m, bool full) { return (size_t)(full ? 8 * (m + 1) + 24 * m : 8 * m) + 64; };
     auto gpu_side_async = [&](int64_t c) -> int {
       wfagpu_batch* b = shells[c & 1];
-      const int64_t off = c * chunk;
+      const int64_t off = starts[c];
       const double g0 = now_ms();
       CK(cudaStreamWaitEvent(ctx->stream, ctx->uploaded[c & 1], 0));
       CK(cudaStreamWaitEvent(ctx->stream, ctx->d2h_done[c & 1], 0));   /* chunk c-2 left this shell's result buffers */
@@ -995,7 +1022,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
         cv.wait(lk, [&] { return consumed + 2 > c || err != WFAGPU_OK; });   /* staging slot c&1 is free */
         if (err != WFAGPU_OK) break;
       }
-      const int64_t off = c * chunk, m = std::min(chunk, n - off);
+      const int64_t off = starts[c], m = starts[c + 1] - off;
       const double t0 = now_ms();
       int r = batch_pack(ctx, shells[c & 1], ctx->staging[c & 1], cfg, seq, p_off + off, p_len + off,
                          t_off + off, t_len + off, m, off);

@@ -1,0 +1,5 @@
+( timeout 1200 python -m pytest tests -x -q -m gpu 2>&1 ) | tail -8
+timeout 600 python bench.py --workload cfg1 --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | grep -E "device-resident|e2e:" | tail -3
+timeout 600 python bench.py --workload cfg2 --steps 2 --warmup 3 --no-cpu-baseline 2>&1 | grep -E "device-resident|e2e:" | tail -3
+export WFAGPU_TRACE=1
+timeout 500 python scripts/long_reads.py 16 2>&1 | grep -v "tier [0-4] " | tail -12

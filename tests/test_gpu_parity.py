@@ -70,6 +70,72 @@ def test_parity_ragged_and_empty(gpu_ctx, oracle):
         assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"ragged {kw}")
 
 
+def _ragged_pairs(seed, n, lo_len, hi_len):
+    """Pairs of unequal lengths: a pattern, and a text that embeds a mutated copy of part of it
+    between random flanks (or is unrelated), so that wavefronts run along the matrix borders."""
+    rng = np.random.default_rng(seed)
+    acgt = "ACGT"
+    rnd = lambda m: "".join(acgt[i] for i in rng.integers(0, 4, m))
+    pairs = []
+    for _ in range(n):
+        lp = int(rng.integers(lo_len, hi_len))
+        p = rnd(lp)
+        mode = rng.integers(0, 4)
+        if mode == 0:
+            t = rnd(int(rng.integers(lo_len, hi_len)))
+        else:
+            a, b = sorted(int(x) for x in rng.integers(0, lp + 1, 2))
+            core = list(p[a:b])
+            for j in range(len(core)):
+                if rng.random() < 0.08:
+                    core[j] = rnd(1) if rng.random() < 0.6 else ("" if rng.random() < 0.5 else core[j] + rnd(int(rng.integers(1, 6))))
+            t = rnd(int(rng.integers(0, 60))) + "".join(core) + rnd(int(rng.integers(0, 60)))
+        if mode == 3:
+            p, t = t, p
+        pairs.append((p, t))
+    return pairs
+
+
+VEC_KW = [
+    dict(span="end-to-end"),
+    dict(),
+    dict(distance="affine2p", span="end-to-end"),
+    dict(distance="affine2p", scope="score"),
+    dict(pattern_begin_free=3, pattern_end_free=5, text_begin_free=4, text_end_free=6),
+    dict(distance="affine2p", text_begin_free=8, text_end_free=8),
+    dict(span="end-to-end", mismatch=3, gap_opening=1, gap_extension=1),
+    dict(span="end-to-end", match=-1),
+    dict(heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=10, steps_between_cutoffs=2),
+    dict(heuristic="X-drop", xdrop=60, steps_between_cutoffs=1, distance="affine2p"),
+    dict(span="end-to-end", max_steps=40),
+]
+
+
+@pytest.mark.parametrize("nw", ["1", "8", "16"])
+def test_vec_tier_every_group_size(gpu_ctx, oracle, monkeypatch, nw):
+    """The packed-halfword tier with one warp, 8 warps and 16 warps per pair (normally picked by
+    wavefront width) on inputs that live on the matrix borders: unequal lengths, free ends,
+    cut-offs, step limits -- the paths where ranges are scanned instead of derived."""
+    monkeypatch.setenv("WFAGPU_NO_REG_TIER", "1")
+    monkeypatch.setenv("WFAGPU_VEC_NW", nw)
+    ragged = _ragged_pairs(int(nw), 500, 8, 260)
+    tiny = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C")]
+    batch_all = pairs_from_strings(tiny + ragged)
+    batch_long = pairs_from_strings([pt for pt in ragged if min(len(pt[0]), len(pt[1])) >= 8])    # free ends must fit
+    for kw in VEC_KW:
+        batch = batch_long if any(k.endswith("_free") for k in kw) else batch_all
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = gpu_ctx.align_batch(cfg, *batch)
+        assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"vec nw={nw} {kw}")
+    synth = generate_pairs(300, 400, 0.12, seed=17 + int(nw))
+    for kw in (dict(span="end-to-end"), dict(distance="affine2p"), dict(heuristic="adaptive", span="end-to-end")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *synth, kind="port")
+        got = gpu_ctx.align_batch(cfg, *synth)
+        assert_same(got, want, what=f"vec nw={nw} synthetic {kw}")
+
+
 def _check_cigar(runs, pattern, text, x, o1, e1, o2, e2):
     """cigar_check_alignment + cigar_score of the reference (W/alignment/cigar.c:277-345, :617-690)
     restated for RLE runs: the CIGAR must spell the two sequences, and returns its gap-affine-2p cost."""
