@@ -153,6 +153,14 @@ WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
 WFA_DEV int first_set(uint32_t x) { return __builtin_ctz(x); }
 WFA_DEV int last_set(uint32_t x) { return 31 - __builtin_clz(x); }
 #endif
+/* load that bypasses the (non-coherent) L1: data another CTA of the same pair may have written */
+template <class T> WFA_DEV T ld_cg(const T* p) {
+#ifdef __CUDA_ARCH__
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 WFA_DEV int imax(int a, int b) { return a > b ? a : b; }
 WFA_DEV int imin(int a, int b) { return a < b ? a : b; }
 
@@ -199,9 +207,10 @@ struct Src {
   const OffT* slot;  /* ring slot base (circular: element of diagonal k is slot[k & wmask]) */
   int lo, hi;        /* valid range; lo > hi = null */
 };
-template <class OffT>
+template <bool CG, class OffT>
 WFA_DEV int rd(const Src<OffT>& s, int k, int km) {
-  return (k >= s.lo && k <= s.hi) ? (int)s.slot[km] : OFFNULL;
+  if (!(k >= s.lo && k <= s.hi)) return OFFNULL;
+  return CG ? (int)ld_cg(s.slot + km) : (int)s.slot[km];
 }
 
 /* ---- CIGAR run emitter (one thread); runs are produced in CIGAR order ----------------- */
@@ -267,8 +276,9 @@ WFA_DEV int backtrace_codes(const KParams& P, const uint8_t* h_code, const HistR
                             FwdEmitter& em) {
   int mt = CM, score = a_score, k = a_k, nops = 0;
   while (score > 0) {
-    const HistRow hm = hmeta[score];
-    const int code = h_code[hm.off + (k - hm.lo)];
+    HistRow hm;
+    hm.off = ld_cg(&hmeta[score].off); hm.lo = ld_cg(&hmeta[score].lo);
+    const int code = ld_cg(h_code + hm.off + (k - hm.lo));
     int type;
     if (mt == CM) type = code & 15;
     else if (mt == CI1) type = (code & 0x10) ? BT_I1_EXT : BT_I1_OPEN;
@@ -327,8 +337,10 @@ WFA_DEV bool term_cell(const KParams& P, int plen, int tlen, int ak, int k, int 
 
 /* ------------------------------------------------------------------------------------ */
 /*
- * Align one pair with the thread group `g`.  G provides: rank, size, sync(),
- * template<int N> allmin(int (&v)[N]).
+ * Align one pair with the thread group `g`.  G provides: rank, size (over the whole group),
+ * lrank, lsize (within the CTA: the metadata ring is per CTA), sync() (group), lsync() (CTA),
+ * template<int N> allmin(int (&v)[N]) (group-wide, implies sync) and kGrid (group spans CTAs:
+ * ring data comes from other SMs and must bypass L1).
  * Returns PAIR_DONE (res filled; for scope=full the runs are in gm.runs_stage, in CIGAR order)
  * or PAIR_OVERFLOW (a tier capacity was exceeded; retry on a larger tier).
  */
@@ -360,7 +372,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     const int lo = ef ? -P.pbf : 0, hi = ef ? P.tbf : 0;
     if (hi - lo + 1 > wcap) return PAIR_OVERFLOW;
     /* every metadata slot starts null: scores < 0 read as the null wavefront */
-    for (int i = g.rank; i < P.mr * NC; i += g.size) meta[i] = make_int4(1, -1, 0, 0);
+    for (int i = g.lrank; i < P.mr * NC; i += g.lsize) meta[i] = make_int4(1, -1, 0, 0);
     g.sync();
     int t = KNONE;
     OffT* const mslot = gm.ring[CM];
@@ -375,8 +387,8 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     term_k = r[0];
     for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
     clo[CM] = lo; chi[CM] = hi;
-    if (g.rank == 0) meta[CM] = make_int4(lo, hi, 0, 1);
-    g.sync();
+    if (g.lrank == 0) meta[CM] = make_int4(lo, hi, 0, 1);
+    g.lsync();
   }
 
   for (;;) {
@@ -384,7 +396,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     if (cur_exists) {
       if (term_k != KNONE) {
         end_k = term_k;
-        end_off = (int)gm.ring[CM][cm * wcap + (term_k & wmask)];
+        end_off = (int)ld_cg(gm.ring[CM] + cm * wcap + (term_k & wmask));
         status = 1; end_score = s * P.g;
         cells += imax(0, chi[CM] - clo[CM] + 1);
         break;
@@ -400,7 +412,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
             if (hi_base - lo_base + 1 >= P.min_wf_len) {
               int dm = INT_MAX;
               for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-                const int f = (int)mslot[k & wmask];
+                const int f = G::kGrid ? (int)ld_cg(mslot + (k & wmask)) : (int)mslot[k & wmask];
                 const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
                 dm = imin(dm, d);
               }
@@ -409,7 +421,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
               const int min_d = imin(imax(plen, tlen), r1[0]);
               int kf = INT_MAX, kl = INT_MIN;
               for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-                const int f = (int)mslot[k & wmask];
+                const int f = G::kGrid ? (int)ld_cg(mslot + (k & wmask)) : (int)mslot[k & wmask];
                 const int d = (f >= 0) ? imax(plen - (f - k), tlen - f) : (1 << 30);
                 if (d - min_d <= P.max_dist_thr) { kf = imin(kf, k); kl = imax(kl, k); }
               }
@@ -429,7 +441,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
             const int so = s * P.g;
             int cmax = INT_MIN, kf = INT_MAX, kl = INT_MIN;
             for (int k = lo_base + g.rank; k <= hi_base; k += g.size) {
-              const int f = (int)mslot[k & wmask];
+              const int f = G::kGrid ? (int)ld_cg(mslot + (k & wmask)) : (int)mslot[k & wmask];
               if (f < 0) continue;
               const int sw = (swg * (2 * f - k) - so) / 2;
               cmax = imax(cmax, sw);
@@ -455,7 +467,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
             if (clo[CM] > clo[c]) clo[c] = clo[CM];
             if (chi[CM] < chi[c]) chi[c] = chi[CM];
           }
-          if (g.rank == 0) {
+          if (g.lrank == 0) {
             int4* const mrow = meta + (s & mmask) * NC;
             for (int c = 0; c < NC; ++c) {
               const bool nn = clo[c] <= chi[c];
@@ -497,8 +509,8 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         cur_exists = false;
         for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
         term_k = KNONE;
-        for (int c = g.rank; c < NC; c += g.size) mrow[c] = make_int4(1, -1, 0, 0);
-        g.sync();
+        for (int c = g.lrank; c < NC; c += g.lsize) mrow[c] = make_int4(1, -1, 0, 0);
+        g.lsync();
       } else {
         s_exist = s * P.g;
         Src<OffT> sMx, sMo1, sI1, sD1, sMo2, sI2, sD2;
@@ -537,15 +549,15 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         for (int i = 0; i < 2 * 5 + 1; ++i) red[i] = INT_MAX;
         for (int k = lo + g.rank; k <= hi; k += g.size) {
           const int km = k & wmask, kl = (k - 1) & wmask, kr = (k + 1) & wmask;
-          const int i1o = rd(sMo1, k - 1, kl), i1e = rd(sI1, k - 1, kl);
-          const int d1o = rd(sMo1, k + 1, kr), d1e = rd(sD1, k + 1, kr);
-          const int mis = rd(sMx, k, km) + 1;
+          const int i1o = rd<G::kGrid>(sMo1, k - 1, kl), i1e = rd<G::kGrid>(sI1, k - 1, kl);
+          const int d1o = rd<G::kGrid>(sMo1, k + 1, kr), d1e = rd<G::kGrid>(sD1, k + 1, kr);
+          const int mis = rd<G::kGrid>(sMx, k, km) + 1;
           const int ins1 = imax(i1o, i1e) + 1, del1 = imax(d1o, d1e);
           int ins = ins1, del = del1;
           int i2o = OFFNULL, i2e = OFFNULL, d2o = OFFNULL, d2e = OFFNULL, ins2 = OFFNULL, del2 = OFFNULL;
           if (TWO_P) {
-            i2o = rd(sMo2, k - 1, kl); i2e = rd(sI2, k - 1, kl);
-            d2o = rd(sMo2, k + 1, kr); d2e = rd(sD2, k + 1, kr);
+            i2o = rd<G::kGrid>(sMo2, k - 1, kl); i2e = rd<G::kGrid>(sI2, k - 1, kl);
+            d2o = rd<G::kGrid>(sMo2, k + 1, kr); d2e = rd<G::kGrid>(sD2, k + 1, kr);
             ins2 = imax(i2o, i2e) + 1; del2 = imax(d2o, d2e);
             ins = imax(ins1, ins2); del = imax(del1, del2);
           }
@@ -596,7 +608,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           else { clo[c] = 1; chi[c] = -1; }
         }
         cur_exists = true;
-        for (int c = g.rank; c < NC; c += g.size) {
+        for (int c = g.lrank; c < NC; c += g.lsize) {
           /* lane c publishes component c */
           int l = clo[0], h = chi[0], z = cm;
           if (c == 1) { l = clo[1]; h = chi[1]; z = c1; }
@@ -611,7 +623,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           if (g.rank == 0) { HistRow hr; hr.off = cell_off; hr.lo = lo; hr.pad = 0; gm.hmeta[s] = hr; }
           cell_off += width;
         }
-        g.sync();
+        g.lsync();          /* ring stores were made visible by the barrier inside allmin */
       }
     }
     /* unreachable (extend.c:99-106: M[s] missing and num_null_steps > max_score_scope) and the

@@ -28,8 +28,10 @@ constexpr int MAX_RED = 11;
 
 /* ---- thread groups ------------------------------------------------------------------ */
 struct WarpGroup {
-  int rank, size;
+  static constexpr bool kGrid = false;
+  int rank, size, lrank, lsize;
   __device__ __forceinline__ void sync() { __syncwarp(); }
+  __device__ __forceinline__ void lsync() { __syncwarp(); }
   template <int N>
   __device__ __forceinline__ void allmin(int (&v)[N]) {
 #pragma unroll
@@ -40,10 +42,12 @@ struct WarpGroup {
 };
 
 struct BlockGroup {
-  int rank, size;
+  static constexpr bool kGrid = false;
+  int rank, size, lrank, lsize;
   int* red;        /* 2 * MAX_RED * 32 ints of shared memory */
   int parity;
   __device__ __forceinline__ void sync() { __syncthreads(); }
+  __device__ __forceinline__ void lsync() { __syncthreads(); }
   template <int N>
   __device__ __forceinline__ void allmin(int (&v)[N]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -88,11 +92,11 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
   int group_id;
   unsigned char* base;
   if (BLOCK) {
-    g.rank = threadIdx.x; g.size = blockDim.x;
+    g.rank = threadIdx.x; g.size = blockDim.x; g.lrank = g.rank; g.lsize = g.size;
     group_id = blockIdx.x;
     base = smem_raw;
   } else {
-    g.rank = threadIdx.x & 31; g.size = 32;
+    g.rank = threadIdx.x & 31; g.size = 32; g.lrank = g.rank; g.lsize = 32;
     const int wpb = blockDim.x >> 5;
     group_id = blockIdx.x * wpb + (threadIdx.x >> 5);
     base = smem_raw + (size_t)(threadIdx.x >> 5) * P.group_bytes;
@@ -163,6 +167,180 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
           if (nr > P.runcap || (unsigned long long)(rbase + nr) > P.runs_tmp_cap) { st = ST_OOM; nr = 0; }
           g.sync();
           for (int i = g.rank; i < nr; i += g.size) P.runs_tmp[rbase + i] = gm.runs_stage[i];
+        } else if (nr < 0) { st = ST_OOM; nr = 0; }
+        if (g.rank == 0) {
+          P.score[pid] = res.score; P.status[pid] = st;
+          int4 l = make_int4(res.locs[0], res.locs[1], res.locs[2], res.locs[3]);
+          if (nr == 0) l = make_int4(0, 0, 0, 0);
+          reinterpret_cast<int4*>(P.locs)[pid] = l;
+          P.nruns[pid] = nr; P.runs_base[pid] = rbase;
+        }
+      } else if (g.rank == 0) {
+        P.score[pid] = res.score; P.status[pid] = res.status;
+      }
+    }
+    g.sync();
+  }
+  if (g.rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
+}
+
+/* ---- several CTAs per pair (long reads): the group spans `ncta` co-resident CTAs ------------ */
+/*
+ * 100 kbp pairs have wavefronts of up to 2*10^5 diagonals and ~10 GB of origin bytes each, so only
+ * about a dozen pairs fit in HBM at a time: one CTA per pair would leave 90 % of the SMs idle.
+ * Here the diagonals of one wavefront are dealt over all threads of `ncta` CTAs (cooperative
+ * launch, so they are co-resident); the offset rings live in an L2-resident HBM arena and are
+ * read with ld.global.cg; one software barrier per score (inside the min-reduction that trims
+ * the wavefront) orders the ring stores of score s before the loads of score s+1.
+ */
+struct GridScratch {            /* one per group, in HBM, zero-initialised by the host before the launch */
+  unsigned int count;           /* barrier arrivals, monotonic */
+  int slot;                     /* broadcast value */
+  long long slot_ll;
+  int red[3][MAX_RED + 1];      /* three rotating reduction sets */
+};
+
+struct GridGroup {
+  static constexpr bool kGrid = true;
+  int rank, size, lrank, lsize;
+  int* red;                     /* 2 * MAX_RED * 32 ints of shared memory (CTA-level reduction) */
+  int parity;
+  GridScratch* gs;
+  unsigned int target;          /* arrivals that complete the next barrier */
+  int ncta, phase;
+  __device__ __forceinline__ void lsync() { __syncthreads(); }
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (lrank == 0) {
+      __threadfence();
+      atomicAdd(&gs->count, 1u);
+      target += (unsigned int)ncta;
+      while ((int)(*reinterpret_cast<volatile unsigned int*>(&gs->count) - target) < 0) { }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+  template <int N>
+  __device__ __forceinline__ void allmin(int (&v)[N]) {
+    /* CTA level */
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int* buf = red + parity * (MAX_RED * 32);
+    parity ^= 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const int r = __reduce_min_sync(0xffffffffu, v[i]);
+      if (lane == 0) buf[i * 32 + warp] = r;
+    }
+    __syncthreads();
+    /* group level: warp 0 folds the CTA's minima into the group's reduction set */
+    int* const gred = gs->red[phase];
+    if (warp == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int t = (lane < nw) ? buf[i * 32 + lane] : INT_MAX;
+        const int r = __reduce_min_sync(0xffffffffu, t);
+        if (lane == 0 && r != INT_MAX) atomicMin(&gred[i], r);
+      }
+    }
+    sync();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = ld_cg(&gred[i]);
+    /* the set used two reductions from now was last read before the barrier above */
+    {
+      int* const nxt = gs->red[phase == 0 ? 2 : phase - 1];
+      if (rank < MAX_RED) nxt[rank] = INT_MAX;
+      phase = (phase == 2) ? 0 : phase + 1;
+    }
+  }
+  __device__ __forceinline__ int bcast(int v) {
+    if (rank == 0) *reinterpret_cast<volatile int*>(&gs->slot) = v;
+    sync();
+    const int r = ld_cg(&gs->slot);
+    sync();
+    return r;
+  }
+  __device__ __forceinline__ long long bcastll(long long v) {
+    if (rank == 0) *reinterpret_cast<volatile long long*>(&gs->slot_ll) = v;
+    sync();
+    const long long r = ld_cg(&gs->slot_ll);
+    sync();
+    return r;
+  }
+};
+
+template <bool TWO_P, bool FULL>
+__global__ void __launch_bounds__(512, 1) wfa_grid_kernel(const __grid_constant__ KParams P, GridScratch* scratch, int ncta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NC = TWO_P ? 5 : 3;
+  GridGroup g;
+  const int group_id = blockIdx.x / ncta, cta = blockIdx.x % ncta;
+  g.lrank = threadIdx.x; g.lsize = blockDim.x;
+  g.rank = cta * blockDim.x + threadIdx.x; g.size = ncta * blockDim.x;
+  g.red = reinterpret_cast<int*>(smem_raw + P.group_bytes); g.parity = 0;
+  g.gs = scratch + group_id; g.target = 0; g.ncta = ncta; g.phase = 0;
+
+  GroupMem<int32_t> gm;
+  gm.meta = reinterpret_cast<int4*>(smem_raw);
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(smem_raw + (size_t)P.mr * NC * 16);
+  int32_t* ringbase = reinterpret_cast<int32_t*>(P.gring) + (long long)group_id * P.gring_elems;
+  gm.ring[CM] = ringbase;
+  gm.ring[CI1] = gm.ring[CM] + P.rm * P.wcap;
+  gm.ring[CD1] = gm.ring[CI1] + P.r1 * P.wcap;
+  gm.ring[CI2] = gm.ring[CD1] + P.r1 * P.wcap;
+  gm.ring[CD2] = gm.ring[CI2] + (TWO_P ? P.r2 * P.wcap : 0);
+  if (FULL) {
+    gm.h_code = P.hist_code + (long long)group_id * P.hcap;
+    gm.ops = P.rops + (long long)group_id * P.ropcap; gm.opcap = P.ropcap;
+    gm.hmeta = P.hmeta + (long long)group_id * P.scap;
+    gm.runs_stage = P.runs_stage + (long long)group_id * P.runcap;
+  } else {
+    gm.h_code = nullptr; gm.hmeta = nullptr; gm.runs_stage = nullptr; gm.ops = nullptr; gm.opcap = 0;
+  }
+  /* the host zeroed the scratch (barrier count); the reduction sets start at +inf */
+  if (g.rank < 3 * (MAX_RED + 1)) (&g.gs->red[0][0])[g.rank] = INT_MAX;
+  g.sync();
+  const int n_work = *P.n_work;
+  long long cells_acc = 0;
+  for (;;) {
+    int w = 0;
+    if (g.rank == 0) w = atomicAdd(P.work_counter, 1);
+    w = g.bcast(w);
+    if (w >= n_work) break;
+    const int pid = P.worklist ? P.worklist[w] : w;
+    const PairMeta pm = P.pairs[pid];
+    const int plen = pm.plen, tlen = pm.tlen;
+    const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+    int rc;
+    PairResult res;
+    if (P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) {
+      rc = PAIR_OVERFLOW;
+    } else {
+      const uint32_t* gw = P.words + pm.woff;
+      if (P.seq_words_cap > 0) {
+        uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
+        for (int i = g.lrank; i < pwn; i += g.lsize) sp[i] = gw[i];
+        for (int i = g.lrank; i < twn; i += g.lsize) st[i] = gw[pwn + i];
+        if (g.lrank == 0) { sp[pwn] = 0; st[twn] = 0; }
+        gm.pw = sp; gm.tw = st;
+      } else {
+        gm.pw = gw; gm.tw = gw + pwn;
+      }
+      g.lsync();
+      rc = align_pair<GridGroup, int32_t, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+    }
+    if (rc == PAIR_OVERFLOW) {
+      if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
+    } else {
+      cells_acc += res.cells;
+      if (FULL) {
+        int nr = g.bcast(res.nruns);
+        long long rbase = 0;
+        int st = res.status;
+        if (nr > 0) {
+          if (g.rank == 0) rbase = (long long)atomicAdd(P.runs_cursor, (unsigned long long)nr);
+          rbase = g.bcastll(rbase);
+          if (nr > P.runcap || (unsigned long long)(rbase + nr) > P.runs_tmp_cap) { st = ST_OOM; nr = 0; }
+          for (int i = g.rank; i < nr; i += g.size) P.runs_tmp[rbase + i] = ld_cg(gm.runs_stage + i);
         } else if (nr < 0) { st = ST_OOM; nr = 0; }
         if (g.rank == 0) {
           P.score[pid] = res.score; P.status[pid] = st;
@@ -547,6 +725,28 @@ static cudaError_t init_reg(int smem_optin) {
   return e;
 }
 
+/* several CTAs per pair: cooperative launch of groups * ncta CTAs; scratch = groups zeroed GridScratch */
+size_t grid_scratch_bytes(int groups) { return sizeof(GridScratch) * (size_t)groups; }
+
+cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int ncta, size_t smem, void* scratch, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(scratch, 0, grid_scratch_bytes(groups), st);
+  if (e != cudaSuccess) return e;
+  KParams Pc = P;
+  GridScratch* gs = static_cast<GridScratch*>(scratch);
+  void* args[3] = {&Pc, &gs, &ncta};
+  const void* fn = two_p ? (full ? (const void*)wfa_grid_kernel<true, true> : (const void*)wfa_grid_kernel<true, false>)
+                         : (full ? (const void*)wfa_grid_kernel<false, true> : (const void*)wfa_grid_kernel<false, false>);
+  return cudaLaunchCooperativeKernel(fn, dim3(groups * ncta), dim3(512), args, smem, st);
+}
+
+static cudaError_t init_grid(int smem_optin) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(wfa_grid_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(wfa_grid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(wfa_grid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(wfa_grid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
+}
+
 /* packed-halfword tier: NW = 1 (warp per pair), 8 or 16 warps per pair */
 #define WFA_VEC_DISPATCH(STMT)                                                          \
   do {                                                                                  \
@@ -609,7 +809,9 @@ cudaError_t init_kernels(int smem_optin) {
         }
   const cudaError_t e = init_reg(smem_optin);
   if (e != cudaSuccess) return e;
-  return init_vec(smem_optin);
+  const cudaError_t e2 = init_vec(smem_optin);
+  if (e2 != cudaSuccess) return e2;
+  return init_grid(smem_optin);
 }
 
 size_t block_reduce_smem_bytes() { return 2 * MAX_RED * 32 * sizeof(int); }

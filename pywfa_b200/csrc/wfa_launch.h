@@ -24,6 +24,11 @@ int reg_occupancy(int regs, bool full, int block, size_t smem);
 cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int grid, int block, size_t smem, cudaStream_t st);
 int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem);
 
+/* several CTAs per pair (long reads): groups * ncta co-resident CTAs of 512 threads; `scratch` holds
+ * grid_scratch_bytes(groups) bytes of device memory */
+size_t grid_scratch_bytes(int groups);
+cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int ncta, size_t smem, void* scratch, cudaStream_t st);
+
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
  * last one); otherwise gather into cig_off[n+1] (values offset by cig_base) / runs_out. */
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,

@@ -110,7 +110,7 @@ struct wfagpu_ctx {
   std::vector<wfagpu_batch*> spare;
   int64_t last_launches = 0;
   /* per-run scratch shared by all batches of this context (grow-only) */
-  DevBuf hist_code, hmeta, runs_stage, gring, rhist, rops;
+  DevBuf hist_code, hmeta, runs_stage, gring, rhist, rops, gscratch;
 };
 
 struct wfagpu_batch {
@@ -294,6 +294,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     t.smem = (size_t)t.group_bytes + block_reduce_smem_bytes();
     t.hcap = cells_bound;
     t.scap = (int)std::min<long long>(2 * scap_bound, INT_MAX / 4);
+    if (b->full) t.max_groups = 64;
     b->tiers.push_back(t);
     if (b->full) {
       /* scope=full: the origin bytes of a 100 kbp pair need ~10 GB; pairs whose history outgrows
@@ -449,7 +450,7 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   for (wfagpu_batch* b : ctx->spare) batch_release(b);
   ctx->spare.clear();
   ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
-  ctx->rhist.release(); ctx->rops.release();
+  ctx->rhist.release(); ctx->rops.release(); ctx->gscratch.release();
   cudaStreamDestroy(ctx->stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->d2h_stream);
@@ -598,6 +599,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       KParams k = b->kp;
       long long groups;
       int blocks;
+      int grid_ctas = 1;
       if (t.mode == 0) {
         blocks = (int)std::min<long long>((nwork + t.groups_per_block - 1) / t.groups_per_block, (long long)ctx->sms * t.blocks_per_sm);
         groups = (long long)blocks * t.groups_per_block;
@@ -605,6 +607,12 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         blocks = (int)std::min<long long>(nwork, (long long)ctx->sms * t.blocks_per_sm);
         if (t.max_groups) blocks = std::min(blocks, t.max_groups);
         groups = blocks;
+        if (t.mode == 2) {
+          /* several CTAs per pair: all SMs work even when only a few pairs fit in HBM */
+          groups = std::min<long long>(groups, ctx->sms);
+          grid_ctas = std::max(1, ctx->sms / (int)groups);
+          blocks = (int)groups;
+        }
       }
       k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
       k.hcap = t.hcap; k.scap = t.scap;
@@ -652,13 +660,17 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       const double tier_t0 = trace_on() ? now_ms() : 0;
       if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
       else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, blocks, t.threads, t.smem, st));
+      else if (t.mode == 2) {
+        CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
+        CK(launch_grid(k, b->two_p, b->full, (int)groups, grid_ctas, t.smem, ctx->gscratch.p, st));
+      }
       else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
       b->stats.kernel_launches++;
       CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (trace_on())
         fprintf(stderr, "[wfagpu]   tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d): %lld pairs in, %d overflowed, %.2f ms\n",
-                ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks, t.threads,
+                ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
                 nwork, hc->retry[ti], now_ms() - tier_t0);
       nwork = hc->retry[ti];
       if (ti == 0) b->stats.retried_pairs = nwork;

@@ -19,8 +19,10 @@
 using namespace wfagpu;
 
 struct EmuGroup {
-  int rank = 0, size = 1;
+  static constexpr bool kGrid = false;
+  int rank = 0, size = 1, lrank = 0, lsize = 1;
   void sync() {}
+  void lsync() {}
   template <int N> void allmin(int (&)[N]) {}
 };
 
