@@ -36,12 +36,20 @@ WORKLOADS = {
     "cfg2": (10_000_000, 250, 0.10, 0, dict(span="end-to-end", scope="score")),
     "cfg3": (100_000, 1000, 0.10, 0, dict(distance="affine2p", span="ends-free", scope="full")),
     "cfg4-adaptive": (20_000, 10_000, 0.15, 0, dict(span="end-to-end", scope="full", heuristic="adaptive")),
+    "cfg4-xdrop": (20_000, 10_000, 0.15, 0, dict(span="end-to-end", scope="full", heuristic="X-drop", xdrop=20)),
+    "cfg4-none": (2_000, 10_000, 0.15, 0, dict(span="end-to-end", scope="full")),
+    "cfg5": (16, 100_000, 0.20, 0, dict(distance="affine2p", span="end-to-end", scope="full")),
 }
+# pywfa pairs/s per host core (survey measurements), used to size the bounded CPU samples
+REF_PER_CORE = {"cfg1": 90_000, "cfg2": 25_000, "cfg3": 280, "cfg4-adaptive": 120, "cfg4-xdrop": 20_000, "cfg4-none": 1.5, "cfg5": 0.005}
 WORKLOAD_DESC = {
     "cfg1": "1M synthetic 150 bp pairs, 5% divergence, affine (x=4,o=6,e=2), end-to-end, scope=full",
     "cfg2": "10M synthetic 250 bp pairs, 10% divergence, affine (x=4,o=6,e=2), end-to-end, scope=score",
     "cfg3": "100k (of 1M) synthetic 1 kbp pairs, 10% divergence, affine2p, ends-free, scope=full",
     "cfg4-adaptive": "20k (of 100k) synthetic 10 kbp pairs, 15% divergence, affine, heuristic=adaptive, scope=full",
+    "cfg4-xdrop": "20k (of 100k) synthetic 10 kbp pairs, 15% divergence, affine, heuristic=X-drop (xdrop=20), scope=full",
+    "cfg4-none": "2k (of 100k) synthetic 10 kbp pairs, 15% divergence, affine, no heuristic, scope=full",
+    "cfg5": "16 (of 10k) synthetic 100 kbp pairs, 20% divergence, affine2p, end-to-end, scope=full, several CTAs per pair, history in HBM",
 }
 
 
@@ -211,7 +219,7 @@ def algorithmic_figures(stats, n, length_p, length_t_mean, two_p, full, runs_tot
     int_ops = cells * ops_cell + extend
     hbm = n * (np.ceil(length_p / 4) + np.ceil(length_t_mean / 4) + 32) + 4 * runs_total
     if full:
-        hbm += 2 * 5 * cells       # history record (int32 offset + origin code), written + read once
+        hbm += cells               # one origin byte per cell, written once (the backtrace reads only the path)
     return float(hbm), float(int_ops)
 
 
@@ -250,8 +258,8 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (reference build) missing"}))
             return
         # bounded sample per step: about 10 s of wall-clock on the host cores
-        per_core = {"cfg1": 90_000, "cfg2": 25_000, "cfg3": 280, "cfg4-adaptive": 120}[args.workload]
-        sample = int(min(n_pairs, max(cores * 64, per_core * cores * 6)))
+        per_core = REF_PER_CORE[args.workload]
+        sample = int(min(n_pairs, max(cores * (64 if per_core > 10 else 1), per_core * cores * 6)))
         batch = make_batch(sample, length, div, flank, seed=1234)
         rates = []
         for i in range(args.warmup + args.steps):
@@ -391,12 +399,17 @@ def main():
                               "frac": int_ops / kernel_s / int_peak, "cells_per_step": stats["cells"],
                               "unit": "INT32 lane-ops/s (19|33 per cell + extend, SURVEY.md 8(d))"}}
 
+    # arithmetic type of the offsets the dominant tier computes in (scores are int32 everywhere)
+    dtype = "int32" if length > 12_000 else "int16"
     # ---- CPU baseline: the reference on the host cores, bounded sample ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and args.workload == "cfg5" and not args.cpu_sample:
+        cpu = {"value": None, "unit": "pairs/s", "cores": cores, "kind": "reference",
+               "sample": "not timed by default: one 100 kbp pair takes the reference minutes per core (BASELINE.md); pass --cpu-sample N"}
+    elif not args.no_cpu_baseline:
         if have_reference():
-            per_core = {"cfg1": 90_000, "cfg2": 25_000, "cfg3": 280, "cfg4-adaptive": 120}[args.workload]
-            sample = args.cpu_sample or int(min(n_pairs, per_core * cores * 2))
+            per_core = REF_PER_CORE[args.workload]
+            sample = args.cpu_sample or int(min(n_pairs, max(cores, per_core * cores * 2)))
             sub = tuple(a[:sample] if i else a for i, a in enumerate(batch))
             r, n, slow, wall = reference_pool_rate(sub, kw, cores)
             c_rate = reference_c_rate(sub, cfg, cores)
@@ -408,7 +421,7 @@ def main():
 
     line = {"metric": "aligned pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["kernel_launches"]) * args.steps,
             "roofline": roofline, "cpu_baseline": cpu,
             "parity": {"status_histogram": status_hist, "retried_pairs": stats["retried_pairs"]}}
