@@ -110,6 +110,7 @@ struct KParams {
   const int* n_work;             /* device pointer to the number of work items */
   int* work_counter;
   int* retry_list; int* retry_count;
+  int skip_groups;               /* > 0: groups in flight; a tier that overflows most of its first pairs forwards the rest */
   /* results (SoA) */
   int* score; int* status; int* locs; int* nruns; long long* runs_base;
   /* scope=full scratch */
@@ -199,6 +200,17 @@ WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
   const int32_t sum = (int32_t)((uint32_t)plen + (uint32_t)tlen);
   const int32_t prod = (int32_t)((uint32_t)swg_match * (uint32_t)sum);
   return (int32_t)((uint32_t)prod - (uint32_t)wf_score) / 2;
+}
+
+/*
+ * Adaptive tier skipping: once at least 256 pairs of this launch have finished and three quarters
+ * of them exceeded the tier's capacity, the remaining pairs are forwarded to the next tier
+ * unprocessed (their partial work would be thrown away).  w = index of the work item just fetched.
+ */
+WFA_DEV bool tier_gives_up(const KParams& P, int w) {
+  if (P.skip_groups <= 0 || w < P.skip_groups + 256) return false;
+  const int overflowed = ld_cg(P.retry_count);
+  return 4ll * overflowed > 3ll * (w - P.skip_groups);
 }
 
 /* one source wavefront component as the recurrence reads it */

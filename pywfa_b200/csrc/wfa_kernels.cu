@@ -136,7 +136,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
     int rc;
     PairResult res;
-    if (P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) {
+    if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || tier_gives_up(P, w)) {
       rc = PAIR_OVERFLOW;
     } else {
       const uint32_t* gw = P.words + pm.woff;
@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
     const int pwn = (plen + 15) >> 4;
     int rc = PAIR_OVERFLOW;
     PairResult res;
-    if (plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN) {
+    if (plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN && !tier_gives_up(K, w)) {
       /* packed words in HBM (the batch buffer carries one pad word) -> per-base windows in smem */
       const uint32_t* gp = K.words + pm.woff;
       const uint32_t* gt = gp + pwn;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
     int rc = PAIR_OVERFLOW;
     PairResult res;
-    if (pwn + twn + 2 <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {
+    if (pwn + twn + 2 <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN && !tier_gives_up(P, w)) {
       const uint32_t* gw = P.words + pm.woff;
       uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
       for (int i = rank; i < pwn; i += gsize) sp[i] = gw[i];

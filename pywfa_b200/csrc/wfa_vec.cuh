@@ -55,6 +55,12 @@ constexpr uint32_t NULL2 = 0xC000C000u;    /* two int16 nulls */
 constexpr int NULL16 = -16384;
 constexpr int UB_MIN = -8192;              /* floor of ub[k] left of the matrix */
 constexpr uint32_t ONE2 = 0x00010001u;
+#ifndef WFA_VEC_PAD
+#define WFA_VEC_PAD 1
+#endif
+#ifndef WFA_VEC_EXT2
+#define WFA_VEC_EXT2 0      /* interleaving the two extensions of a lane measured slower (r01: -6 % on cfg3) */
+#endif
 constexpr int RENORM_MASK = 4095;          /* I/D nulls drift by one per step: re-based every 4096 scores */
 
 /* per-step reduction cells in shared memory (three rotating sets) */
@@ -93,7 +99,7 @@ struct __align__(16) PlanOut {
   int fl, fh;                                /* blocks in [fl, fh] need no range checks */
   int kind;                                  /* 0 compute, 1 null step, 2 capacity exceeded */
   int exact;                                 /* ranges must be scanned from this score on */
-  int pad0;
+  int pad;                                   /* 1: one all-null block is written either side of [nblo, nbhi] */
   int lo[5], hi[5];                          /* ranges of the valid cells (derived; replaced by the scan when exact) */
 };
 static_assert(sizeof(PlanOut) == 192, "PlanOut is copied through shared memory as 12 int4");
@@ -130,6 +136,21 @@ __device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int 
   return imin(n, rem);
 }
 
+/* extension of the lane's two M offsets, interleaved so that their loads overlap;
+ * rem = bases left on the diagonal (0 for a null offset) */
+__device__ __forceinline__ void vext2(const uint32_t* pw, const uint32_t* tw, int v0, int& o0, int rem0, int v1, int& o1, int rem1) {
+  int n0 = 0, n1 = 0;
+  bool m0 = rem0 > 0, m1 = rem1 > 0;
+  while (m0 || m1) {
+    uint32_t x0 = 0, x1 = 0;
+    if (m0) x0 = fetch16(pw, v0 + n0) ^ fetch16(tw, o0 + n0);
+    if (m1) x1 = fetch16(pw, v1 + n1) ^ fetch16(tw, o1 + n1);
+    if (m0) { const int a = x0 ? (first_set(x0) >> 1) : 16; n0 += a; m0 = (a == 16) && n0 < rem0; }
+    if (m1) { const int a = x1 ? (first_set(x1) >> 1) : 16; n1 += a; m1 = (a == 16) && n1 < rem1; }
+  }
+  o0 += imin(n0, rem0); o1 += imin(n1, rem1);
+}
+
 /*
  * Extend the two M cells of the lane, detect matrix-edge contact / termination, store the word.
  * k0 = diagonal of the low half, u0 / u1 = ub of the two diagonals.
@@ -138,8 +159,12 @@ __device__ __forceinline__ void finish_m(const VCtx& c, uint32_t* oM, int* F, bo
   using namespace lv;
   int o0 = sx_lo(Mn), o1 = sx_hi(Mn);
   const bool v0 = o0 >= 0, v1 = o1 >= 0;
+#if WFA_VEC_EXT2
+  vext2(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
+#else
   o0 += vext(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0);
   o1 += vext(c.pw, c.tw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
+#endif
   oM[pos] = pack2(o0, o1);
   const bool e0 = v0 && o0 == u0, e1 = v1 && o1 == u1;
   if (__any_sync(0xffffffffu, e0 || e1)) {
@@ -289,12 +314,13 @@ __device__ inline int backtrace_vcodes(const KParams& P, const uint8_t* h_code, 
  * the scalars passed in, so that one warp can run it for score s+1 while the others still work
  * on score s.  `writer`: this thread publishes the metadata / history row of the score.
  */
-template <bool TWO_P, bool FULL>
+template <bool TWO_P, bool FULL, bool PAD>
 __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int plen, int tlen, int s, int cm, int c1, int c2,
                                           int tp, int tb, long long cell_off, bool exact, bool writer, PlanOut& o) {
   const int capw = P.wcap >> 1, nblk = P.wcap >> 6, mmask = P.mr - 1;
   const int4* const meta = vm.meta;
   const int rI1 = P.rm * capw, rD1 = rI1 + P.r1 * capw, rI2 = rD1 + P.r1 * capw, rD2 = rI2 + (TWO_P ? P.r2 * capw : 0);   /* ring word offsets */
+  const int rNull = (P.rm + 2 * P.r1 + (TWO_P ? 2 * P.r2 : 0)) * capw;       /* the all-null slot follows the last ring slot */
   const int4 aMx = meta[((s - P.dx) & mmask) * 3];
   const int4 aMo1 = meta[((s - P.doe1) & mmask) * 3];
   const int4* const rowe1 = meta + ((s - P.de1) & mmask) * 3;
@@ -310,7 +336,7 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
   const bool n_i2 = TWO_P ? cE2.x > cE2.y : true;
   const bool n_d2 = TWO_P ? cE2.z > cE2.w : true;
   int4* const mrow = vm.meta + (s & mmask) * 3;
-  o.cell_off = cell_off; o.tp = tp; o.nblo = tb; o.nbhi = tb - 1; o.exact = exact; o.fl = INT_MAX; o.fh = INT_MIN;
+  o.cell_off = cell_off; o.tp = tp; o.nblo = tb; o.nbhi = tb - 1; o.exact = exact; o.fl = INT_MAX; o.fh = INT_MIN; o.pad = 0;
   for (int c = 0; c < 5; ++c) { o.lo[c] = 1; o.hi[c] = -1; }
   if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
     /* null step: allocate_output_null, compute.c:374-400 */
@@ -321,9 +347,8 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
   int lo = INT_MAX, hi = INT_MIN, li1 = INT_MAX, hi1 = INT_MIN, ld1 = INT_MAX, hd1 = INT_MIN;
   int li2 = INT_MAX, hi2 = INT_MIN, ld2 = INT_MAX, hd2 = INT_MIN;
   int fl = INT_MIN, fh = INT_MAX;
-  bool all_src = true;
   auto use = [&](const int4& a, bool null_) {
-    if (null_) { all_src = false; return; }
+    if (null_) return;                       /* reads of a null source go to the all-null slot */
     fl = imax(fl, a.z + 1); fh = imin(fh, a.w - 1);
   };
   if (!n_mx) { lo = aMx.x; hi = aMx.y; }
@@ -339,11 +364,13 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
     lo = imin(lo, imin(li2, ld2)); hi = imax(hi, imax(hi2, hd2));
     use(aMo2, n_mo2); use(aE2, n_i2); use(aE2, n_d2);
   }
-  if (!all_src) { fl = INT_MAX; fh = INT_MIN; }
   if (lo < -plen || hi > tlen) exact = true;
   const int nblo = (lo + BIAS) >> 6, nbhi = (hi + BIAS) >> 6;
   const int rowlen = (nbhi - nblo + 1) << 6;
   if (nbhi - nblo + 1 > nblk || (FULL && (s >= P.scap || cell_off + rowlen > P.hcap))) { o.kind = 2; return; }
+  /* one all-null block either side, ring capacity permitting: later scores, a few diagonals wider,
+   * then find their whole neighbourhood inside the written range and skip the range checks */
+  const int pad = (PAD && nbhi - nblo + 3 <= nblk) ? 1 : 0;
   tp += (nblo - tb) << 5;
   while (tp >= capw) tp -= capw;
   while (tp < 0) tp += capw;
@@ -351,8 +378,8 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
   const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
   const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
   auto src = [&](VSrc& v, int off, const int4& a, bool null_) {
-    v.off = off;
-    if (null_) { v.w0 = INT_MAX; v.span = 0; } else { v.w0 = a.z << 5; v.span = (unsigned)(((a.w - a.z) << 5) + 31); }
+    if (null_) { v.off = rNull; v.w0 = INT_MAX; v.span = 0; }
+    else { v.off = off; v.w0 = a.z << 5; v.span = (unsigned)(((a.w - a.z) << 5) + 31); }
   };
   auto mslot = [&](int d) { int sl = cm - d; if (sl < 0) sl += P.rm; return sl * capw; };
   const int e1s = (c1 + 1 == P.r1) ? 0 : c1 + 1;           /* slot of score s - e1 */
@@ -379,7 +406,7 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
     if (writer) { HistRow hr; hr.off = cell_off; hr.lo = 64 * nblo - BIAS; hr.pad = 0; vm.hmeta[s] = hr; }
     o.cell_off = cell_off + rowlen;
   }
-  o.kind = 0; o.exact = exact; o.nblo = nblo; o.nbhi = nbhi; o.tp = tp; o.fl = fl; o.fh = fh;
+  o.kind = 0; o.exact = exact; o.nblo = nblo; o.nbhi = nbhi; o.tp = tp; o.fl = fl; o.fh = fh; o.pad = pad;
   o.lo[CM] = lo; o.hi[CM] = hi;
   if (has_i1) { o.lo[CI1] = li1; o.hi[CI1] = hi1; }
   if (has_d1) { o.lo[CD1] = ld1; o.hi[CD1] = hd1; }
@@ -387,7 +414,7 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
   if (has_d2) { o.lo[CD2] = ld2; o.hi[CD2] = hd2; }
   if (writer && !exact) {
     /* derived ranges are final: publish them now (the scan publishes them otherwise) */
-    mrow[0] = make_int4(lo, hi, nblo, nbhi);
+    mrow[0] = make_int4(lo, hi, nblo - pad, nbhi + pad);
     mrow[1] = make_int4(o.lo[CI1], o.hi[CI1], o.lo[CD1], o.hi[CD1]);
     mrow[2] = make_int4(o.lo[CI2], o.hi[CI2], o.lo[CD2], o.hi[CD2]);
   }
@@ -401,8 +428,10 @@ template <bool TWO_P, bool FULL, int NW>
 __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tlen, PairResult& res) {
   constexpr int GS = NW * 32;
   constexpr int NC = TWO_P ? 5 : 3;
+  constexpr int CW = NW > 1 ? NW - 1 : 1;       /* warps that take blocks; with NW > 1 the last warp only plans */
   const int lane = (int)(threadIdx.x & 31);
   const int warp = NW == 1 ? 0 : (int)(threadIdx.x >> 5);
+  const int wofs = warp < CW ? warp : (1 << 28);     /* block offset of this warp (the planner warp never matches a range) */
   const int rank = NW == 1 ? lane : (int)threadIdx.x;
   const int capw = P.wcap >> 1, nblk = P.wcap >> 6, mmask = P.mr - 1;
   int4* const meta = vm.meta;
@@ -425,6 +454,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
   int end_k = KNONE, end_off = OFFNULL, end_score = 0, status = 0;
   int tb, tp = 0;                               /* ring position tp (words) of block tb */
   int blo, bhi;                                 /* written block range of the current score */
+  int cur_pad = 0;                              /* padding blocks of the current score */
   bool have_plan = false;                       /* vm.plan[(s+1)&1] holds the plan of the next score */
   const bool is_writer = NW == 1 ? lane == 0 : (warp == NW - 1 && lane == 0);   /* publishes metadata (the planner's lane 0) */
 
@@ -436,9 +466,13 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     if (bhi - blo + 1 > nblk) return PAIR_OVERFLOW;
     for (int i = rank; i < P.mr * 3; i += GS) meta[i] = make_int4(1, -1, 1, -1);
     for (int i = rank; i < 3 * NFLAG; i += GS) vm.flags[i] = flag_init(i % NFLAG);
+    {
+      uint32_t* const nullslot = rD2 + (TWO_P ? P.r2 * capw : 0);      /* read in place of null sources */
+      for (int i = rank; i < capw; i += GS) nullslot[i] = NULL2;
+    }
     gsync<NW>();
     tb = blo;
-    for (int b = blo + warp; b <= bhi; b += NW) {
+    for (int b = blo + wofs; b <= bhi; b += CW) {
       const int pos = ((b - blo) << 5) + lane;
       const int kblock = 64 * b - BIAS, k0 = kblock + 2 * lane;
       const int u0 = imax(imin(tlen, plen + k0), UB_MIN), u1 = imax(imin(tlen, plen + k0 + 1), UB_MIN);
@@ -479,7 +513,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
             /* wavefront_heuristic_wfadaptive, heuristic.c:257-293 */
             if (hi_base - lo_base + 1 >= P.min_wf_len) {
               int dm = INT_MAX;
-              for (int b = hb_lo + warp; b <= hb_hi; b += NW) {
+              for (int b = hb_lo + wofs; b <= hb_hi; b += CW) {
                 int pos = tp + ((b - tb) << 5); if (pos >= capw) pos -= capw;
                 const uint32_t w = mslot[pos + lane];
                 const int k0 = 64 * b - BIAS + 2 * lane;
@@ -492,7 +526,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
               gsync<NW>();
               const int min_d = imin(imax(plen, tlen), F[F_MINA]);
               int kf = INT_MAX, kl = INT_MIN;
-              for (int b = hb_lo + warp; b <= hb_hi; b += NW) {
+              for (int b = hb_lo + wofs; b <= hb_hi; b += CW) {
                 int pos = tp + ((b - tb) << 5); if (pos >= capw) pos -= capw;
                 const uint32_t w = mslot[pos + lane];
                 const int k0 = 64 * b - BIAS + 2 * lane;
@@ -522,7 +556,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
             const int swg = (P.match != 0) ? -P.match : -1;
             const int so = s * P.g;
             int cmax = INT_MIN, kf = INT_MAX, kl = INT_MIN;
-            for (int b = hb_lo + warp; b <= hb_hi; b += NW) {
+            for (int b = hb_lo + wofs; b <= hb_hi; b += CW) {
               int pos = tp + ((b - tb) << 5); if (pos >= capw) pos -= capw;
               const uint32_t w = mslot[pos + lane];
               const int k0 = 64 * b - BIAS + 2 * lane;
@@ -580,7 +614,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
               }
             }
           }
-          for (int b = blo + warp; b <= bhi; b += NW) {
+          for (int b = blo + wofs; b <= bhi; b += CW) {
             int pos = tp + ((b - tb) << 5); if (pos >= capw) pos -= capw;
             pos += lane;
             const int k0 = 64 * b - BIAS + 2 * lane;
@@ -590,7 +624,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
           if (rank == 0) {
             int4* const mrow = meta + (s & mmask) * 3;
             const bool n0 = clo[CM] > chi[CM];
-            mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], blo, bhi);
+            mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], blo - cur_pad, bhi + cur_pad);
             const bool n1 = clo[CI1] > chi[CI1], n2 = clo[CD1] > chi[CD1], n3 = clo[CI2] > chi[CI2], n4 = clo[CD2] > chi[CD2];
             mrow[1] = make_int4(n1 ? 1 : clo[CI1], n1 ? -1 : chi[CI1], n2 ? 1 : clo[CD1], n2 ? -1 : chi[CD1]);
             mrow[2] = make_int4(n3 ? 1 : clo[CI2], n3 ? -1 : chi[CI2], n4 ? 1 : clo[CD2], n4 ? -1 : chi[CD2]);
@@ -630,12 +664,12 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         pl = vm.plan[s & 1];
         if (exact) pl.exact = 1;
       } else {
-        plan_step<TWO_P, FULL>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
+        plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
       }
       if (pl.kind == 2) return PAIR_OVERFLOW;
       exact = pl.exact != 0;
       tp = pl.tp; tb = pl.nblo; cell_off = pl.cell_off;
-      blo = pl.nblo; bhi = pl.nbhi;
+      blo = pl.nblo; bhi = pl.nbhi; cur_pad = pl.pad;
       for (int c = 0; c < 5; ++c) { clo[c] = pl.lo[c]; chi[c] = pl.hi[c]; }
       /* the planner may run one score ahead while nothing can invalidate derived ranges */
       const bool pipelined = NW > 1 && P.heuristic == 0 && !exact;
@@ -644,9 +678,20 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       } else {
         cur_exists = true;
         s_exist = s * P.g;
-        for (int b = blo + warp; b <= bhi; b += NW) {
-          int posb = tp + ((b - blo) << 5); if (posb >= capw) posb -= capw;
-          if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false>(cx, pl, Fn, exact, b, posb, lane);
+        for (int b = blo - pl.pad + wofs; b <= bhi + pl.pad; b += CW) {
+          int posb = tp + ((b - blo) << 5);
+          if (posb >= capw) posb -= capw;
+          if (posb < 0) posb += capw;
+          if (b < blo || b > bhi) {
+            /* padding block: nulls in every component this score owns */
+            vm.ring[pl.oM + posb + lane] = NULL2;
+            if (pl.oI1 >= 0) vm.ring[pl.oI1 + posb + lane] = NULL2;
+            if (pl.oD1 >= 0) vm.ring[pl.oD1 + posb + lane] = NULL2;
+            if (TWO_P) {
+              if (pl.oI2 >= 0) vm.ring[pl.oI2 + posb + lane] = NULL2;
+              if (pl.oD2 >= 0) vm.ring[pl.oD2 + posb + lane] = NULL2;
+            }
+          } else if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false>(cx, pl, Fn, exact, b, posb, lane);
           else vec_block<TWO_P, FULL, true>(cx, pl, Fn, exact, b, posb, lane);
         }
       }
@@ -656,7 +701,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
           const int ncm = (cm + 1 == P.rm) ? 0 : cm + 1, nc1 = (c1 + 1 == P.r1) ? 0 : c1 + 1;
           const int nc2 = TWO_P ? ((c2 + 1 == P.r2) ? 0 : c2 + 1) : 0;
           __syncwarp();                                    /* lane 0's metadata of score s is visible to the warp */
-          plan_step<TWO_P, FULL>(P, vm, plen, tlen, s + 1, ncm, nc1, nc2, tp, tb, cell_off, false, lane == 0, nx);
+          plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s + 1, ncm, nc1, nc2, tp, tb, cell_off, false, lane == 0, nx);
           if (lane == 0) vm.plan[(s + 1) & 1] = nx;
         }
         have_plan = pipelined;
@@ -671,7 +716,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         }
         if (Fn[F_POISON]) {
           /* offsets beyond the matrix that the trimmed range no longer covers read as NULL */
-          for (int b = blo + warp; b <= bhi; b += NW) {
+          for (int b = blo + wofs; b <= bhi; b += CW) {
             int pos = tp + ((b - blo) << 5); if (pos >= capw) pos -= capw;
             pos += lane;
             const int k0 = 64 * b - BIAS + 2 * lane;
@@ -686,7 +731,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         if (is_writer) {
           int4* const mrow = meta + (s & mmask) * 3;
           const bool n0 = clo[CM] > chi[CM];
-          mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], blo, bhi);
+          mrow[0] = make_int4(n0 ? 1 : clo[CM], n0 ? -1 : chi[CM], blo - pl.pad, bhi + pl.pad);
           mrow[1] = make_int4(clo[CI1], chi[CI1], clo[CD1], chi[CD1]);
           mrow[2] = make_int4(clo[CI2], chi[CI2], clo[CD2], chi[CD2]);
         }

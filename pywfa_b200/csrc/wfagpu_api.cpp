@@ -209,7 +209,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const bool no_vec = getenv("WFAGPU_NO_VEC_TIER") != nullptr;            /* tests / debugging */
   bool vec_covers_smem = false;
   if (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN) {
-    const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
+    const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
     const long long fixed0 = (long long)k.mr * 48 + 256 + 4ll * seqw;
     const long long nblk_max = (wmax + 63) / 64 + 1;
     long long last_nblk = 0;
@@ -656,6 +656,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.n_work = (last_tier < 0) ? &dc->nwork0 : &dc->retry[last_tier];
       k.work_counter = &dc->work[ti];
       k.retry_list = lists[ti & 1];
+      k.skip_groups = (ti + 1 < b->tiers.size() && !getenv("WFAGPU_NO_TIER_SKIP")) ? (int)std::min<long long>(groups, INT_MAX / 2) : 0;   /* never on the last tier */
       k.retry_count = &dc->retry[ti];
       const double tier_t0 = trace_on() ? now_ms() : 0;
       if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
