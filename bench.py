@@ -8,7 +8,7 @@ x=4 o=6 e=2, end-to-end, scope=score); with N>1 every rank aligns its own batch 
 
   value     device-resident: packed batch already in HBM, CUDA events around K runs
   e2e       through the C ABI from HOST buffers: 2-bit pack + H2D + kernels + D2H every step
-  roofline  dominant kernel (wfa_align_kernel) against the measured HBM peak, plus the
+  roofline  dominant kernel (wfa_reg_kernel for the bench line) against the measured HBM peak, plus the
             integer-issue figure that actually bounds this path
   cpu_baseline  the reference (oracle/_ref: unmodified WFA2-lib + pywfa compiled in the build
             container) on all host cores, bounded sample of the same workload
@@ -392,8 +392,11 @@ def main():
     achieved = hbm_bytes / kernel_s / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     int_peak = 148 * 128 * sm_mhz * 1e6     # INT32 lane-ops/s at the clock seen under load
+    # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
+    # `ncu --set full` capture of this exact command (profiles/r01_reg_cfg2_10M_ncu_summary.txt)
+    traffic = 1.470791e9 + 87.846144e6 if (args.workload == "cfg2" and n_pairs == 10_000_000) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "integer-DP kernel: HBM is not the binding resource (SURVEY.md 8(d)); see int_issue",
                 "int_issue": {"achieved_gops": int_ops / kernel_s / 1e9, "peak_gops": int_peak / 1e9,
                               "frac": int_ops / kernel_s / int_peak, "cells_per_step": stats["cells"],

@@ -632,7 +632,11 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
           gsync<NW>();
         }
       }
+#ifdef WFA_VEC_DEBUG_EXACT
+      cells += exact ? 1 : 0;          /* debugging build: count the scores spent in the scanned-range variant */
+#else
       cells += imax(0, chi[CM] - clo[CM] + 1);
+#endif
     }
 
     /* ---- compute score s+1 (compute_affine.c:229-260 / compute_affine2p.c:334-368) ---- */
