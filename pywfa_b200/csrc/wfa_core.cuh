@@ -99,6 +99,7 @@ struct KParams {
   /* tier capacities */
   int wcap;                      /* wavefront width capacity per ring slot: power of two */
   int seq_words_cap;             /* words of smem for both packed sequences (0: read HBM) */
+  int vec_seqw;                  /* packed-halfword tier: the sequences are staged as per-base windows */
   int group_bytes;               /* shared memory of one group (multiple of 16) */
   long long hcap;                /* history cells per group */
   int scap;                      /* history score-table entries per group */

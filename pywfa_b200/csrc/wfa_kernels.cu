@@ -491,13 +491,25 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
     int rc = PAIR_OVERFLOW;
     PairResult res;
-    if (pwn + twn + 2 <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN && !tier_gives_up(P, w)) {
+    const int need_words = P.vec_seqw ? plen + tlen + 2 : pwn + twn + 2;
+    if (need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN && !tier_gives_up(P, w)) {
       const uint32_t* gw = P.words + pm.woff;
-      uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
-      for (int i = rank; i < pwn; i += gsize) sp[i] = gw[i];
-      for (int i = rank; i < twn; i += gsize) st[i] = gw[pwn + i];
-      if (rank == 0) { sp[pwn] = 0; st[twn] = 0; }
-      vm.pw = sp; vm.tw = st;
+      vm.bpw = gw; vm.btw = gw + pwn; vm.seqw = P.vec_seqw;
+      if (P.vec_seqw) {
+        /* per-base windows: word i = the 16 bases from position i, first base in the top bits
+         * (the packed batch buffer is readable one word past every sequence) */
+        uint32_t* sp = sm_seq; uint32_t* st = sm_seq + plen + 1;
+        for (int i = rank; i <= plen; i += gsize) sp[i] = i < plen ? __brev(__funnelshift_r(gw[i >> 4], gw[(i >> 4) + 1], (i & 15) << 1)) : 0u;
+        const uint32_t* gt = gw + pwn;
+        for (int i = rank; i <= tlen; i += gsize) st[i] = i < tlen ? __brev(__funnelshift_r(gt[i >> 4], gt[(i >> 4) + 1], (i & 15) << 1)) : 0u;
+        vm.pw = sp; vm.tw = st;
+      } else {
+        uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
+        for (int i = rank; i < pwn; i += gsize) sp[i] = gw[i];
+        for (int i = rank; i < twn; i += gsize) st[i] = gw[pwn + i];
+        if (rank == 0) { sp[pwn] = 0; st[twn] = 0; }
+        vm.pw = sp; vm.tw = st;
+      }
       vec::gsync<NW>();
       rc = vec::align_pair_vec<TWO_P, FULL, NW>(P, vm, plen, tlen, res);
     }

@@ -74,7 +74,9 @@ __device__ __forceinline__ int flag_init(int i) {
 struct VMem {
   int4* meta;            /* [mr][3]: {mlo, mhi, wblo, wbhi}, {i1lo, i1hi, d1lo, d1hi}, {i2lo, i2hi, d2lo, d2hi} */
   int* flags;            /* [3][NFLAG] */
-  const uint32_t* pw; const uint32_t* tw;     /* 2-bit packed sequences in shared memory (+1 pad word) */
+  const uint32_t* pw; const uint32_t* tw;     /* shared memory: 2-bit packed sequences (+1 pad word), or per-base windows */
+  const uint32_t* bpw; const uint32_t* btw;   /* 2-bit packed sequences for the backtrace (any memory) */
+  int seqw;                                   /* 1: pw / tw are windows (16 bases from every position, first base in the top bits) */
   uint32_t* ring;        /* slots x capw words */
   struct PlanOut* plan;  /* [2], NW > 1 only */
   uint8_t* h_code; HistRow* hmeta; uint32_t* runs_stage; uint8_t* ops; int opcap;
@@ -110,6 +112,7 @@ struct VCtx {
   const uint32_t *pw, *tw;
   int plen, tlen, capw, ak;
   int endsfree, pef, tef;
+  int seqw;
 };
 
 template <int NW> __device__ __forceinline__ void gsync() {
@@ -126,8 +129,17 @@ __device__ __forceinline__ void report_range(int* F, int c, uint32_t b0, uint32_
 }
 
 /* extension of one valid M offset; rem = bases left on the diagonal */
-__device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int v, int h, int rem) {
+__device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int seqw, int v, int h, int rem) {
   int n = 0;
+  if (seqw) {
+    /* per-base windows: 16 bases = LDS, LDS, XOR, CLZ */
+    while (n < rem) {
+      const int a = __clz((int)(pw[v + n] ^ tw[h + n])) >> 1;
+      n += a;
+      if (a < 16) break;
+    }
+    return imin(n, rem);
+  }
   while (n < rem) {
     const uint32_t x = fetch16(pw, v + n) ^ fetch16(tw, h + n);
     if (x) { n += first_set(x) >> 1; break; }
@@ -162,8 +174,8 @@ __device__ __forceinline__ void finish_m(const VCtx& c, uint32_t* oM, int* F, bo
 #if WFA_VEC_EXT2
   vext2(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
 #else
-  o0 += vext(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0);
-  o1 += vext(c.pw, c.tw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
+  o0 += vext(c.pw, c.tw, c.seqw, o0 - k0, o0, v0 ? u0 - o0 : 0);
+  o1 += vext(c.pw, c.tw, c.seqw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
 #endif
   oM[pos] = pack2(o0, o1);
   const bool e0 = v0 && o0 == u0, e1 = v1 && o1 == u1;
@@ -243,10 +255,11 @@ __device__ __forceinline__ void vec_block(const VCtx& c, const PlanOut& pl, int*
     r = vimax2p(del1, r, p2h, p2l);
     if (TWO_P) r = vimax2p(del2, r, p3h, p3l);
     m = vimax2p(mis, r, p4h, p4l);
-    const uint32_t wl = p4l ? 5u : (p3l ? 4u : (p2l ? 3u : (p1l ? 2u : 1u)));
-    const uint32_t wh = p4h ? 5u : (p3h ? 4u : (p2h ? 3u : (p1h ? 2u : 1u)));
-    const uint32_t cl = wl | (x1l ? 0x10u : 0u) | (y1l ? 0x20u : 0u) | (x2l ? 0x40u : 0u) | (y2l ? 0x80u : 0u);
-    const uint32_t ch = wh | (x1h ? 0x10u : 0u) | (y1h ? 0x20u : 0u) | (x2h ? 0x40u : 0u) | (y2h ? 0x80u : 0u);
+    /* origin byte = the eight predicates as they are (the backtrace decodes the priority) */
+    const uint32_t cl = (p1l ? 1u : 0u) | (p2l ? 2u : 0u) | (p3l ? 4u : 0u) | (p4l ? 8u : 0u) |
+                        (x1l ? 0x10u : 0u) | (y1l ? 0x20u : 0u) | (x2l ? 0x40u : 0u) | (y2l ? 0x80u : 0u);
+    const uint32_t ch = (p1h ? 1u : 0u) | (p2h ? 2u : 0u) | (p3h ? 4u : 0u) | (p4h ? 8u : 0u) |
+                        (x1h ? 0x10u : 0u) | (y1h ? 0x20u : 0u) | (x2h ? 0x40u : 0u) | (y2h ? 0x80u : 0u);
     *reinterpret_cast<uint16_t*>(pl.hrow + (64 * b + 2 * lane)) = (uint16_t)(cl | (ch << 8));
   } else if (TWO_P) {
     m = vimax3(vimax3(mis, ins1, ins2), del1, del2);
@@ -279,8 +292,9 @@ __device__ __forceinline__ void clip_word(uint32_t* slot, int pos, int k0, int l
   if (mask != 0xffffffffu) { const uint32_t x = slot[pos]; slot[pos] = (x & mask) | (NULL2 & ~mask); }
 }
 
-/* Backtrace over the origin bytes of this tier (one thread): low 3 bits winner of M
- * (1 I1, 2 I2, 3 D1, 4 D2, 5 mismatch), bits 4-7 "extension" flags of I1, D1, I2, D2 at the cell. */
+/* Backtrace over the origin bytes of this tier (one thread): bits 0-3 = "this candidate >= the best of
+ * the lower-priority ones" for I2, D1, D2, mismatch (the winner of M is the highest bit set, I1 if none),
+ * bits 4-7 "extension >= opening" of I1, D1, I2, D2 at the cell. */
 __device__ inline int backtrace_vcodes(const KParams& P, const uint8_t* h_code, const HistRow* hmeta, int a_score, int a_k,
                                        int plen, int tlen, const uint32_t* pw, const uint32_t* tw, uint8_t* ops, int opcap,
                                        FwdEmitter& em) {
@@ -290,9 +304,9 @@ __device__ inline int backtrace_vcodes(const KParams& P, const uint8_t* h_code, 
     const int code = h_code[hm.off + (k - hm.lo)];
     int comp = mt;
     if (mt == CM) {
-      const int w = code & 7;
-      if (w == 5) { if (nops < opcap) ops[nops] = EOP_X; ++nops; score -= P.dx; continue; }
-      comp = (w == 1) ? CI1 : (w == 2) ? CI2 : (w == 3) ? CD1 : CD2;
+      /* winner of the max chain I1 < I2 < D1 < D2 < mismatch (later wins ties): highest predicate set */
+      if (code & 8) { if (nops < opcap) ops[nops] = EOP_X; ++nops; score -= P.dx; continue; }
+      comp = (code & 4) ? CD2 : (code & 2) ? CD1 : (code & 1) ? CI2 : CI1;
     }
     const bool ext = (code >> (comp == CI1 ? 4 : comp == CD1 ? 5 : comp == CI2 ? 6 : 7)) & 1;
     const bool is_ins = comp == CI1 || comp == CI2;
@@ -444,7 +458,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
 
   VCtx cx;
   cx.ring = vm.ring; cx.pw = vm.pw; cx.tw = vm.tw; cx.plen = plen; cx.tlen = tlen; cx.capw = capw; cx.ak = ak;
-  cx.endsfree = P.endsfree; cx.pef = P.pef; cx.tef = P.tef;
+  cx.endsfree = P.endsfree; cx.pef = P.pef; cx.tef = P.tef; cx.seqw = vm.seqw;
 
   int s = 0, cm = 0, c1 = 0, c2 = 0, fb = 0;
   int s_exist = 0, steps_wait = P.steps_between, max_sw = 0;
@@ -774,7 +788,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     if (status == 1) {
       if (rank == 0) {
         FwdEmitter em; em.init(vm.runs_stage, P.runcap);
-        const int n = backtrace_vcodes(P, vm.h_code, vm.hmeta, s, end_k, plen, tlen, vm.pw, vm.tw, vm.ops, vm.opcap, em);
+        const int n = backtrace_vcodes(P, vm.h_code, vm.hmeta, s, end_k, plen, tlen, vm.bpw, vm.btw, vm.ops, vm.opcap, em);
         res.nruns = n;
         if (n >= 0) locations_from_runs(vm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }

@@ -76,6 +76,7 @@ struct Staging { PinBuf words, meta; };
 struct Tier {
   int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
   int vec_nw = 0;          /* > 0: packed-halfword tier (wfa_vec.cuh) with vec_nw warps per pair */
+  bool vec_seqw = false;   /* ... with the sequences staged as per-base windows */
   int max_groups = 0;      /* > 0: at most this many pairs in flight (history arena per pair grows accordingly) */
   int mode = 0;            /* 0 warp/smem, 1 block/smem, 2 block/HBM ring */
   int threads = 128;
@@ -214,14 +215,18 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const long long nblk_max = (wmax + 63) / 64 + 1;
     long long last_nblk = 0;
     auto add_vec = [&](int nw, long long budget, long long hcap, long long scap) {
-      const long long fixed = fixed0 + (nw > 1 ? 512 : 0);      /* step plans of the planner warp */
+      /* per-base sequence windows (one word per base: 16 bases = LDS, LDS, XOR, CLZ) where they are small
+       * next to the rings, 2-bit packed words otherwise */
+      const long long winw = (long long)b->maxp + b->maxt + 2;
+      const bool seqw_t = 4 * winw <= (nw > 1 ? 16384 : 2560);
+      const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw) + (nw > 1 ? 512 : 0);   /* + step plans of the planner warp */
       long long nblk = (budget - fixed) / ((long long)nslots * 128);
       nblk = std::min(nblk, nblk_max);
       if (nblk < 2 || nblk <= last_nblk) return;
       Tier t;
       t.vec_nw = nw; t.mode = nw == 1 ? 0 : 1;
       t.threads = nw == 1 ? 128 : nw * 32; t.groups_per_block = nw == 1 ? 4 : 1;
-      t.wcap = (int)(64 * nblk); t.seq_words_cap = seqw;
+      t.wcap = (int)(64 * nblk); t.seq_words_cap = (int)(seqw_t ? winw : seqw); t.vec_seqw = seqw_t;
       t.group_bytes = (int)((fixed + nblk * nslots * 128 + 15) & ~15ll);
       t.smem = (size_t)t.group_bytes * t.groups_per_block;
       t.scap = (int)std::min<long long>(scap, scap_bound);
@@ -614,7 +619,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
           blocks = (int)groups;
         }
       }
-      k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes;
+      k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes; k.vec_seqw = t.vec_seqw ? 1 : 0;
       k.hcap = t.hcap; k.scap = t.scap;
       const size_t elem = t.off16 ? 2 : 4;
       if (t.regs) {
