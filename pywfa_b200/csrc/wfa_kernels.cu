@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
   vm.meta = reinterpret_cast<int4*>(base);
   vm.flags = reinterpret_cast<int*>(base + (size_t)P.mr * 48);
   vm.plan = reinterpret_cast<vec::PlanOut*>(base + (size_t)P.mr * 48 + 256);
-  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * 48 + (NW == 1 ? 256 : 768));   /* one warp per pair plans for itself */
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(base + (size_t)P.mr * 48 + 768);
   vm.ring = sm_seq + P.seq_words_cap;
   if (FULL) {
     vm.h_code = P.hist_code + (long long)group_id * P.hcap;

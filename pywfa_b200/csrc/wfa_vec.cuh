@@ -58,6 +58,9 @@ constexpr uint32_t ONE2 = 0x00010001u;
 #ifndef WFA_VEC_PAD
 #define WFA_VEC_PAD 1
 #endif
+#ifndef WFA_VEC_SIMD_NW1
+#define WFA_VEC_SIMD_NW1 0      /* one warp per pair: the lane-parallel planner measured 3 % slower than the one-thread one */
+#endif
 #ifndef WFA_VEC_EXT2
 #define WFA_VEC_EXT2 0      /* interleaving the two extensions of a lane measured slower (r01: -6 % on cfg3) */
 #endif
@@ -129,9 +132,10 @@ __device__ __forceinline__ void report_range(int* F, int c, uint32_t b0, uint32_
 }
 
 /* extension of one valid M offset; rem = bases left on the diagonal */
+template <bool WIN>
 __device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int seqw, int v, int h, int rem) {
   int n = 0;
-  if (seqw) {
+  if (WIN && seqw) {
     /* per-base windows: 16 bases = LDS, LDS, XOR, CLZ */
     while (n < rem) {
       const int a = __clz((int)(pw[v + n] ^ tw[h + n])) >> 1;
@@ -167,6 +171,7 @@ __device__ __forceinline__ void vext2(const uint32_t* pw, const uint32_t* tw, in
  * Extend the two M cells of the lane, detect matrix-edge contact / termination, store the word.
  * k0 = diagonal of the low half, u0 / u1 = ub of the two diagonals.
  */
+template <bool WIN>
 __device__ __forceinline__ void finish_m(const VCtx& c, uint32_t* oM, int* F, bool exact, uint32_t Mn, int pos, int k0, int u0, int u1, int kblock, int lane) {
   using namespace lv;
   int o0 = sx_lo(Mn), o1 = sx_hi(Mn);
@@ -174,8 +179,8 @@ __device__ __forceinline__ void finish_m(const VCtx& c, uint32_t* oM, int* F, bo
 #if WFA_VEC_EXT2
   vext2(c.pw, c.tw, o0 - k0, o0, v0 ? u0 - o0 : 0, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
 #else
-  o0 += vext(c.pw, c.tw, c.seqw, o0 - k0, o0, v0 ? u0 - o0 : 0);
-  o1 += vext(c.pw, c.tw, c.seqw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
+  o0 += vext<WIN>(c.pw, c.tw, c.seqw, o0 - k0, o0, v0 ? u0 - o0 : 0);
+  o1 += vext<WIN>(c.pw, c.tw, c.seqw, o1 - k0 - 1, o1, v1 ? u1 - o1 : 0);
 #endif
   oM[pos] = pack2(o0, o1);
   const bool e0 = v0 && o0 == u0, e1 = v1 && o1 == u1;
@@ -204,7 +209,7 @@ __device__ __forceinline__ void scan_gap(int* F, int comp, uint32_t x, uint32_t 
 }
 
 /* one block of 64 diagonals of the recurrence */
-template <bool TWO_P, bool FULL, bool CHECK>
+template <bool TWO_P, bool FULL, bool CHECK, bool WIN>
 __device__ __forceinline__ void vec_block(const VCtx& c, const PlanOut& pl, int* F, bool exact, int b, int posb, int lane) {
   const uint32_t* const ring = c.ring;
   using namespace lv;
@@ -283,7 +288,7 @@ __device__ __forceinline__ void vec_block(const VCtx& c, const PlanOut& pl, int*
       if (pl.oD2 >= 0) scan_gap(F, CD2, del2, nub, kblock, lane);
     }
   }
-  finish_m(c, c.ring + pl.oM, F, exact, Mn, pos, k0, u0, u1, kblock, lane);
+  finish_m<WIN>(c, c.ring + pl.oM, F, exact, Mn, pos, k0, u0, u1, kblock, lane);
 }
 
 /* null the cells of one ring word that lie outside [lo, hi] */
@@ -435,6 +440,111 @@ __device__ __forceinline__ void plan_step(const KParams& P, const VMem& vm, int 
 }
 
 /*
+ * plan_step spread over the lanes of one warp: lane i < 7 owns source i (Mx, Mo1, I1e, D1e, Mo2, I2e,
+ * D2e), the ranges are warp min-reductions, and the plan goes straight to shared memory (lane i
+ * stores its source, lane 0 the rest).  ~4x shorter dependent chain than the one-thread version,
+ * which is what bounds a step when one warp plans for the whole group.  Must produce exactly what
+ * plan_step produces (the forced-group-size parity tests run both).
+ */
+template <bool TWO_P, bool FULL, bool PAD>
+__device__ __forceinline__ void plan_step_simd(const KParams& P, const VMem& vm, int plen, int tlen, int s, int cm, int c1, int c2,
+                                               int tp, int tb, long long cell_off, bool exact, PlanOut* out) {
+  const int lane = (int)(threadIdx.x & 31);
+  const int capw = P.wcap >> 1, nblk = P.wcap >> 6, mmask = P.mr - 1;
+  const int4* const meta = vm.meta;
+  const int rI1 = P.rm * capw, rD1 = rI1 + P.r1 * capw, rI2 = rD1 + P.r1 * capw, rD2 = rI2 + (TWO_P ? P.r2 * capw : 0);
+  const int rNull = (P.rm + 2 * P.r1 + (TWO_P ? 2 * P.r2 : 0)) * capw;
+  /* lane -> source: look-back, metadata row / half holding its range, ring base and current slot */
+  const int nsrc = TWO_P ? 7 : 4;
+  const bool is_m = lane == 0 || lane == 1 || lane == 4;
+  const int d = lane == 0 ? P.dx : lane == 1 ? P.doe1 : lane <= 3 ? P.de1 : lane == 4 ? P.doe2 : P.de2;
+  const int rowsel = is_m ? 0 : (lane <= 3 ? 1 : 2);
+  const bool second_half = lane == 3 || lane == 6;
+  int slot_off;
+  if (is_m) { int sl = cm - d; if (sl < 0) sl += P.rm; slot_off = sl * capw; }
+  else if (lane <= 3) { const int e1s = (c1 + 1 == P.r1) ? 0 : c1 + 1; slot_off = (lane == 2 ? rI1 : rD1) + e1s * capw; }
+  else { const int e2s = (c2 + 1 == P.r2) ? 0 : c2 + 1; slot_off = (lane == 5 ? rI2 : rD2) + e2s * capw; }
+  const int row = ((s - d) & mmask) * 3;
+  const int4 a = meta[row];
+  const int4 r = meta[row + rowsel];
+  const int lo_c = second_half ? r.z : r.x, hi_c = second_half ? r.w : r.y;
+  const bool null_ = lane >= nsrc || lo_c > hi_c;
+  /* contributions to the ranges */
+  const bool to_m = lane == 0, to_i = lane == 1 || lane == 2 || lane == 4 || lane == 5, to_d = lane == 1 || lane == 3 || lane == 4 || lane == 6;
+  const bool p2 = lane >= 4;
+  const int BIG = INT_MAX;
+  auto rmin = [](int v) { return __reduce_min_sync(0xffffffffu, v); };
+  auto rmax = [](int v) { return __reduce_max_sync(0xffffffffu, v); };
+  const bool ok = !null_;
+  int lo = rmin(ok && to_m ? lo_c : BIG), hi = rmax(ok && to_m ? hi_c : INT_MIN);
+  const int li1 = rmin(ok && to_i && !p2 ? lo_c + 1 : BIG), hi1 = rmax(ok && to_i && !p2 ? hi_c + 1 : INT_MIN);
+  const int ld1 = rmin(ok && to_d && !p2 ? lo_c - 1 : BIG), hd1 = rmax(ok && to_d && !p2 ? hi_c - 1 : INT_MIN);
+  int li2 = BIG, hi2 = INT_MIN, ld2 = BIG, hd2 = INT_MIN;
+  if (TWO_P) {
+    li2 = rmin(ok && to_i && p2 ? lo_c + 1 : BIG); hi2 = rmax(ok && to_i && p2 ? hi_c + 1 : INT_MIN);
+    ld2 = rmin(ok && to_d && p2 ? lo_c - 1 : BIG); hd2 = rmax(ok && to_d && p2 ? hi_c - 1 : INT_MIN);
+  }
+  const int fl = rmax(ok ? a.z + 1 : INT_MIN), fh = rmin(ok ? a.w - 1 : BIG);
+  const bool any_src = __any_sync(0xffffffffu, ok);
+  int4* const mrow = vm.meta + (s & mmask) * 3;
+  /* this lane's source */
+  {
+    VSrc v;
+    if (null_) { v.off = rNull; v.w0 = INT_MAX; v.span = 0; }
+    else { v.off = slot_off; v.w0 = a.z << 5; v.span = (unsigned)(((a.w - a.z) << 5) + 31); }
+    if (lane < 7) (&out->mx)[lane] = v;
+  }
+  if (!any_src) {
+    /* null step: allocate_output_null, compute.c:374-400 */
+    if (lane == 0) {
+      out->cell_off = cell_off; out->tp = tp; out->nblo = tb; out->nbhi = tb - 1; out->exact = exact;
+      out->fl = INT_MAX; out->fh = INT_MIN; out->pad = 0; out->kind = 1;
+      for (int c = 0; c < 5; ++c) { out->lo[c] = 1; out->hi[c] = -1; }
+      mrow[0] = make_int4(1, -1, 1, -1); mrow[1] = make_int4(1, -1, 1, -1); mrow[2] = make_int4(1, -1, 1, -1);
+    }
+    return;
+  }
+  lo = imin(lo, imin(imin(li1, ld1), imin(li2, ld2)));
+  hi = imax(hi, imax(imax(hi1, hd1), imax(hi2, hd2)));
+  if (lo < -plen || hi > tlen) exact = true;
+  const int nblo = (lo + BIAS) >> 6, nbhi = (hi + BIAS) >> 6;
+  const int rowlen = (nbhi - nblo + 1) << 6;
+  if (nbhi - nblo + 1 > nblk || (FULL && (s >= P.scap || cell_off + rowlen > P.hcap))) {
+    if (lane == 0) out->kind = 2;
+    return;
+  }
+  const int pad = (PAD && nbhi - nblo + 3 <= nblk) ? 1 : 0;
+  tp += (nblo - tb) << 5;
+  while (tp >= capw) tp -= capw;
+  while (tp < 0) tp += capw;
+  const bool has_i1 = li1 != BIG, has_d1 = ld1 != BIG, has_i2 = TWO_P && li2 != BIG, has_d2 = TWO_P && ld2 != BIG;
+  if (lane == 0) {
+    out->oM = cm * capw;
+    out->oI1 = has_i1 ? rI1 + c1 * capw : -1;
+    out->oD1 = has_d1 ? rD1 + c1 * capw : -1;
+    out->oI2 = has_i2 ? rI2 + c2 * capw : -1;
+    out->oD2 = has_d2 ? rD2 + c2 * capw : -1;
+    out->hrow = nullptr; out->cell_off = cell_off;
+    if (FULL) {
+      out->hrow = vm.h_code + cell_off - 64ll * nblo;
+      HistRow hr; hr.off = cell_off; hr.lo = 64 * nblo - BIAS; hr.pad = 0; vm.hmeta[s] = hr;
+      out->cell_off = cell_off + rowlen;
+    }
+    out->kind = 0; out->exact = exact; out->nblo = nblo; out->nbhi = nbhi; out->tp = tp; out->fl = fl; out->fh = fh; out->pad = pad;
+    const int l1 = has_i1 ? li1 : 1, h1 = has_i1 ? hi1 : -1, l2 = has_d1 ? ld1 : 1, h2 = has_d1 ? hd1 : -1;
+    const int l3 = has_i2 ? li2 : 1, h3 = has_i2 ? hi2 : -1, l4 = has_d2 ? ld2 : 1, h4 = has_d2 ? hd2 : -1;
+    out->lo[CM] = lo; out->hi[CM] = hi;
+    out->lo[CI1] = l1; out->hi[CI1] = h1; out->lo[CD1] = l2; out->hi[CD1] = h2;
+    out->lo[CI2] = l3; out->hi[CI2] = h3; out->lo[CD2] = l4; out->hi[CD2] = h4;
+    if (!exact) {
+      mrow[0] = make_int4(lo, hi, nblo - pad, nbhi + pad);
+      mrow[1] = make_int4(l1, h1, l2, h2);
+      mrow[2] = make_int4(l3, h3, l4, h4);
+    }
+  }
+}
+
+/*
  * Align one pair with a group of NW warps.  Returns PAIR_DONE (res filled; scope=full: runs in
  * vm.runs_stage, res.nruns / res.locs valid on rank 0 only) or PAIR_OVERFLOW.
  */
@@ -492,7 +602,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       const int u0 = imax(imin(tlen, plen + k0), UB_MIN), u1 = imax(imin(tlen, plen + k0 + 1), UB_MIN);
       const int s0 = (k0 >= lo0 && k0 <= hi0) ? imax(k0, 0) : NULL16;
       const int s1 = (k0 + 1 >= lo0 && k0 + 1 <= hi0) ? imax(k0 + 1, 0) : NULL16;
-      finish_m(cx, rM, vm.flags, false, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
+      finish_m<(NW > 1)>(cx, rM, vm.flags, false, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
     }
     for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
     clo[CM] = lo0; chi[CM] = hi0;
@@ -682,7 +792,14 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         pl = vm.plan[s & 1];
         if (exact) pl.exact = 1;
       } else {
-        plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
+        if (NW == 1 && WFA_VEC_SIMD_NW1) {
+          /* one warp per pair: plan across the lanes, exchange through shared memory */
+          plan_step_simd<TWO_P, FULL, false>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, &vm.plan[s & 1]);
+          __syncwarp();
+          pl = vm.plan[s & 1];
+        } else {
+          plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
+        }
       }
       if (pl.kind == 2) return PAIR_OVERFLOW;
       exact = pl.exact != 0;
@@ -709,18 +826,16 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
               if (pl.oI2 >= 0) vm.ring[pl.oI2 + posb + lane] = NULL2;
               if (pl.oD2 >= 0) vm.ring[pl.oD2 + posb + lane] = NULL2;
             }
-          } else if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false>(cx, pl, Fn, exact, b, posb, lane);
-          else vec_block<TWO_P, FULL, true>(cx, pl, Fn, exact, b, posb, lane);
+          } else if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false, (NW > 1)>(cx, pl, Fn, exact, b, posb, lane);
+          else vec_block<TWO_P, FULL, true, (NW > 1)>(cx, pl, Fn, exact, b, posb, lane);
         }
       }
       if (NW > 1) {
         if (pipelined && warp == NW - 1) {
-          PlanOut nx;
           const int ncm = (cm + 1 == P.rm) ? 0 : cm + 1, nc1 = (c1 + 1 == P.r1) ? 0 : c1 + 1;
           const int nc2 = TWO_P ? ((c2 + 1 == P.r2) ? 0 : c2 + 1) : 0;
           __syncwarp();                                    /* lane 0's metadata of score s is visible to the warp */
-          plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s + 1, ncm, nc1, nc2, tp, tb, cell_off, false, lane == 0, nx);
-          if (lane == 0) vm.plan[(s + 1) & 1] = nx;
+          plan_step_simd<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s + 1, ncm, nc1, nc2, tp, tb, cell_off, false, &vm.plan[(s + 1) & 1]);
         }
         have_plan = pipelined;
       }

@@ -218,8 +218,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
       /* per-base sequence windows (one word per base: 16 bases = LDS, LDS, XOR, CLZ) where they are small
        * next to the rings, 2-bit packed words otherwise */
       const long long winw = (long long)b->maxp + b->maxt + 2;
-      const bool seqw_t = 4 * winw <= (nw > 1 ? 16384 : 2560);
-      const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw) + (nw > 1 ? 512 : 0);   /* + step plans of the planner warp */
+      const bool seqw_t = nw > 1 && 4 * winw <= 16384;          /* (the one-warp kernel is compiled without the window variant) */
+      const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw) + 512;   /* + two step plans */
       long long nblk = (budget - fixed) / ((long long)nslots * 128);
       nblk = std::min(nblk, nblk_max);
       if (nblk < 2 || nblk <= last_nblk) return;
@@ -239,8 +239,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const char* only_e = getenv("WFAGPU_VEC_NW");                          /* tests: push everything through one group size */
     const int only = only_e ? atoi(only_e) : 0;
     if (!only || only == 1) {
-      add_vec(1, 11264, 2ll << 20, 16384);
-      if (last_nblk == 0) add_vec(1, 22528, 2ll << 20, 16384);
+      add_vec(1, 11264 + 512, 2ll << 20, 16384);
+      if (last_nblk == 0) add_vec(1, 22528 + 512, 2ll << 20, 16384);
     }
     if (!only || only == 8) add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768);
     if (!only || only == 16) add_vec(16, smem_max - 1024, 64ll << 20, 65536);
