@@ -120,6 +120,7 @@ struct KParams {
   /* global ring arena for the widest tier (elements per group = gring_elems) */
   int* gring; long long gring_elems;
   unsigned long long* cells_total;
+  unsigned long long* dbg;       /* WFA_VEC_TIMING builds only */
   /* register-resident tier (wfa_reg.cuh): per-warp origin-byte arena and edit-operation stack */
   uint8_t* rhist; long long rhist_bytes; int rhrows;
   uint8_t* rops; int ropcap;

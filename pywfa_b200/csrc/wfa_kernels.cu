@@ -436,7 +436,7 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
 
 /* ---- the packed-halfword tier (wfa_vec.cuh): NW warps per pair, rings in shared memory ---- */
 /* shared memory of one group: [metadata int4 x mr*3][flags 256 B][2 step plans 512 B][packed sequences][offset rings] */
-template <bool TWO_P, bool FULL, int NW>
+template <bool TWO_P, bool FULL, int NW, int HEUR>
 __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8 ? 2 : 1) wfa_vec_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int sh_i;
@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
         vm.pw = sp; vm.tw = st;
       }
       vec::gsync<NW>();
-      rc = vec::align_pair_vec<TWO_P, FULL, NW>(P, vm, plen, tlen, res);
+      rc = vec::align_pair_vec<TWO_P, FULL, NW, HEUR>(P, vm, plen, tlen, res);
     }
     if (rc == PAIR_OVERFLOW) {
       if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
@@ -759,33 +759,39 @@ static cudaError_t init_grid(int smem_optin) {
   return cudaFuncSetAttribute(wfa_grid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin);
 }
 
-/* packed-halfword tier: NW = 1 (warp per pair), 8 or 16 warps per pair */
-#define WFA_VEC_DISPATCH(STMT)                                                          \
+/* packed-halfword tier: NW = 1 (warp per pair), 8 or 16 warps per pair; HEUR = 0 none, 1 adaptive, 2 X-drop */
+#define WFA_VEC_DISPATCH_H(STMT, TP, FU, NWW)                                            \
+  do {                                                                                  \
+    if (heur == 0) { STMT(TP, FU, NWW, 0); } else if (heur == 1) { STMT(TP, FU, NWW, 1); } else { STMT(TP, FU, NWW, 2); } \
+  } while (0)
+#define WFA_VEC_DISPATCH_K(STMT, NWW)                                                   \
   do {                                                                                  \
     const int key = (two_p ? 1 : 0) | (full ? 2 : 0);                                   \
-    if (nw == 1) {                                                                      \
-      switch (key) { case 0: STMT(false, false, 1); break; case 1: STMT(true, false, 1); break; \
-                     case 2: STMT(false, true, 1); break; default: STMT(true, true, 1); break; } \
-    } else if (nw == 8) {                                                               \
-      switch (key) { case 0: STMT(false, false, 8); break; case 1: STMT(true, false, 8); break; \
-                     case 2: STMT(false, true, 8); break; default: STMT(true, true, 8); break; } \
-    } else {                                                                            \
-      switch (key) { case 0: STMT(false, false, 16); break; case 1: STMT(true, false, 16); break; \
-                     case 2: STMT(false, true, 16); break; default: STMT(true, true, 16); break; } \
+    switch (key) {                                                                      \
+      case 0: WFA_VEC_DISPATCH_H(STMT, false, false, NWW); break;                       \
+      case 1: WFA_VEC_DISPATCH_H(STMT, true, false, NWW); break;                        \
+      case 2: WFA_VEC_DISPATCH_H(STMT, false, true, NWW); break;                        \
+      default: WFA_VEC_DISPATCH_H(STMT, true, true, NWW); break;                        \
     }                                                                                   \
   } while (0)
+#define WFA_VEC_DISPATCH(STMT)                                                          \
+  do {                                                                                  \
+    if (nw == 1) WFA_VEC_DISPATCH_K(STMT, 1);                                           \
+    else if (nw == 8) WFA_VEC_DISPATCH_K(STMT, 8);                                      \
+    else WFA_VEC_DISPATCH_K(STMT, 16);                                                  \
+  } while (0)
 
-cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int grid, int block, size_t smem, cudaStream_t st) {
-#define WFA_VEC_LAUNCH(TP, FU, NWW) wfa_vec_kernel<TP, FU, NWW><<<grid, block, smem, st>>>(P)
+cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st) {
+#define WFA_VEC_LAUNCH(TP, FU, NWW, HH) wfa_vec_kernel<TP, FU, NWW, HH><<<grid, block, smem, st>>>(P)
   WFA_VEC_DISPATCH(WFA_VEC_LAUNCH);
 #undef WFA_VEC_LAUNCH
   return cudaGetLastError();
 }
 
-int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem) {
+int vec_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t smem) {
   int nb = 0;
-#define WFA_VEC_OCC(TP, FU, NWW) \
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfa_vec_kernel<TP, FU, NWW>, block, smem) != cudaSuccess) nb = 0
+#define WFA_VEC_OCC(TP, FU, NWW, HH) \
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfa_vec_kernel<TP, FU, NWW, HH>, block, smem) != cudaSuccess) nb = 0
   WFA_VEC_DISPATCH(WFA_VEC_OCC);
 #undef WFA_VEC_OCC
   return nb;
@@ -794,14 +800,15 @@ int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem) {
 static cudaError_t init_vec(int smem_optin) {
   cudaError_t e = cudaSuccess;
   for (int nw : {1, 8, 16})
-    for (int k = 0; k < 4; ++k) {
-      const bool two_p = k & 1, full = k & 2;
-#define WFA_VEC_INIT(TP, FU, NWW) \
-  e = cudaFuncSetAttribute(wfa_vec_kernel<TP, FU, NWW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 256)   /* the kernel has a few bytes of static shared memory */
-      WFA_VEC_DISPATCH(WFA_VEC_INIT);
+    for (int heur = 0; heur < 3; ++heur)
+      for (int k = 0; k < 4; ++k) {
+        const bool two_p = k & 1, full = k & 2;
+#define WFA_VEC_INIT(TP, FU, NWW, HH) \
+  e = cudaFuncSetAttribute(wfa_vec_kernel<TP, FU, NWW, HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 256)   /* the kernel has a few bytes of static shared memory */
+        WFA_VEC_DISPATCH(WFA_VEC_INIT);
 #undef WFA_VEC_INIT
-      if (e != cudaSuccess) return e;
-    }
+        if (e != cudaSuccess) return e;
+      }
   return e;
 }
 

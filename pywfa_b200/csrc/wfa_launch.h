@@ -21,8 +21,8 @@ cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int bloc
 int reg_occupancy(int regs, bool full, int block, size_t smem);
 
 /* packed-halfword tier (wfa_vec.cuh): nw = warps per pair (1, 8 or 16) */
-cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int grid, int block, size_t smem, cudaStream_t st);
-int vec_occupancy(bool two_p, bool full, int nw, int block, size_t smem);
+cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st);
+int vec_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t smem);
 
 /* several CTAs per pair (long reads): groups * ncta co-resident CTAs of 512 threads; `scratch` holds
  * grid_scratch_bytes(groups) bytes of device memory */

@@ -545,10 +545,11 @@ __device__ __forceinline__ void plan_step_simd(const KParams& P, const VMem& vm,
 }
 
 /*
- * Align one pair with a group of NW warps.  Returns PAIR_DONE (res filled; scope=full: runs in
+ * Align one pair with a group of NW warps; HEUR = 0 none, 1 WF-adaptive, 2 X-drop (compiled apart: the
+ * step loop has to stay small enough for the instruction cache).  Returns PAIR_DONE (res filled; scope=full: runs in
  * vm.runs_stage, res.nruns / res.locs valid on rank 0 only) or PAIR_OVERFLOW.
  */
-template <bool TWO_P, bool FULL, int NW>
+template <bool TWO_P, bool FULL, int NW, int HEUR>
 __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tlen, PairResult& res) {
   constexpr int GS = NW * 32;
   constexpr int NC = TWO_P ? 5 : 3;
@@ -610,8 +611,15 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     gsync<NW>();
   }
 
+#ifdef WFA_VEC_TIMING   /* debugging build: where the cycles of a step go (per warp; see wfagpu_api.cpp trace) */
+  long long tm_prev = clock64(), tm_acc[6] = {0, 0, 0, 0, 0, 0};
+#define WFA_TM(i) { const long long t_ = clock64(); tm_acc[i] += t_ - tm_prev; tm_prev = t_; }
+#else
+#define WFA_TM(i)
+#endif
   for (;;) {
     /* ---- after-extend step of score s (extend.c:90-125 / :263-297) ---- */
+    WFA_TM(5)
     int* const F = vm.flags + fb * NFLAG;
     if (cur_exists) {
       const int term_k = F[F_TERM];
@@ -626,14 +634,14 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         cells += imax(0, chi[CM] - clo[CM] + 1);
         break;
       }
-      if (P.heuristic != 0 && clo[CM] <= chi[CM]) {
+      if (HEUR != 0 && clo[CM] <= chi[CM]) {
         /* wavefront_heuristic_cufoff, heuristic.c:509-567 */
         --steps_wait;
         const int lo_base = clo[CM], hi_base = chi[CM];
         const uint32_t* const mslot = rM + cm * capw;
         if (steps_wait <= 0) {
           const int hb_lo = (lo_base + BIAS) >> 6, hb_hi = (hi_base + BIAS) >> 6;
-          if (P.heuristic == 1) {
+          if (HEUR == 1) {
             /* wavefront_heuristic_wfadaptive, heuristic.c:257-293 */
             if (hi_base - lo_base + 1 >= P.min_wf_len) {
               int dm = INT_MAX;
@@ -806,8 +814,9 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       tp = pl.tp; tb = pl.nblo; cell_off = pl.cell_off;
       blo = pl.nblo; bhi = pl.nbhi; cur_pad = pl.pad;
       for (int c = 0; c < 5; ++c) { clo[c] = pl.lo[c]; chi[c] = pl.hi[c]; }
+      WFA_TM(1)
       /* the planner may run one score ahead while nothing can invalidate derived ranges */
-      const bool pipelined = NW > 1 && P.heuristic == 0 && !exact;
+      const bool pipelined = NW > 1 && HEUR == 0 && !exact;
       if (pl.kind == 1) {
         cur_exists = false;
       } else {
@@ -830,6 +839,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
           else vec_block<TWO_P, FULL, true, (NW > 1)>(cx, pl, Fn, exact, b, posb, lane);
         }
       }
+      WFA_TM(2)
       if (NW > 1) {
         if (pipelined && warp == NW - 1) {
           const int ncm = (cm + 1 == P.rm) ? 0 : cm + 1, nc1 = (c1 + 1 == P.r1) ? 0 : c1 + 1;
@@ -839,6 +849,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         }
         have_plan = pipelined;
       }
+      WFA_TM(3)
       if (exact && pl.kind == 0) {
         gsync<NW>();
         /* trim_ends, compute.c:571-605: [first in-matrix cell, last in-matrix cell] per component */
@@ -870,6 +881,10 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         }
       }
       gsync<NW>();
+      WFA_TM(4)
+#ifdef WFA_VEC_TIMING
+      ++tm_acc[0];
+#endif
     }
     /* unreachable (extend.c:99-106) and the step limit (unialign.c:98-109), in ORIGINAL score
      * units: between two multiples of g every score is a null step of the reference */
@@ -887,6 +902,9 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     }
   }
 
+#ifdef WFA_VEC_TIMING
+  if (lane == 0 && P.dbg) for (int i = 0; i < 6; ++i) atomicAdd(P.dbg + i, (unsigned long long)tm_acc[i]);
+#endif
   /* ---- wavefront_unialign_terminate, unialign.c:147-237 ---- */
   res.cells = cells;
   res.nruns = 0;

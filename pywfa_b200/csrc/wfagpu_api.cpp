@@ -69,6 +69,7 @@ struct DevCounters {       /* one per batch, in HBM */
   int pad;
   unsigned long long runs_cursor;
   unsigned long long cells_total;
+  unsigned long long dbg[16];   /* WFA_VEC_TIMING builds: cycle counters of the packed-halfword tier */
 };
 
 struct Staging { PinBuf words, meta; };
@@ -310,7 +311,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   }
   for (auto& t : b->tiers) {
     int bps = t.regs ? reg_occupancy(t.regs, b->full, t.threads, t.smem)
-              : t.vec_nw ? vec_occupancy(b->two_p, b->full, t.vec_nw, t.threads, t.smem)
+              : t.vec_nw ? vec_occupancy(b->two_p, b->full, t.vec_nw, k.heuristic, t.threads, t.smem)
                          : align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
     t.blocks_per_sm = std::max(1, bps);
   }
@@ -579,6 +580,7 @@ int batch_upload(wfagpu_ctx* ctx, wfagpu_batch* b, const Staging& sg, cudaStream
   DevCounters* dc = b->counters.as<DevCounters>();
   k.runs_cursor = &dc->runs_cursor;
   k.cells_total = &dc->cells_total;
+  k.dbg = dc->dbg;
   plan_tiers(ctx, b);
   return WFAGPU_OK;
 }
@@ -665,7 +667,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.retry_count = &dc->retry[ti];
       const double tier_t0 = trace_on() ? now_ms() : 0;
       if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
-      else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, blocks, t.threads, t.smem, st));
+      else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
       else if (t.mode == 2) {
         CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
         CK(launch_grid(k, b->two_p, b->full, (int)groups, grid_ctas, t.smem, ctx->gscratch.p, st));
@@ -678,6 +680,10 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         fprintf(stderr, "[wfagpu]   tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d): %lld pairs in, %d overflowed, %.2f ms\n",
                 ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
                 nwork, hc->retry[ti], now_ms() - tier_t0);
+      if (trace_on() && hc->dbg[0])
+        fprintf(stderr, "[wfagpu]     cycles per warp-step: overhead %.0f, blocks %.0f, planner %.0f, barrier wait %.0f, after-barrier %.0f (warp-steps %llu)\n",
+                (double)hc->dbg[1] / hc->dbg[0], (double)hc->dbg[2] / hc->dbg[0], (double)hc->dbg[3] / hc->dbg[0],
+                (double)hc->dbg[4] / hc->dbg[0], (double)hc->dbg[5] / hc->dbg[0], hc->dbg[0]);
       nwork = hc->retry[ti];
       if (ti == 0) b->stats.retried_pairs = nwork;
       cur_list = lists[ti & 1];
