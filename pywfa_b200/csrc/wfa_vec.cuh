@@ -58,9 +58,6 @@ constexpr uint32_t ONE2 = 0x00010001u;
 #ifndef WFA_VEC_PAD
 #define WFA_VEC_PAD 1
 #endif
-#ifndef WFA_VEC_SIMD_NW1
-#define WFA_VEC_SIMD_NW1 0      /* one warp per pair: the lane-parallel planner measured 3 % slower than the one-thread one */
-#endif
 #ifndef WFA_VEC_EXT2
 #define WFA_VEC_EXT2 0      /* interleaving the two extensions of a lane measured slower (r01: -6 % on cfg3) */
 #endif
@@ -800,13 +797,15 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         pl = vm.plan[s & 1];
         if (exact) pl.exact = 1;
       } else {
-        if (NW == 1 && WFA_VEC_SIMD_NW1) {
-          /* one warp per pair: plan across the lanes, exchange through shared memory */
-          plan_step_simd<TWO_P, FULL, false>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, &vm.plan[s & 1]);
-          __syncwarp();
-          pl = vm.plan[s & 1];
+        if (NW == 1) {
+          plan_step<TWO_P, FULL, false>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
         } else {
-          plan_step<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
+          /* start-up and scanned-range steps: every warp runs the lane-parallel planner (same values,
+           * same destination), then the plan is read back like a precomputed one -- the kernel carries
+           * ONE planner, which keeps the step loop small */
+          plan_step_simd<TWO_P, FULL, (NW > 1) && WFA_VEC_PAD>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, &vm.plan[s & 1]);
+          gsync<NW>();
+          pl = vm.plan[s & 1];
         }
       }
       if (pl.kind == 2) return PAIR_OVERFLOW;
