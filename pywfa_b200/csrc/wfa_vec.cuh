@@ -620,6 +620,9 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
     int* const F = vm.flags + fb * NFLAG;
     if (cur_exists) {
       const int term_k = F[F_TERM];
+#ifdef WFA_VEC_TIMING
+      if (F[F_EDGE] && !exact && lane == 0 && P.dbg) atomicAdd(P.dbg + 8, 1ull);
+#endif
       if (F[F_EDGE]) exact = true;
       if (term_k != KNONE) {
         end_k = term_k;
@@ -739,7 +742,12 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
                 const int wi = (k + BIAS) >> 1;
                 int pos = tp + (((wi >> 5) - tb) << 5); if (pos >= capw) pos -= capw;
                 const uint32_t w = slots[c][pos + (wi & 31)];
-                if ((((k + BIAS) & 1) ? lv::sx_hi(w) : lv::sx_lo(w)) < 0) exact = true;
+                if ((((k + BIAS) & 1) ? lv::sx_hi(w) : lv::sx_lo(w)) < 0) {
+#ifdef WFA_VEC_TIMING
+                  if (!exact && lane == 0 && P.dbg) atomicAdd(P.dbg + 9 + c, 1ull);
+#endif
+                  exact = true;
+                }
               }
             }
           }

@@ -684,6 +684,9 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         fprintf(stderr, "[wfagpu]     cycles per warp-step: overhead %.0f, blocks %.0f, planner %.0f, barrier wait %.0f, after-barrier %.0f (warp-steps %llu)\n",
                 (double)hc->dbg[1] / hc->dbg[0], (double)hc->dbg[2] / hc->dbg[0], (double)hc->dbg[3] / hc->dbg[0],
                 (double)hc->dbg[4] / hc->dbg[0], (double)hc->dbg[5] / hc->dbg[0], hc->dbg[0]);
+      if (trace_on() && hc->dbg[0])
+        fprintf(stderr, "[wfagpu]     scanned-range mode entered through: matrix edge %llu, cut-off end cell M %llu I1 %llu D1 %llu I2 %llu D2 %llu\n",
+                hc->dbg[8], hc->dbg[9], hc->dbg[10], hc->dbg[11], hc->dbg[12], hc->dbg[13]);
       nwork = hc->retry[ti];
       if (ti == 0) b->stats.retried_pairs = nwork;
       cur_list = lists[ti & 1];
