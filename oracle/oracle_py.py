@@ -190,6 +190,12 @@ def align_batch(cfg: Config, seq: np.ndarray, p_off, p_len, t_off, t_len, kind="
     p_len = np.ascontiguousarray(p_len, np.int32)
     t_len = np.ascontiguousarray(t_len, np.int32)
     n = len(p_len)
+    if cfg.span == 1 and n:
+        # the reference exit(1)s on free ends longer than a sequence (W/wavefront/wavefront_align.c:89-100);
+        # a checker must refuse them too instead of reading outside the DP matrix
+        if (max(cfg.pattern_begin_free, cfg.pattern_end_free) > int(p_len.min())
+                or max(cfg.text_begin_free, cfg.text_end_free) > int(t_len.min())):
+            raise ValueError("ends-free parameters larger than a sequence of the batch")
     score = np.zeros(n, np.int32)
     status = np.zeros(n, np.int32)
     cells = np.zeros(n, np.int64)

@@ -469,6 +469,22 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
 
 extern "C" const char* wfagpu_last_error(const wfagpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
+/* host copy of a result array out of the pinned landing zone: a few threads for large arrays (one
+ * core moves ~8 GB/s; the last chunk's copy is not overlapped by anything) */
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  const size_t kMin = 1u << 20;
+  if (bytes < 2 * kMin) { memcpy(dst, src, bytes); return; }
+  const int parts = (int)std::min<size_t>(4, bytes / kMin);
+  const size_t step = ((bytes / parts) + 63) & ~(size_t)63;
+  std::vector<std::thread> th;
+  for (int i = 1; i < parts; ++i) {
+    const size_t off = step * i, len = std::min(step, bytes - std::min(bytes, off));
+    if (len) th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, len); });
+  }
+  memcpy(dst, src, std::min(step, bytes));
+  for (auto& t : th) t.join();
+}
+
 static double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -853,7 +869,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     if (want > 0) chunk = want;
     else if (n >= 524288) chunk = std::max<int64_t>(262144, (n + 7) / 8);
     int64_t first = chunk;
-    if (want <= 0 && n >= 524288) first = std::min<int64_t>(chunk, std::max<int64_t>(131072, n / 40));
+    if (want <= 0 && n >= 524288) first = std::min<int64_t>(chunk, std::max<int64_t>(65536, n / 40));
     starts.push_back(0);
     /* ramp up by 1.5x per chunk: packing chunk c+1 must not take longer than the GPU needs for chunk c */
     int64_t cur = first;
@@ -1009,13 +1025,13 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
         const unsigned char* base = ctx->out_stage[c & 1].as<unsigned char>();
         const size_t m = (size_t)d.m;
         if (d.full) {
-          if (cig_off) memcpy(cig_off + d.off, base, 8 * (m + (d.last ? 1 : 0)));
-          if (locs) memcpy(locs + 4 * d.off, base + 8 * (m + 1), 16 * m);
-          if (score) memcpy(score + d.off, base + 8 * (m + 1) + 16 * m, 4 * m);
-          if (status) memcpy(status + d.off, base + 8 * (m + 1) + 20 * m, 4 * m);
+          if (cig_off) par_memcpy(cig_off + d.off, base, 8 * (m + (d.last ? 1 : 0)));
+          if (locs) par_memcpy(locs + 4 * d.off, base + 8 * (m + 1), 16 * m);
+          if (score) par_memcpy(score + d.off, base + 8 * (m + 1) + 16 * m, 4 * m);
+          if (status) par_memcpy(status + d.off, base + 8 * (m + 1) + 20 * m, 4 * m);
         } else {
-          if (score) memcpy(score + d.off, base, 4 * m);
-          if (status) memcpy(status + d.off, base + 4 * m, 4 * m);
+          if (score) par_memcpy(score + d.off, base, 4 * m);
+          if (status) par_memcpy(status + d.off, base + 4 * m, 4 * m);
           if (locs && m) memset(locs + 4 * d.off, 0, 16 * m);
           if (cig_off) for (size_t i = 0; i < m + (d.last ? 1 : 0); ++i) cig_off[d.off + i] = d.run_base;
         }

@@ -36,6 +36,9 @@ CASES = [
     ("cfg5-proxy-10kbp-2p-e2e", dict(distance="affine2p", span="end-to-end"), 3, 10000, 0.20, 0),
     ("long-low-divergence-2kbp", dict(span="end-to-end"), 200, 2000, 0.01, 0),
     ("mixed-lengths-bwa-like-penalties", dict(span="end-to-end", mismatch=4, gap_opening=6, gap_extension=1), 2000, 180, 0.08, 0),
+    # > 4096 scores in units of gcd 1: crosses the re-basing of drifting I/D nulls of the packed-halfword tier
+    ("renorm-4kbp-gcd1-5000-scores", dict(span="end-to-end", mismatch=5, gap_opening=7, gap_extension=2), 12, 4000, 0.25, 0),
+    ("near-vec-length-limit-12kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 12, 11900, 0.05, 0),
 ]
 
 
