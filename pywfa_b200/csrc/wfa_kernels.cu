@@ -269,7 +269,7 @@ struct GridGroup {
 };
 
 template <bool TWO_P, bool FULL>
-__global__ void __launch_bounds__(512, 1) wfa_grid_kernel(const __grid_constant__ KParams P, GridScratch* scratch, int ncta) {
+__global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant__ KParams P, GridScratch* scratch, int ncta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NC = TWO_P ? 5 : 3;
   GridGroup g;
@@ -749,6 +749,14 @@ cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int
   const void* fn = two_p ? (full ? (const void*)wfa_grid_kernel<true, true> : (const void*)wfa_grid_kernel<true, false>)
                          : (full ? (const void*)wfa_grid_kernel<false, true> : (const void*)wfa_grid_kernel<false, false>);
   return cudaLaunchCooperativeKernel(fn, dim3(groups * ncta), dim3(512), args, smem, st);
+}
+
+int grid_occupancy(bool two_p, bool full, size_t smem) {
+  int nb = 0;
+  const void* fn = two_p ? (full ? (const void*)wfa_grid_kernel<true, true> : (const void*)wfa_grid_kernel<true, false>)
+                         : (full ? (const void*)wfa_grid_kernel<false, true> : (const void*)wfa_grid_kernel<false, false>);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, 512, smem) != cudaSuccess) nb = 0;
+  return nb;
 }
 
 static cudaError_t init_grid(int smem_optin) {

@@ -27,6 +27,7 @@ int vec_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t sme
 /* several CTAs per pair (long reads): groups * ncta co-resident CTAs of 512 threads; `scratch` holds
  * grid_scratch_bytes(groups) bytes of device memory */
 size_t grid_scratch_bytes(int groups);
+int grid_occupancy(bool two_p, bool full, size_t smem);   /* resident CTAs per SM */
 cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int ncta, size_t smem, void* scratch, cudaStream_t st);
 
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the

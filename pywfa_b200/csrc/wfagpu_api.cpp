@@ -300,17 +300,17 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     t.smem = (size_t)t.group_bytes + block_reduce_smem_bytes();
     t.hcap = cells_bound;
     t.scap = (int)std::min<long long>(2 * scap_bound, INT_MAX / 4);
-    if (b->full) t.max_groups = 64;
     b->tiers.push_back(t);
     if (b->full) {
       /* scope=full: the origin bytes of a 100 kbp pair need ~10 GB; pairs whose history outgrows
-       * an even split of the free HBM are redone with fewer pairs in flight */
-      t.max_groups = 12; b->tiers.push_back(t);
-      t.max_groups = 2; b->tiers.push_back(t);
+       * an even split of the free HBM over the pairs in flight are redone with fewer neighbours */
+      t.max_groups = 4; b->tiers.push_back(t);
+      t.max_groups = 1; b->tiers.push_back(t);
     }
   }
   for (auto& t : b->tiers) {
     int bps = t.regs ? reg_occupancy(t.regs, b->full, t.threads, t.smem)
+              : t.mode == 2 ? grid_occupancy(b->two_p, b->full, t.smem)
               : t.vec_nw ? vec_occupancy(b->two_p, b->full, t.vec_nw, k.heuristic, t.threads, t.smem)
                          : align_occupancy(b->two_p, b->full, t.mode, t.off16, t.threads, t.smem);
     t.blocks_per_sm = std::max(1, bps);
@@ -632,8 +632,20 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         groups = blocks;
         if (t.mode == 2) {
           /* several CTAs per pair: all SMs work even when only a few pairs fit in HBM */
-          groups = std::min<long long>(groups, ctx->sms);
-          grid_ctas = std::max(1, ctx->sms / (int)groups);
+          /* CTAs per pair: between ~16 and ~2 diagonals per thread and score (a wavefront is about half
+           * as wide as the sequences are long).  Few pairs: one CTA per SM and as many CTAs per pair as
+           * that allows (two CTAs sharing an SM lengthen every score's critical path); many pairs: two
+           * CTAs per SM and the fewest CTAs per pair, which keeps the per-score barrier short.
+           * Measured r01: 8 x 10 kbp 68 ms (18 CTAs/pair) vs 83 (8) vs 116 (37, 2/SM); 16 x 100 kbp
+           * 3.9 s (24 CTAs/pair, 2/SM) vs 5.4 s (49) vs 9.1 s (9, 1/SM). */
+          const long long L = (long long)b->maxp + b->maxt;
+          const int resident2 = ctx->sms * std::max(1, t.blocks_per_sm);     /* co-resident CTAs (cooperative launch) */
+          const int ncta_min = (int)std::min<long long>(resident2, std::max<long long>(1, L / 8192));
+          const int ncta_max = (int)std::min<long long>(resident2, std::max<long long>(1, L / 1024));
+          groups = std::min<long long>(groups, std::max(1, resident2 / ncta_min));
+          const int resident = (groups * ncta_min <= ctx->sms) ? ctx->sms : resident2;
+          grid_ctas = std::max(1, std::min(std::max(resident / (int)groups, ncta_min), ncta_max));
+          if ((long long)grid_ctas * groups > resident2) grid_ctas = std::max(1, resident2 / (int)groups);
           blocks = (int)groups;
         }
       }
