@@ -571,6 +571,8 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
   int s = 0, cm = 0, c1 = 0, c2 = 0, fb = 0;
   int s_exist = 0, steps_wait = P.steps_between, max_sw = 0;
   bool sw_init = false, exact = false, cur_exists = true;
+  bool sticky = false;                          /* scanned ranges for good: an offset touched the matrix border */
+  int exact_until = -1;                         /* scanned ranges up to this score: a cut-off left a null end cell in a wavefront still in the ring */
   long long cells = 0, cell_off = 0;
   int clo[5], chi[5];
   int end_k = KNONE, end_off = OFFNULL, end_score = 0, status = 0;
@@ -623,7 +625,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
 #ifdef WFA_VEC_TIMING
       if (F[F_EDGE] && !exact && lane == 0 && P.dbg) atomicAdd(P.dbg + 8, 1ull);
 #endif
-      if (F[F_EDGE]) exact = true;
+      if (F[F_EDGE]) { exact = true; sticky = true; }
       if (term_k != KNONE) {
         end_k = term_k;
         const int wi = (term_k + BIAS) >> 1;
@@ -733,8 +735,9 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
             if (chi[CM] < chi[c]) chi[c] = chi[CM];
           }
           uint32_t* const slots[5] = {rM + cm * capw, rI1 + c1 * capw, rD1 + c1 * capw, rI2 + c2 * capw, rD2 + c2 * capw};
-          if (!exact) {
-            /* the derived ranges of later scores assume valid end cells: otherwise scan from now on */
+          if (!sticky) {
+            /* the derived ranges of later scores assume valid end cells: otherwise scan while this
+             * wavefront can still be a source (max look-back = ring depth) */
             for (int c = 0; c < NC; ++c) {
               if (clo[c] > chi[c]) continue;
               for (int e = 0; e < 2; ++e) {
@@ -746,7 +749,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
 #ifdef WFA_VEC_TIMING
                   if (!exact && lane == 0 && P.dbg) atomicAdd(P.dbg + 9 + c, 1ull);
 #endif
-                  exact = true;
+                  exact_until = s + P.rm;
                 }
               }
             }
@@ -798,12 +801,13 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       }
       gsync<NW>();
     }
+    if (HEUR != 0) exact = sticky || s <= exact_until;
     {
       /* plan of this score: precomputed by the planner warp during the previous step, or by everybody now */
       PlanOut pl;
       if (NW > 1 && have_plan) {
         pl = vm.plan[s & 1];
-        if (exact) pl.exact = 1;
+        if (exact) pl.exact = 1;      /* (multi-warp groups never run cut-offs pipelined: exact here means sticky) */
       } else {
         if (NW == 1) {
           plan_step<TWO_P, FULL, false>(P, vm, plen, tlen, s, cm, c1, c2, tp, tb, cell_off, exact, is_writer, pl);
@@ -817,6 +821,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         }
       }
       if (pl.kind == 2) return PAIR_OVERFLOW;
+      if (pl.exact != 0 && !exact) sticky = true;        /* the planned range left the matrix */
       exact = pl.exact != 0;
       tp = pl.tp; tb = pl.nblo; cell_off = pl.cell_off;
       blo = pl.nblo; bhi = pl.nbhi; cur_pad = pl.pad;

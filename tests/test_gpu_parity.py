@@ -176,6 +176,27 @@ def test_long_reads_cigar_consistency(gpu_ctx, oracle):
         assert -cost == got["score"][i] == sc["score"][i]
 
 
+def test_long_reads_against_reference_golden(gpu_ctx, oracle):
+    """cfg5 (100 kbp, 20 %, affine2p, end-to-end, full CIGAR through the several-CTAs-per-pair tier)
+    against golden vectors of the unmodified reference in its low-memory mode
+    (tests/golden/make_golden_long.py: score, status and a SHA-256 of the CIGAR run words)."""
+    import glob
+    import hashlib
+    import json
+    import os
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long_reads_*.json")))
+    assert files, "tests/golden/long_reads_*.json missing"
+    for path in files:
+        g = json.load(open(path))
+        gen = g["generator"]
+        batch = generate_pairs(gen["n"], gen["length"], gen["div"], seed=gen["seed"])
+        got = gpu_ctx.align_batch(oracle.make_config(**g["config"]), *batch)
+        for i, want in enumerate(g["pairs"]):
+            runs = np.ascontiguousarray(got["runs"][got["cig_off"][i]:got["cig_off"][i + 1]], np.uint32)
+            assert (int(got["score"][i]), int(got["status"][i]), len(runs)) == (want["score"], want["status"], want["nruns"]), (path, i)
+            assert hashlib.sha256(runs.tobytes()).hexdigest() == want["runs_sha256"], (path, i)
+
+
 def test_empty_batch(gpu_ctx, oracle):
     cfg = oracle.make_config()
     z64, z32 = np.zeros(0, np.int64), np.zeros(0, np.int32)

@@ -84,3 +84,21 @@ def test_oracle_matches_reference_live(oracle, name, kw, n, length, div, flank):
             assert np.array_equal(ref[k], port[k]), (name, bt, k)
         if kw.get("scope", "full") == "full":
             assert np.array_equal(ref["cells"], port["cells"])
+
+
+def test_oracle_matches_long_read_golden(oracle):
+    """The port against the reference's low-memory mode on 20 kbp affine2p pairs
+    (tests/golden/long_reads_20kbp.json, made by make_golden_long.py); the 100 kbp vectors are
+    checked on the GPU only (the port keeps the full history in host memory)."""
+    import hashlib
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "long_reads_20kbp.json")
+    g = json.load(open(path))
+    gen = g["generator"]
+    batch = generate_pairs(gen["n"], gen["length"], gen["div"], seed=gen["seed"])
+    r = oracle.align_batch(oracle.make_config(**g["config"]), *batch, kind="port")
+    for i, want in enumerate(g["pairs"]):
+        runs = np.ascontiguousarray(r["runs"][r["cig_off"][i]:r["cig_off"][i + 1]], np.uint32)
+        assert (int(r["score"][i]), int(r["status"][i]), len(runs)) == (want["score"], want["status"], want["nruns"])
+        assert hashlib.sha256(runs.tobytes()).hexdigest() == want["runs_sha256"]
