@@ -694,18 +694,20 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
 }
 
 /* register tier: instantiated for the penalty shapes (x, o+e, e)/gcd = (2, 4, 1) -- pywfa's
- * default 4/6/2 -- and windows of 128 / 256 diagonals */
+ * default 4/6/2 -- and windows of 128 / 192 / 256 diagonals */
 #define WFA_REG_DISPATCH(STMT)                                  \
   do {                                                          \
     if (regs == 2) {                                            \
       if (full) { STMT(2, 2, 4, true); } else { STMT(2, 2, 4, false); } \
+    } else if (regs == 3) {                                     \
+      if (full) { STMT(3, 2, 4, true); } else { STMT(3, 2, 4, false); } \
     } else {                                                    \
       if (full) { STMT(4, 2, 4, true); } else { STMT(4, 2, 4, false); } \
     }                                                           \
   } while (0)
 
 bool reg_tier_supported(int dx, int doe, int de, int regs) {
-  return dx == 2 && doe == 4 && de == 1 && (regs == 2 || regs == 4);
+  return dx == 2 && doe == 4 && de == 1 && (regs >= 2 && regs <= 4);
 }
 
 cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st) {
@@ -726,7 +728,7 @@ int reg_occupancy(int regs, bool full, int block, size_t smem) {
 
 static cudaError_t init_reg(int smem_optin) {
   cudaError_t e = cudaSuccess;
-  for (int regs = 2; regs <= 4; regs += 2)
+  for (int regs = 2; regs <= 4; ++regs)
     for (int full = 0; full < 2; ++full) {
 #define WFA_REG_INIT(PP, DX, DOE, FULL) \
   e = cudaFuncSetAttribute(wfa_reg_kernel<PP, DX, DOE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)

@@ -195,8 +195,10 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const bool no_reg = getenv("WFAGPU_NO_REG_TIER") != nullptr;            /* tests / debugging */
   const int winw = b->maxp + b->maxt + 2;       /* sequence windows: one word per base */
   if (!no_reg && !b->two_p && k.heuristic == 0 && std::max(b->maxp, b->maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
-    const int first = std::max(b->maxp, b->maxt) <= 192 ? 2 : 4;
-    for (int regs = first; regs <= 4; regs += 2) {
+    const int maxlen = std::max(b->maxp, b->maxt);
+    const int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;     /* window the typical pair of this length needs */
+    for (int regs = first; regs <= 4; ++regs) {
+      if (regs == 3 && first == 2) continue;                         /* 128 -> 256 directly: few pairs get that far */
       if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs)) continue;
       Tier t;
       t.regs = regs; t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = 64 * regs;

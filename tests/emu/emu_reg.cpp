@@ -60,6 +60,7 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
     if (plen > REG_MAX_LEN || tlen > REG_MAX_LEN) rc = PAIR_OVERFLOW;
     else if (regs == 1) rc = run_pair<1, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
     else if (regs == 2) rc = run_pair<2, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
+    else if (regs == 3) rc = run_pair<3, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
     else if (regs == 4) rc = run_pair<4, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
     else return -3;
     cig_off[i] = used;

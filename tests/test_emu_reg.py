@@ -64,6 +64,10 @@ CASES = [
     ("cfg1-endsfree-default-128", dict(), 1000, 150, 0.05, 0, 2, 0.0),
     ("cfg2-score-256", dict(span="end-to-end", scope="score"), 800, 250, 0.10, 0, 4, 0.0),
     ("cfg2-full-256", dict(span="end-to-end"), 500, 250, 0.10, 0, 4, 0.0),
+    ("cfg2-score-192", dict(span="end-to-end", scope="score"), 800, 250, 0.10, 0, 3, 0.15),
+    ("cfg2-full-192", dict(span="end-to-end"), 500, 250, 0.10, 0, 3, 0.15),
+    ("endsfree-all-four-192", dict(pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7),
+     600, 200, 0.10, 4, 3, 0.1),
     ("cfg2-score-128-overflows", dict(span="end-to-end", scope="score"), 300, 250, 0.10, 0, 2, 1.0),
     ("endsfree-all-four", dict(pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7),
      1000, 150, 0.10, 4, 4, 0.0),
