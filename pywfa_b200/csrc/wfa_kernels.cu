@@ -5,7 +5,9 @@
  *       pairs from a device work queue and runs wfagpu::align_pair (wfa_core.cuh) on them.
  *       MODE 0: warp-per-pair, wavefront ring + packed sequences in shared memory
  *       MODE 1: block-per-pair, ring in shared memory
- *       MODE 2: block-per-pair, ring in an L2-resident HBM arena (very wide wavefronts)
+ *   wfa_vec_kernel<TWO_P, FULL, NW, HEUR>   packed-halfword tier (wfa_vec.cuh): the general case up to 12 kbp
+ *   wfa_grid_kernel<TWO_P, FULL>   several CTAs per pair, rings in an L2-resident HBM arena (long reads)
+ *   wfa_reg_kernel<P, DX, DOE, FULL>   register-resident tier (wfa_reg.cuh): short gap-affine reads
  *   cigar_count_kernel / cigar_scan_kernel / cigar_gather_kernel   order the per-pair CIGAR
  *       runs into the caller's layout (cig_off[n+1] + contiguous run words).
  *
@@ -676,11 +678,7 @@ static int occupancy_one(int block, size_t smem) {
       case 4: return FN<false, false, 1, int32_t>(__VA_ARGS__);                 \
       case 5: return FN<true, false, 1, int32_t>(__VA_ARGS__);                  \
       case 6: return FN<false, true, 1, int32_t>(__VA_ARGS__);                  \
-      case 7: return FN<true, true, 1, int32_t>(__VA_ARGS__);                   \
-      case 8: return FN<false, false, 2, int32_t>(__VA_ARGS__);                 \
-      case 9: return FN<true, false, 2, int32_t>(__VA_ARGS__);                  \
-      case 10: return FN<false, true, 2, int32_t>(__VA_ARGS__);                 \
-      default: return FN<true, true, 2, int32_t>(__VA_ARGS__);                  \
+      default: return FN<true, true, 1, int32_t>(__VA_ARGS__);                  \
     }                                                                           \
   } while (0)
 
@@ -831,8 +829,8 @@ static cudaError_t init_dispatch(bool two_p, bool full, int mode, bool off16, in
 cudaError_t init_kernels(int smem_optin) {
   for (int two_p = 0; two_p < 2; ++two_p)
     for (int full = 0; full < 2; ++full)
-      for (int mode = 0; mode < 3; ++mode)
-        for (int off16 = 0; off16 < (mode <= 1 ? 2 : 1); ++off16) {
+      for (int mode = 0; mode < 2; ++mode)         /* (the HBM-ring mode runs as wfa_grid_kernel) */
+        for (int off16 = 0; off16 < 2; ++off16) {
           const cudaError_t e = init_dispatch(two_p, full, mode, off16, smem_optin);
           if (e != cudaSuccess) return e;
         }
