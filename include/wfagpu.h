@@ -81,7 +81,9 @@ typedef struct wfagpu_config {
   int32_t gap_opening2;
   int32_t gap_extension2;
   int32_t max_steps;               /* <= 0 means unlimited (align.pyx:415)   */
-  int32_t reserved;
+  int32_t wildcard;                /* 0: none; else the (upper-case) byte that matches every base --
+                                      pywfa's wildcard= kwarg, wavefront_align_lambda with
+                                      wildcard_match_fun (pywfa/align.pyx:297-304,438-442)          */
 } wfagpu_config_t;
 
 typedef struct wfagpu_ctx wfagpu_ctx;       /* one per CUDA device            */

@@ -30,7 +30,7 @@ _FIELDS = [
     "heuristic", "min_wavefront_length", "max_distance_threshold",
     "steps_between_cutoffs", "xdrop",
     "match", "mismatch", "gap_opening1", "gap_extension1", "gap_opening2", "gap_extension2",
-    "max_steps", "reserved",
+    "max_steps", "wildcard",
 ]
 
 
@@ -49,7 +49,7 @@ def make_config(distance="affine", match=0, mismatch=4, gap_opening=6, gap_exten
                 gap_opening2=24, gap_extension2=1, scope="full", span="ends-free",
                 pattern_begin_free=0, pattern_end_free=0, text_begin_free=0, text_end_free=0,
                 heuristic=None, min_wavefront_length=10, max_distance_threshold=50,
-                steps_between_cutoffs=1, xdrop=20, max_steps=0) -> Config:
+                steps_between_cutoffs=1, xdrop=20, max_steps=0, wildcard=None) -> Config:
     """kwargs with the names/defaults of pywfa's constructor (pywfa/align.pyx:309-334)."""
     return Config(
         distance=_DIST[distance], scope=_SCOPE[scope], span=_SPAN[span],
@@ -59,7 +59,8 @@ def make_config(distance="affine", match=0, mismatch=4, gap_opening=6, gap_exten
         max_distance_threshold=max_distance_threshold,
         steps_between_cutoffs=steps_between_cutoffs, xdrop=xdrop,
         match=match, mismatch=mismatch, gap_opening1=gap_opening, gap_extension1=gap_extension,
-        gap_opening2=gap_opening2, gap_extension2=gap_extension2, max_steps=max_steps, reserved=0)
+        gap_opening2=gap_opening2, gap_extension2=gap_extension2, max_steps=max_steps,
+        wildcard=ord(wildcard.upper()) if wildcard else 0)
 
 
 def build(ref: bool | None = None) -> None:

@@ -91,6 +91,14 @@ static int64_t ref_count_cells(wavefront_aligner_t* a) {
   return cells;
 }
 
+/* wildcard_fun_args / wildcard_match_fun of pywfa/align.pyx:297-304 */
+typedef struct { const char* pattern; const char* query; char wildcard; } ref_wildcard_args_t;
+static int ref_wildcard_match(int pattern_pos, int query_pos, void* argsptr) {
+  const ref_wildcard_args_t* a = (const ref_wildcard_args_t*)argsptr;
+  return a->pattern[pattern_pos] == a->wildcard || a->query[query_pos] == a->wildcard ||
+         a->pattern[pattern_pos] == a->query[query_pos];
+}
+
 /*
  * Align one pair.  ops receives the raw operation characters
  * cigar->operations[begin_offset, end_offset) (no terminator); returns the
@@ -99,7 +107,13 @@ static int64_t ref_count_cells(wavefront_aligner_t* a) {
 int ref_align(void* handle, const char* pattern, int plen, const char* text, int tlen,
               int32_t* score, int32_t* status, char* ops, int ops_cap, int64_t* cells) {
   ref_handle_t* h = (ref_handle_t*)handle;
-  wavefront_align(h->aligner, pattern, plen, text, tlen);
+  if (h->cfg.wildcard) {
+    /* pywfa/align.pyx:438-442: the wildcard goes through wavefront_align_lambda */
+    ref_wildcard_args_t args = {pattern, text, (char)h->cfg.wildcard};
+    wavefront_align_lambda(h->aligner, ref_wildcard_match, &args, plen, tlen);
+  } else {
+    wavefront_align(h->aligner, pattern, plen, text, tlen);
+  }
   cigar_t* cg = h->aligner->cigar;
   if (score) *score = cg->score;
   if (status) *status = h->aligner->align_status.status;

@@ -169,7 +169,10 @@ static void init_wf0(oracle_t* o) {
 /* ---- extend: extend_kernels.c:64-88 (the sentinels clamp at either sequence end) ----- */
 static inline int32_t extend_cell(const oracle_t* o, int k, int32_t off) {
   int v = off - k, h = off;
-  while (v < o->plen && h < o->tlen && o->p[v] == o->t[h]) { ++v; ++h; ++off; }
+  /* with a wildcard: wildcard_match_fun of pywfa/align.pyx:302-304 through wavefront_extend_matches_custom
+   * (extend_kernels.c:167-203) and wavefront_sequences_cmp (wavefront_sequences.c:226-252) */
+  const int w = o->cfg.wildcard;
+  while (v < o->plen && h < o->tlen && (o->p[v] == o->t[h] || (w && ((uint8_t)o->p[v] == w || (uint8_t)o->t[h] == w)))) { ++v; ++h; ++off; }
   return off;
 }
 /* wavefront_termination_endsfree, termination.c:115-162 */

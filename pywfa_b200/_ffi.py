@@ -19,7 +19,7 @@ CONFIG_FIELDS = [
     "heuristic", "min_wavefront_length", "max_distance_threshold",
     "steps_between_cutoffs", "xdrop",
     "match", "mismatch", "gap_opening1", "gap_extension1", "gap_opening2", "gap_extension2",
-    "max_steps", "reserved",
+    "max_steps", "wildcard",
 ]
 
 

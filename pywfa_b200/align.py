@@ -12,7 +12,7 @@ through ``libwfagpu.so``; there is no CPU fallback.
 Intentional deviations from the reference:
   * configurations the reference ``exit(1)``s on raise ``ValueError`` before any launch;
   * distances other than ``affine`` / ``affine2p``, ``memory_mode="biwfa"`` (different
-    tie-breaks), wildcards and non-ACGT bases raise ``NotImplementedError``.
+    tie-breaks); non-ACGT bases and the wildcard are aligned in the library's byte mode.
 """
 from __future__ import annotations
 
@@ -456,14 +456,18 @@ class WavefrontAligner:
 
     @wildcard.setter
     def wildcard(self, wildcard):
+        # pywfa/align.pyx:709-719; the byte goes to the C ABI, whose extension then treats it as
+        # "matches every base" (wildcard_match_fun, pywfa/align.pyx:302-304)
         if wildcard is None:
             self._wildcard = None
+            self._cfg.wildcard = 0
             return
         if not isinstance(wildcard, str):
             raise TypeError(f"expected wildcard to be a string, but it is {type(wildcard)}")
         if len(wildcard) > 1:
             raise ValueError(f"wildcard must have length 1, but has length {len(wildcard)}")
-        raise NotImplementedError("wildcard matching is not on the B200 accelerated path")
+        self._wildcard = wildcard
+        self._cfg.wildcard = wildcard.upper().encode("ascii")[0] if wildcard else 0
 
     @property
     def max_steps(self):

@@ -180,14 +180,15 @@ static void parallel_for(int nthreads, int64_t n, F&& fn) {
 }
 
 int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, PairMetaHost* meta,
-                     int32_t* max_plen, int32_t* max_tlen) {
+                     int32_t* max_plen, int32_t* max_tlen, int bases_per_word) {
+  const int64_t bpw = bases_per_word;
   const int nt = pack_threads(n, n * 16);
   std::vector<int64_t> part(nt + 1, 0);
   std::vector<int32_t> mp(nt, 0), mt(nt, 0);
   parallel_for(nt, n, [&](int t, int64_t a, int64_t b) {
     int64_t s = 0; int32_t xp = 0, xt = 0;
     for (int64_t i = a; i < b; ++i) {
-      s += ((int64_t)p_len[i] + 15) / 16 + ((int64_t)t_len[i] + 15) / 16;
+      s += ((int64_t)p_len[i] + bpw - 1) / bpw + ((int64_t)t_len[i] + bpw - 1) / bpw;
       xp = std::max(xp, p_len[i]); xt = std::max(xt, t_len[i]);
     }
     part[t + 1] = s; mp[t] = xp; mt[t] = xt;
@@ -197,7 +198,7 @@ int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, Pair
     int64_t off = part[t];
     for (int64_t i = a; i < b; ++i) {
       meta[i].woff = off; meta[i].plen = p_len[i]; meta[i].tlen = t_len[i];
-      off += ((int64_t)p_len[i] + 15) / 16 + ((int64_t)t_len[i] + 15) / 16;
+      off += ((int64_t)p_len[i] + bpw - 1) / bpw + ((int64_t)t_len[i] + bpw - 1) / bpw;
     }
   });
   *max_plen = *std::max_element(mp.begin(), mp.end());
@@ -223,6 +224,24 @@ int64_t pack_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_of
   });
   const int64_t fb = first_bad.load();
   return fb == INT64_MAX ? -1 : fb;
+}
+
+void pack_pairs_bytes(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
+                      const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint) {
+  const int nt = pack_threads(n, seq_bytes_hint);
+  auto put = [](const uint8_t* s, int len, uint32_t* out) {
+    /* upper-case a-z like pywfa does before the C call (pywfa/align.pyx:431-435); byte j of a word in bits 8j.. */
+    uint8_t* o = reinterpret_cast<uint8_t*>(out);
+    for (int i = 0; i < len; ++i) { const uint8_t c = s[i]; o[i] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+    for (int i = len; i < ((len + 3) & ~3); ++i) o[i] = 0;
+  };
+  parallel_for(nt, n, [&](int, int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) {
+      uint32_t* w = words + meta[i].woff;
+      put(seq + p_off[i], meta[i].plen, w);
+      put(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
+    }
+  });
 }
 
 void parallel_copy(void* dst, const void* src, size_t bytes) {

@@ -96,6 +96,8 @@ struct KParams {
   int pbf, pef, tbf, tef;
   int heuristic, min_wf_len, max_dist_thr, steps_between, xdrop;
   int max_steps;                 /* INT_MAX = unlimited */
+  int byte_mode;                 /* sequences are bytes (4 per word) instead of 2-bit codes: non-ACGT input / wildcard */
+  int wildcard;                  /* byte mode: 0 or the byte that matches everything */
   /* tier capacities */
   int wcap;                      /* wavefront width capacity per ring slot: power of two */
   int seq_words_cap;             /* words of smem for both packed sequences (0: read HBM) */
@@ -178,10 +180,34 @@ WFA_DEV uint32_t fetch16(const uint32_t* w, int i) {
  * W/wavefront/wavefront_extend_kernels.c:64-88, does 8 bytes at a time with sentinels):
  * here 16 bases per XOR, clamped to the sequence ends instead of sentinels.
  */
-WFA_DEV int extend_offset(const uint32_t* pw, const uint32_t* tw, int plen, int tlen, int k, int off) {
+/* Byte mode (any ASCII, optional wildcard): 4 bases per word, byte j of a word in bits 8j..8j+7.
+ * `wild` = 0 or the wildcard byte: a position matches if the bytes are equal or either one is the
+ * wildcard -- wildcard_match_fun of pywfa/align.pyx:302-304, reached in the reference through
+ * wavefront_extend_matches_custom (W/wavefront/wavefront_extend_kernels.c:167-203). */
+WFA_DEV uint32_t fetch4(const uint32_t* w, int i) {
+  const int j = i >> 2;
+  return funnel_r(w[j], w[j + 1], (i & 3) << 3);
+}
+/* 0x80 in every byte of x that is zero (exact, no carries between bytes) */
+WFA_DEV uint32_t zero_bytes(uint32_t x) {
+  return ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x | 0x7f7f7f7fu);
+}
+WFA_DEV int extend_offset(const uint32_t* pw, const uint32_t* tw, int plen, int tlen, int k, int off, int wild = -1) {
   const int v = off - k, h = off;
   const int rem = imin(plen - v, tlen - h);
   int n = 0;
+  if (wild >= 0) {
+    const uint32_t w4 = (uint32_t)wild * 0x01010101u;
+    while (n < rem) {
+      const uint32_t a = fetch4(pw, v + n), b = fetch4(tw, h + n);
+      uint32_t eq = zero_bytes(a ^ b);
+      if (wild) eq |= zero_bytes(a ^ w4) | zero_bytes(b ^ w4);
+      const uint32_t ne = ~eq & 0x80808080u;
+      if (ne) { n += first_set(ne) >> 3; break; }
+      n += 4;
+    }
+    return off + imin(n, rem);
+  }
   while (n < rem) {
     const uint32_t x = fetch16(pw, v + n) ^ fetch16(tw, h + n);
     if (x) { n += first_set(x) >> 1; break; }
@@ -250,12 +276,12 @@ enum { EOP_X = 0, EOP_I_OPEN = 1, EOP_I_EXT = 2, EOP_D_OPEN = 3, EOP_D_EXT = 4 }
  * prefix, leading matches, operations with their match runs, free suffix.
  */
 WFA_DEV void replay_ops(const uint8_t* ops, int nops, int k, int plen, int tlen, const uint32_t* pw, const uint32_t* tw,
-                        FwdEmitter& em) {
+                        FwdEmitter& em, int wild = -1) {
   int off = k > 0 ? k : 0;
   em.push(OP_I, k > 0 ? k : 0);            /* free text prefix (ends-free seeds) */
   em.push(OP_D, k < 0 ? -k : 0);           /* free pattern prefix */
   {
-    const int e = extend_offset(pw, tw, plen, tlen, k, off);
+    const int e = extend_offset(pw, tw, plen, tlen, k, off, wild);
     em.push(OP_M, e - off); off = e;
   }
   for (int i = nops - 1; i >= 0; --i) {
@@ -270,7 +296,7 @@ WFA_DEV void replay_ops(const uint8_t* ops, int nops, int k, int plen, int tlen,
       at_m = !(i > 0 && ops[i - 1] == EOP_D_EXT);
     }
     if (at_m) {
-      const int e = extend_offset(pw, tw, plen, tlen, k, off);
+      const int e = extend_offset(pw, tw, plen, tlen, k, off, wild);
       em.push(OP_M, e - off); off = e;
     }
   }
@@ -318,7 +344,7 @@ WFA_DEV int backtrace_codes(const KParams& P, const uint8_t* h_code, const HistR
     else if (op == EOP_D_OPEN || op == EOP_D_EXT) ++k;
   }
   if (nops > opcap) return -1;
-  replay_ops(ops, nops, k, plen, tlen, pw, tw, em);
+  replay_ops(ops, nops, k, plen, tlen, pw, tw, em, P.byte_mode ? P.wildcard : -1);
   return em.n;
 }
 
@@ -364,6 +390,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
   const int wcap = P.wcap, wmask = P.wcap - 1, mmask = P.mr - 1;
   int4* const meta = gm.meta;
   const int ak = tlen - plen;
+  const int wild = P.byte_mode ? P.wildcard : -1;    /* -1: 2-bit packed sequences */
 
   int s = 0;                                  /* score in units of g */
   int cm = 0, c1 = 0, c2 = 0;                 /* ring slots of the current score */
@@ -392,7 +419,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     OffT* const mslot = gm.ring[CM];
     for (int k = lo + g.rank; k <= hi; k += g.size) {
       const int off0 = k > 0 ? k : 0;
-      const int off = extend_offset(gm.pw, gm.tw, plen, tlen, k, off0);
+      const int off = extend_offset(gm.pw, gm.tw, plen, tlen, k, off0, wild);
       mslot[k & wmask] = (OffT)off;
       if (term_cell(P, plen, tlen, ak, k, off)) t = imin(t, k);
     }
@@ -410,7 +437,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     if (cur_exists) {
       if (term_k != KNONE) {
         end_k = term_k;
-        end_off = (int)ld_cg(gm.ring[CM] + cm * wcap + (term_k & wmask));
+        end_off = G::kGrid ? (int)ld_cg(gm.ring[CM] + cm * wcap + (term_k & wmask)) : (int)gm.ring[CM][cm * wcap + (term_k & wmask)];   /* (shared-memory rings: plain load) */
         status = 1; end_score = s * P.g;
         cells += imax(0, chi[CM] - clo[CM] + 1);
         break;
@@ -602,7 +629,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           }
           if (m_in) {
             red[0] = imin(red[0], k); red[1] = imin(red[1], -k);
-            mx = extend_offset(gm.pw, gm.tw, plen, tlen, k, mx);
+            mx = extend_offset(gm.pw, gm.tw, plen, tlen, k, mx, wild);
             if (term_cell(P, plen, tlen, ak, k, mx)) red[10] = imin(red[10], k);
           }
           oM[km] = off_store<OffT>(mx);

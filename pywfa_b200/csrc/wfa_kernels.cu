@@ -135,7 +135,8 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     const int pid = P.worklist ? P.worklist[w] : w;
     const PairMeta pm = P.pairs[pid];
     const int plen = pm.plen, tlen = pm.tlen;
-    const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+    const int wsh = P.byte_mode ? 2 : 4;                  /* bases per word: 4 (bytes) or 16 (2-bit) */
+    const int pwn = (plen + (1 << wsh) - 1) >> wsh, twn = (tlen + (1 << wsh) - 1) >> wsh;
     int rc;
     PairResult res;
     if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || tier_gives_up(P, w)) {
@@ -311,7 +312,8 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
     const int pid = P.worklist ? P.worklist[w] : w;
     const PairMeta pm = P.pairs[pid];
     const int plen = pm.plen, tlen = pm.tlen;
-    const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+    const int wsh = P.byte_mode ? 2 : 4;
+    const int pwn = (plen + (1 << wsh) - 1) >> wsh, twn = (tlen + (1 << wsh) - 1) >> wsh;
     int rc;
     PairResult res;
     if (P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) {

@@ -121,6 +121,7 @@ struct wfagpu_batch {
   int32_t maxp = 0, maxt = 0;
   int64_t total_words = 0;
   bool two_p = false, full = false;
+  bool byte_mode = false;       /* sequences uploaded as bytes: non-ACGT input or a wildcard (scalar tiers only) */
   KParams kp;
   std::vector<Tier> tiers;
   DevBuf pairs, words, score, status, locs, nruns, runs_base, runs_tmp, retry_a, retry_b, counters,
@@ -182,7 +183,8 @@ size_t group_bytes_of(const KParams& k, bool two_p, int seqw, int wcap, int elem
 
 void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const KParams& k = b->kp;
-  const int seqw = (b->maxp + 15) / 16 + (b->maxt + 15) / 16 + 2;
+  const int bpw = b->byte_mode ? 4 : 16;                  /* bases per sequence word */
+  const int seqw = (b->maxp + bpw - 1) / bpw + (b->maxt + bpw - 1) / bpw + 2;
   const long long wmax = (long long)b->maxp + b->maxt + 1;
   const int wmax2 = pow2_ceil(std::max<long long>(wmax, 32));
   const long long sb = std::min<long long>(score_bound(k, b->maxp, b->maxt), k.max_steps);
@@ -194,7 +196,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   /* register-resident tiers first: gap-affine, no heuristic, instantiated penalty shape, short reads */
   const bool no_reg = getenv("WFAGPU_NO_REG_TIER") != nullptr;            /* tests / debugging */
   const int winw = b->maxp + b->maxt + 2;       /* sequence windows: one word per base */
-  if (!no_reg && !b->two_p && k.heuristic == 0 && std::max(b->maxp, b->maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
+  if (!no_reg && !b->byte_mode && !b->two_p && k.heuristic == 0 && std::max(b->maxp, b->maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
     const int maxlen = std::max(b->maxp, b->maxt);
     const int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;     /* window the typical pair of this length needs */
     for (int regs = first; regs <= 4; ++regs) {
@@ -212,7 +214,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
    * leave two / one CTA per SM */
   const bool no_vec = getenv("WFAGPU_NO_VEC_TIER") != nullptr;            /* tests / debugging */
   bool vec_covers_smem = false;
-  if (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN) {
+  const bool use_vec = !no_vec && !b->byte_mode && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN;   /* byte mode: scalar tiers */
+  if (use_vec) {
     const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
     const long long fixed0 = (long long)k.mr * 48 + 256 + 4ll * seqw;
     const long long nblk_max = (wmax + 63) / 64 + 1;
@@ -250,7 +253,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   }
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
-    if (vec_covers_smem || (!no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN)) return;   /* the vec tiers replace the scalar shared-memory tiers */
+    if (vec_covers_smem || use_vec) return;   /* the vec tiers replace the scalar shared-memory tiers */
     wcap = std::min(wcap, wmax2);
     if (wcap <= last_wcap) return;
     Tier t;
@@ -278,7 +281,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const long long elem = short_reads ? 2 : 4;
     int wcap = avail > elem * ns * 32 ? pow2_floor(avail / (elem * ns)) : 0;
     wcap = std::min(wcap, wmax2);
-    const bool vec_has = !no_vec && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN;
+    const bool vec_has = use_vec;
     if (!vec_has && (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2))) {
       Tier t;
       t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
@@ -349,6 +352,7 @@ extern "C" int wfagpu_config_check(const wfagpu_config_t* c, int64_t plen, int64
   if (c->span != WFAGPU_SPAN_END2END && c->span != WFAGPU_SPAN_ENDSFREE) { set_err(err, errlen, "bad span %d", c->span); return WFAGPU_EINVAL; }
   if (c->heuristic < WFAGPU_HEURISTIC_NONE || c->heuristic > WFAGPU_HEURISTIC_XDROP) { set_err(err, errlen, "bad heuristic %d", c->heuristic); return WFAGPU_EINVAL; }
   /* wavefront_penalties_set_affine/_affine2p, W/wavefront/wavefront_penalties.c:95-173 */
+  if (c->wildcard < 0 || c->wildcard > 255) { set_err(err, errlen, "wildcard must be 0 (none) or one byte"); return WFAGPU_EINVAL; }
   if (c->match > 0) { set_err(err, errlen, "[WFA::Penalties] Match score must be negative or zero (M=%d)", c->match); return WFAGPU_EINVAL; }
   if (c->mismatch <= 0 || c->gap_opening1 < 0 || c->gap_extension1 <= 0) {
     set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O=%d,E=%d) must be (X>0,O>=0,E>0)", c->mismatch, c->gap_opening1, c->gap_extension1);
@@ -545,14 +549,26 @@ int batch_pack(wfagpu_ctx* ctx, wfagpu_batch* b, Staging& sg, const wfagpu_confi
       if (rc != WFAGPU_OK) return fail(ctx, rc, "pair %lld: %s", (long long)(first_pair + i), msg);
     }
   }
-  b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt);
-  if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
-  CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
-  uint32_t* words = sg.words.as<uint32_t>();
-  const int64_t bad = pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes);
-  if (bad >= 0)
-    return fail(ctx, WFAGPU_EUNSUPPORTED, "pair %lld holds a base other than A/C/G/T: the 2-bit accelerated path cannot represent it",
-                (long long)(first_pair + bad));
+  /* 2-bit codes unless a wildcard can match one of ACGT; a batch holding any other byte is packed
+   * again as bytes (byte mode: the extension compares 4 bases per word and honours the wildcard) */
+  const int wc = cfg->wildcard & 0xff;
+  const bool wc_is_base = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
+  b->byte_mode = wc_is_base;
+  uint32_t* words = nullptr;
+  if (!b->byte_mode) {
+    b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt);
+    if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
+    CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
+    words = sg.words.as<uint32_t>();
+    if (pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes) >= 0) b->byte_mode = true;
+  }
+  if (b->byte_mode) {
+    b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt, 4);
+    if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
+    CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
+    words = sg.words.as<uint32_t>();
+    pack_pairs_bytes(seq, p_off, t_off, meta, n, words, seq_bytes);
+  }
   words[b->total_words] = 0;
   return WFAGPU_OK;
 }
@@ -589,6 +605,8 @@ int batch_upload(wfagpu_ctx* ctx, wfagpu_batch* b, const Staging& sg, cudaStream
   }
   KParams& k = b->kp;
   fill_kparams(b->cfg, k);
+  k.byte_mode = b->byte_mode ? 1 : 0;
+  k.wildcard = b->cfg.wildcard & 0xff;
   k.pairs = b->pairs.as<PairMeta>();
   k.words = b->words.as<uint32_t>();
   k.score = b->score.as<int>(); k.status = b->status.as<int>();

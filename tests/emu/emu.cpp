@@ -78,8 +78,18 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
   for (int64_t i = 0; i < n; ++i) {
     const int plen = p_len[i], tlen = t_len[i];
     std::vector<uint32_t> pw((plen + 15) / 16 + 1, 0), tw((tlen + 15) / 16 + 1, 0);
-    if (!pack_sequence(seq + p_off[i], plen, pw.data())) return -2;
-    if (!pack_sequence(seq + t_off[i], tlen, tw.data())) return -2;
+    const int wc = cfg->wildcard & 0xff;
+    bool bytes = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
+    if (!bytes) bytes = !pack_sequence(seq + p_off[i], plen, pw.data()) || !pack_sequence(seq + t_off[i], tlen, tw.data());
+    if (bytes) {
+      /* byte mode of the library (wfagpu_api.cpp batch_pack): upper-cased bytes, 4 per word */
+      pw.assign((plen + 3) / 4 + 1, 0); tw.assign((tlen + 3) / 4 + 1, 0);
+      auto put = [](const uint8_t* s8, int len, uint32_t* out) {
+        for (int j = 0; j < len; ++j) { uint8_t c = s8[j]; if (c >= 'a' && c <= 'z') c -= 32; out[j >> 2] |= (uint32_t)c << (8 * (j & 3)); }
+      };
+      put(seq + p_off[i], plen, pw.data()); put(seq + t_off[i], tlen, tw.data());
+    }
+    P.byte_mode = bytes ? 1 : 0; P.wildcard = wc;
     std::vector<uint32_t> stage((size_t)plen + tlen + 2);
     P.runcap = (int)stage.size();
     PairResult res;

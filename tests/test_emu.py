@@ -144,3 +144,43 @@ def test_host_packer(emu):
         assert got == codes.tolist()
     bad = np.frombuffer(b"ACGTNACGT" * 8, np.uint8).copy()
     assert emu.lib.emu_pack(bad, len(bad), np.zeros(8, np.uint32)) == 0
+
+
+def _pairs_with_n(seed, n, lo, hi, p_n=0.04, t_n=0.05):
+    """Mutated pairs sprinkled with N (and a few lower-case / IUPAC bytes)."""
+    rng = np.random.default_rng(seed)
+    rnd = lambda m, alpha="ACGT": "".join(alpha[i] for i in rng.integers(0, len(alpha), m))
+    pairs = []
+    for _ in range(n):
+        p = list(rnd(int(rng.integers(lo, hi))))
+        t = list(p)
+        for j in range(len(t)):
+            r = rng.random()
+            if r < 0.05: t[j] = rnd(1)
+            elif r < 0.08: t[j] = ""
+            elif r < 0.11: t[j] += rnd(2)
+            elif r < 0.11 + t_n: t[j] = "N"
+            elif r < 0.12 + t_n: t[j] = "r"
+        for j in range(len(p)):
+            if rng.random() < p_n: p[j] = "N"
+        pairs.append(("".join(p), "".join(t)))
+    return pairs
+
+
+BYTE_KW = [dict(span="end-to-end"), dict(span="end-to-end", wildcard="N"), dict(distance="affine2p", wildcard="N"),
+           dict(heuristic="adaptive", wildcard="N", span="end-to-end"), dict(span="end-to-end", wildcard="A", scope="score"),
+           dict(pattern_begin_free=3, text_end_free=5, wildcard="N")]
+
+
+@pytest.mark.parametrize("kw", BYTE_KW, ids=[str(i) for i in range(len(BYTE_KW))])
+def test_byte_mode_non_acgt_and_wildcard(emu, oracle, kw):
+    """non-ACGT bytes and pywfa's wildcard= (wildcard_match_fun, pywfa/align.pyx:302-304): the device
+    source in byte mode (4 bases per word) against the checker, which itself is checked against the
+    reference's wavefront_align_lambda path in test_oracle.py"""
+    batch = pairs_from_strings(_pairs_with_n(5, 300, 20, 220))
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu(cfg, batch, wcap=2048)
+    assert not got["ovf"].any()
+    for k in ("score", "status", "cig_off", "runs", "locs"):
+        assert np.array_equal(got[k], want[k]), (kw, k)

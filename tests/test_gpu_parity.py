@@ -39,6 +39,9 @@ CASES = [
     # > 4096 scores in units of gcd 1: crosses the re-basing of drifting I/D nulls of the packed-halfword tier
     ("renorm-4kbp-gcd1-5000-scores", dict(span="end-to-end", mismatch=5, gap_opening=7, gap_extension=2), 12, 4000, 0.25, 0),
     ("near-vec-length-limit-12kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 12, 11900, 0.05, 0),
+    # beyond the packed-halfword tier's length limit with a narrow band: the scalar shared-memory tiers
+    ("scalar-tiers-20kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 24, 20000, 0.10, 0),
+    ("scalar-tiers-20kbp-xdrop-2p", dict(distance="affine2p", heuristic="X-drop", xdrop=400, scope="score"), 24, 20000, 0.05, 0),
 ]
 
 
@@ -137,6 +140,27 @@ def test_vec_tier_every_group_size(gpu_ctx, oracle, monkeypatch, nw):
         want = oracle.align_batch(cfg, *synth, kind="port")
         got = gpu_ctx.align_batch(cfg, *synth)
         assert_same(got, want, what=f"vec nw={nw} synthetic {kw}")
+
+
+def test_byte_mode_non_acgt_and_wildcard(gpu_ctx, oracle):
+    """Batches holding N / IUPAC / lower-case bytes, and pywfa's wildcard= kwarg (wildcard_match_fun,
+    pywfa/align.pyx:302-304): the library uploads bytes instead of 2-bit codes and the scalar tiers
+    extend 4 bases per word; bit-exact against the checker (itself pinned to the reference's
+    wavefront_align_lambda path in test_oracle.py)."""
+    from test_emu import _pairs_with_n, BYTE_KW
+    short = pairs_from_strings(_pairs_with_n(21, 3000, 20, 300))
+    longer = pairs_from_strings(_pairs_with_n(22, 60, 2500, 3500, p_n=0.01, t_n=0.01))
+    for batch in (short, longer):
+        for kw in BYTE_KW:
+            cfg = oracle.make_config(**kw)
+            want = oracle.align_batch(cfg, *batch, kind="port")
+            got = gpu_ctx.align_batch(cfg, *batch)
+            assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"byte mode {kw}")
+    # a wildcard that never occurs leaves pure-ACGT batches on the 2-bit fast path, with the same result
+    plain = generate_pairs(2000, 150, 0.05, seed=5)
+    a = gpu_ctx.align_batch(oracle.make_config(span="end-to-end"), *plain)
+    b = gpu_ctx.align_batch(oracle.make_config(span="end-to-end", wildcard="N"), *plain)
+    assert_same(b, a, what="wildcard N on ACGT-only input")
 
 
 def _check_cigar(runs, pattern, text, x, o1, e1, o2, e2):
@@ -257,5 +281,9 @@ def test_python_api_single_and_batch(gpu_ctx):
     assert br.score.tolist()[:2] == [-24, 0] and br.cigarstring(0) == "3M1X4M1D7M1I9M1X6M" and br.cigarstring(1) == "32M"
     r0 = br.result(0)
     assert (r0.pattern_start, r0.pattern_end, r0.text_start, r0.text_end) == (0, 32, 0, 32)
-    with pytest.raises(NotImplementedError):
-        a.align_batch(["ACGTNNNN"])
+    # non-ACGT bases no longer raise: the library switches the batch to its byte mode
+    bn = a.align_batch(["TCTTTACTNGCGCGTTGGAGAAATACAATAGT", "ACGTNNNN"])
+    assert bn.cigarstring(0) == "8M1X23M" and bn.score.tolist()[0] == -4
+    w = pywfa_b200.WavefrontAligner("TCTTTACTCGCGCGTTGGAGAAATACAATAGT", wildcard="N")
+    rw = w("TCTTTACTNGCGCGTTGGAGAAATACAATAGT")
+    assert (rw.score, rw.cigarstring) == (0, "32M")

@@ -71,6 +71,22 @@ LIVE = [
 ]
 
 
+def test_oracle_matches_reference_live_wildcard(oracle):
+    """non-ACGT bytes and the wildcard (pywfa/align.pyx:297-304,438-442): the port against the
+    reference's wavefront_align_lambda path"""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    from test_emu import _pairs_with_n, BYTE_KW
+    from pywfa_b200.synth import pairs_from_strings
+    batch = pairs_from_strings(_pairs_with_n(11, 400, 20, 260))
+    for kw in BYTE_KW:
+        cfg = oracle.make_config(**kw)
+        ref = oracle.align_batch(cfg, *batch, kind="reference")
+        port = oracle.align_batch(cfg, *batch, kind="port")
+        for k in ("score", "status", "cig_off", "runs"):
+            assert np.array_equal(ref[k], port[k]), (kw, k)
+
+
 @pytest.mark.parametrize("name,kw,n,length,div,flank", LIVE, ids=[c[0] for c in LIVE])
 def test_oracle_matches_reference_live(oracle, name, kw, n, length, div, flank):
     if not oracle.have_ref():
