@@ -388,13 +388,13 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
     hbm_bytes, int_ops = algorithmic_figures(stats, n_pairs, length, float(np.mean(batch[4])), two_p, full)
-    kernel_s = ms_per_step / 1e3            # the align kernel is >99% of the step (see profiles/)
+    kernel_s = ms_per_step / 1e3            # the register-tier kernels are >99% of the step (see profiles/)
     achieved = hbm_bytes / kernel_s / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
     int_peak = 148 * 128 * sm_mhz * 1e6     # INT32 lane-ops/s at the clock seen under load
     # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, one launch, from the committed
     # `ncu --set full` capture of this exact command (profiles/r01_reg_cfg2_10M_ncu_summary.txt)
-    traffic = 1.470791e9 + 87.846144e6 if (args.workload == "cfg2" and n_pairs == 10_000_000) else None
+    traffic = 1.483855e9 + 87.523584e6 if (args.workload == "cfg2" and n_pairs == 10_000_000) else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "integer-DP kernel: HBM is not the binding resource (SURVEY.md 8(d)); see int_issue",
