@@ -221,6 +221,28 @@ def test_long_reads_against_reference_golden(gpu_ctx, oracle):
             assert hashlib.sha256(runs.tobytes()).hexdigest() == want["runs_sha256"], (path, i)
 
 
+def test_fastx_streaming(gpu_ctx, oracle, tmp_path):
+    """FASTA in, batches out (pywfa_b200.fastx.align_fastx): same results as aligning the strings."""
+    import pywfa_b200
+    from test_emu import _pairs_with_n
+    pairs = _pairs_with_n(9, 700, 30, 200, p_n=0.0, t_n=0.002)
+    with open(tmp_path / "p.fa", "w") as fp, open(tmp_path / "t.fa", "w") as ft:
+        for i, (p, t) in enumerate(pairs):
+            fp.write(f">p{i}\n{p}\n")
+            ft.write(f">t{i} text\n" + "\n".join(t[j:j + 60] for j in range(0, len(t), 60)) + "\n")
+    a = pywfa_b200.WavefrontAligner(span="end-to-end")
+    want = oracle.align_batch(oracle.make_config(span="end-to-end"), *pairs_from_strings(pairs), kind="port")
+    seen = 0
+    for names, br in pywfa_b200.align_fastx(a, tmp_path / "t.fa", tmp_path / "p.fa", batch_size=256):
+        n = len(names)
+        assert names[0] == (f"p{seen}", f"t{seen}")
+        assert br.score.tolist() == want["score"][seen:seen + n].tolist()
+        for i in (0, n - 1):
+            assert br.cigarstring(i) == oracle.runs_to_cigarstring(want["runs"][want["cig_off"][seen + i]:want["cig_off"][seen + i + 1]])
+        seen += n
+    assert seen == len(pairs)
+
+
 def test_empty_batch(gpu_ctx, oracle):
     cfg = oracle.make_config()
     z64, z32 = np.zeros(0, np.int64), np.zeros(0, np.int32)

@@ -170,3 +170,26 @@ def test_alignment_result_helpers():
     assert "ALIGNMENT" in r.pretty and "|||*||||" in r.pretty
     assert "score: -4" in repr(r)
     assert str(AlignmentResult(0, 0, 0, 0, 0, 0, [], -3, "", "", 0)) == "Score: -3"
+
+
+def test_fastx_reader(tmp_path):
+    """FASTA (wrapped lines, comments, blank lines), FASTQ and gzip through pywfa_b200.fastx.read_fastx
+    (what pysam.FastxFile does for the reference's tests, pywfa/tests/test.py:198-232)."""
+    import gzip
+
+    from pywfa_b200.fastx import _batch_arrays, read_fastx
+    fa = tmp_path / "a.fa"
+    fa.write_text(">r1 first record\nACGT\nacgtn\n\n>r2\nTTTT\n>empty\n")
+    recs = list(read_fastx(fa))
+    assert [(r.name, r.sequence, r.comment) for r in recs] == [("r1", "ACGTacgtn", "first record"), ("r2", "TTTT", None), ("empty", "", None)]
+    fq = tmp_path / "b.fq.gz"
+    with gzip.open(fq, "wt") as fh:
+        fh.write("@q1 c\nACGTN\n+\nIIII#\n@q2\nGG\n+q2\n!!\n")
+    recs = list(read_fastx(fq))
+    assert [(r.name, r.sequence, r.quality) for r in recs] == [("q1", "ACGTN", "IIII#"), ("q2", "GG", "!!")]
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@q1\nACGT\n+\nII\n")
+    with pytest.raises(ValueError):
+        list(read_fastx(bad))
+    seq, po, pl, to, tl = _batch_arrays([b"ACG", b"T"], [b"AC", b"TTTT"])
+    assert seq.tobytes() == b"ACGACTTTTT\0" and po.tolist() == [0, 5] and to.tolist() == [3, 6] and pl.tolist() == [3, 1] and tl.tolist() == [2, 4]
