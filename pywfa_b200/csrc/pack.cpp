@@ -207,10 +207,12 @@ int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, Pair
 }
 
 int64_t pack_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
-                   const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint) {
+                   const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint,
+                   std::vector<int64_t>* bad) {
   const int nt = pack_threads(n, seq_bytes_hint);
   std::atomic<int64_t> first_bad(INT64_MAX);
-  parallel_for(nt, n, [&](int, int64_t a, int64_t b) {
+  std::vector<std::vector<int64_t>> bad_t(nt);
+  parallel_for(nt, n, [&](int tid, int64_t a, int64_t b) {
     for (int64_t i = a; i < b; ++i) {
       uint32_t* w = words + meta[i].woff;
       const int pw = (meta[i].plen + 15) / 16;
@@ -219,27 +221,52 @@ int64_t pack_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_of
       if (!ok) {
         int64_t cur = first_bad.load();
         while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
+        if (bad) bad_t[tid].push_back(i);
       }
     }
   });
+  if (bad) {
+    bad->clear();
+    for (auto& v : bad_t) bad->insert(bad->end(), v.begin(), v.end());     /* threads own ascending ranges */
+    std::sort(bad->begin(), bad->end());
+  }
   const int64_t fb = first_bad.load();
   return fb == INT64_MAX ? -1 : fb;
+}
+
+static void put_bytes(const uint8_t* s, int len, uint32_t* out) {
+  /* upper-case a-z like pywfa does before the C call (pywfa/align.pyx:431-435); byte j of a word in bits 8j.. */
+  uint8_t* o = reinterpret_cast<uint8_t*>(out);
+  for (int i = 0; i < len; ++i) { const uint8_t c = s[i]; o[i] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+  for (int i = len; i < ((len + 3) & ~3); ++i) o[i] = 0;
+}
+
+int64_t layout_side_pairs(const std::vector<int64_t>& ids, PairMetaHost* meta) {
+  int64_t off = 0;
+  for (int64_t i : ids) {
+    meta[i].woff = ~off;
+    off += ((int64_t)meta[i].plen + 3) / 4 + ((int64_t)meta[i].tlen + 3) / 4;
+  }
+  return off;
+}
+
+void pack_side_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off, const PairMetaHost* meta,
+                     const std::vector<int64_t>& ids, uint32_t* words2) {
+  for (int64_t i : ids) {
+    uint32_t* w = words2 + ~meta[i].woff;
+    put_bytes(seq + p_off[i], meta[i].plen, w);
+    put_bytes(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
+  }
 }
 
 void pack_pairs_bytes(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
                       const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint) {
   const int nt = pack_threads(n, seq_bytes_hint);
-  auto put = [](const uint8_t* s, int len, uint32_t* out) {
-    /* upper-case a-z like pywfa does before the C call (pywfa/align.pyx:431-435); byte j of a word in bits 8j.. */
-    uint8_t* o = reinterpret_cast<uint8_t*>(out);
-    for (int i = 0; i < len; ++i) { const uint8_t c = s[i]; o[i] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
-    for (int i = len; i < ((len + 3) & ~3); ++i) o[i] = 0;
-  };
   parallel_for(nt, n, [&](int, int64_t a, int64_t b) {
     for (int64_t i = a; i < b; ++i) {
       uint32_t* w = words + meta[i].woff;
-      put(seq + p_off[i], meta[i].plen, w);
-      put(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
+      put_bytes(seq + p_off[i], meta[i].plen, w);
+      put_bytes(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
     }
   });
 }

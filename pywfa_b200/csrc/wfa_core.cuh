@@ -80,7 +80,8 @@ struct HistRow {       /* scope=full: where the origin bytes of one score live *
 };
 
 struct PairMeta {      /* 16 bytes, one per pair, in HBM */
-  int64_t woff;        /* first 32-bit word of the packed pattern; text words follow it */
+  int64_t woff;        /* first 32-bit word of the packed pattern; text words follow it.  Negative: the pair holds
+                          a non-ACGT byte, its sequences are BYTES at words2 + ~woff (scalar tiers only) */
   int32_t plen, tlen;
 };
 
@@ -109,10 +110,12 @@ struct KParams {
   /* batch */
   const PairMeta* pairs;
   const uint32_t* words;
+  const uint32_t* words2;        /* byte-packed sequences of the pairs whose PairMeta::woff is negative (= ~offset into words2) */
   const int* worklist;           /* pair ids, or nullptr = identity */
   const int* n_work;             /* device pointer to the number of work items */
   int* work_counter;
   int* retry_list; int* retry_count;
+  int* done_count; int* ovf_count;   /* pairs this tier tried so far / of those, beyond its capacity (tier_gives_up) */
   int skip_groups;               /* > 0: groups in flight; a tier that overflows most of its first pairs forwards the rest */
   /* results (SoA) */
   int* score; int* status; int* locs; int* nruns; long long* runs_base;
@@ -132,6 +135,7 @@ struct KParams {
 template <class OffT>
 struct GroupMem {
   const uint32_t* pw; const uint32_t* tw;   /* packed sequences, readable one word past the end */
+  int wild;                                 /* -1: 2-bit codes; >= 0: bytes (4 per word), value = wildcard byte or 0 */
   OffT* ring[5];
   int4* meta;                               /* [mr][NC] : lo, hi, ring slot, exists */
   uint8_t* h_code; HistRow* hmeta; uint32_t* runs_stage;
@@ -231,14 +235,23 @@ WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
 }
 
 /*
- * Adaptive tier skipping: once at least 256 pairs of this launch have finished and three quarters
- * of them exceeded the tier's capacity, the remaining pairs are forwarded to the next tier
+ * Adaptive tier skipping: once at least 256 pairs of this launch have left the tier and three quarters
+ * of them exceeded its capacity, the remaining pairs are forwarded to the next tier
  * unprocessed (their partial work would be thrown away).  w = index of the work item just fetched.
  */
 WFA_DEV bool tier_gives_up(const KParams& P, int w) {
-  if (P.skip_groups <= 0 || w < P.skip_groups + 256) return false;
-  const int overflowed = ld_cg(P.retry_count);
-  return 4ll * overflowed > 3ll * (w - P.skip_groups);
+  if (P.skip_groups <= 0 || w < 256) return false;
+  const int done = ld_cg(P.done_count);
+  if (done < 256) return false;
+  return 4ll * ld_cg(P.ovf_count) > 3ll * done;
+}
+/* one pair this tier actually tried left it (one thread of the group); pairs that were forwarded
+ * untried -- given up on, or byte-mode pairs on a 2-bit tier -- do not count: they finish at once
+ * and would dominate the first 256 */
+WFA_DEV void tier_pair_note(const KParams& P, bool overflowed) {
+#ifdef __CUDA_ARCH__
+  if (P.skip_groups > 0) { atomicAdd(P.done_count, 1); if (overflowed) atomicAdd(P.ovf_count, 1); }
+#endif
 }
 
 /* one source wavefront component as the recurrence reads it */
@@ -313,7 +326,7 @@ WFA_DEV void replay_ops(const uint8_t* ops, int nops, int k, int plen, int tlen,
  */
 WFA_DEV int backtrace_codes(const KParams& P, const uint8_t* h_code, const HistRow* hmeta, int a_score, int a_k,
                             int plen, int tlen, const uint32_t* pw, const uint32_t* tw, uint8_t* ops, int opcap,
-                            FwdEmitter& em) {
+                            FwdEmitter& em, int wild = -1) {
   int mt = CM, score = a_score, k = a_k, nops = 0;
   while (score > 0) {
     HistRow hm;
@@ -344,7 +357,7 @@ WFA_DEV int backtrace_codes(const KParams& P, const uint8_t* h_code, const HistR
     else if (op == EOP_D_OPEN || op == EOP_D_EXT) ++k;
   }
   if (nops > opcap) return -1;
-  replay_ops(ops, nops, k, plen, tlen, pw, tw, em, P.byte_mode ? P.wildcard : -1);
+  replay_ops(ops, nops, k, plen, tlen, pw, tw, em, wild);
   return em.n;
 }
 
@@ -390,7 +403,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
   const int wcap = P.wcap, wmask = P.wcap - 1, mmask = P.mr - 1;
   int4* const meta = gm.meta;
   const int ak = tlen - plen;
-  const int wild = P.byte_mode ? P.wildcard : -1;    /* -1: 2-bit packed sequences */
+  const int wild = gm.wild;                   /* -1: 2-bit packed sequences; else byte mode for this pair */
 
   int s = 0;                                  /* score in units of g */
   int cm = 0, c1 = 0, c2 = 0;                 /* ring slots of the current score */
@@ -701,7 +714,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     if (status == 1) {
       if (g.rank == 0) {
         FwdEmitter em; em.init(gm.runs_stage, P.runcap);
-        const int n = backtrace_codes(P, gm.h_code, gm.hmeta, s, end_k, plen, tlen, gm.pw, gm.tw, gm.ops, gm.opcap, em);
+        const int n = backtrace_codes(P, gm.h_code, gm.hmeta, s, end_k, plen, tlen, gm.pw, gm.tw, gm.ops, gm.opcap, em, wild);
         res.nruns = n;
         if (n >= 0) locations_from_runs(gm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }

@@ -135,14 +135,17 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     const int pid = P.worklist ? P.worklist[w] : w;
     const PairMeta pm = P.pairs[pid];
     const int plen = pm.plen, tlen = pm.tlen;
-    const int wsh = P.byte_mode ? 2 : 4;                  /* bases per word: 4 (bytes) or 16 (2-bit) */
+    const bool pbytes = P.byte_mode || pm.woff < 0;       /* this pair's sequences are bytes */
+    const int wsh = pbytes ? 2 : 4;                       /* bases per word: 4 (bytes) or 16 (2-bit) */
     const int pwn = (plen + (1 << wsh) - 1) >> wsh, twn = (tlen + (1 << wsh) - 1) >> wsh;
+    gm.wild = pbytes ? P.wildcard : -1;
     int rc;
     PairResult res;
-    if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || tier_gives_up(P, w)) {
+    const bool tried = !tier_gives_up(P, w);
+    if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || !tried) {
       rc = PAIR_OVERFLOW;
     } else {
-      const uint32_t* gw = P.words + pm.woff;
+      const uint32_t* gw = pm.woff < 0 ? P.words2 + ~pm.woff : P.words + pm.woff;
       if (P.seq_words_cap > 0) {
         /* stage the 2-bit packed pair in shared memory (coalesced word loads) */
         uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
@@ -156,6 +159,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
       g.sync();
       rc = align_pair<G, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
     }
+    if (g.rank == 0 && tried) tier_pair_note(P, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
@@ -312,14 +316,16 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
     const int pid = P.worklist ? P.worklist[w] : w;
     const PairMeta pm = P.pairs[pid];
     const int plen = pm.plen, tlen = pm.tlen;
-    const int wsh = P.byte_mode ? 2 : 4;
+    const bool pbytes = P.byte_mode || pm.woff < 0;
+    const int wsh = pbytes ? 2 : 4;
     const int pwn = (plen + (1 << wsh) - 1) >> wsh, twn = (tlen + (1 << wsh) - 1) >> wsh;
+    gm.wild = pbytes ? P.wildcard : -1;
     int rc;
     PairResult res;
     if (P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) {
       rc = PAIR_OVERFLOW;
     } else {
-      const uint32_t* gw = P.words + pm.woff;
+      const uint32_t* gw = pm.woff < 0 ? P.words2 + ~pm.woff : P.words + pm.woff;
       if (P.seq_words_cap > 0) {
         uint32_t* sp = sm_seq; uint32_t* st = sm_seq + pwn + 1;
         for (int i = g.lrank; i < pwn; i += g.lsize) sp[i] = gw[i];
@@ -396,7 +402,8 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
     const int pwn = (plen + 15) >> 4;
     int rc = PAIR_OVERFLOW;
     PairResult res;
-    if (plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN && !tier_gives_up(K, w)) {
+    const bool tried = pm.woff >= 0 && !tier_gives_up(K, w);
+    if (tried && plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN) {   /* (woff < 0: byte-mode pair, scalar tiers) */
       /* packed words in HBM (the batch buffer carries one pad word) -> per-base windows in smem */
       const uint32_t* gp = K.words + pm.woff;
       const uint32_t* gt = gp + pwn;
@@ -407,6 +414,7 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
       rc = align_pair_reg<P, DX, DOE, FULL>(R, gp, gt, lv::make_seqref(sp), lv::make_seqref(st), plen, tlen, hist, ops,
                                             stage, lane == 0, res);
     }
+    if (lane == 0 && tried) tier_pair_note(K, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (lane == 0) { const int idx = atomicAdd(K.retry_count, 1); K.retry_list[idx] = pid; }
     } else {
@@ -496,7 +504,8 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     int rc = PAIR_OVERFLOW;
     PairResult res;
     const int need_words = P.vec_seqw ? plen + tlen + 2 : pwn + twn + 2;
-    if (need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN && !tier_gives_up(P, w)) {
+    const bool tried = pm.woff >= 0 && !tier_gives_up(P, w);
+    if (tried && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {   /* (woff < 0: byte-mode pair, scalar tiers) */
       const uint32_t* gw = P.words + pm.woff;
       vm.bpw = gw; vm.btw = gw + pwn; vm.seqw = P.vec_seqw;
       if (P.vec_seqw) {
@@ -517,6 +526,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
       vec::gsync<NW>();
       rc = vec::align_pair_vec<TWO_P, FULL, NW, HEUR>(P, vm, plen, tlen, res);
     }
+    if (rank == 0 && tried) tier_pair_note(P, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {

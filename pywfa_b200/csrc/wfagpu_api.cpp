@@ -65,6 +65,8 @@ constexpr int MAX_TIERS = 12;
 struct DevCounters {       /* one per batch, in HBM */
   int work[MAX_TIERS];
   int retry[MAX_TIERS];
+  int done[MAX_TIERS];        /* pairs a tier tried so far / of those, beyond its capacity (adaptive tier skipping) */
+  int ovf[MAX_TIERS];
   int nwork0;
   int pad;
   unsigned long long runs_cursor;
@@ -72,7 +74,7 @@ struct DevCounters {       /* one per batch, in HBM */
   unsigned long long dbg[16];   /* WFA_VEC_TIMING builds: cycle counters of the packed-halfword tier */
 };
 
-struct Staging { PinBuf words, meta; };
+struct Staging { PinBuf words, meta, words2; };
 
 struct Tier {
   int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
@@ -121,10 +123,12 @@ struct wfagpu_batch {
   int32_t maxp = 0, maxt = 0;
   int64_t total_words = 0;
   bool two_p = false, full = false;
-  bool byte_mode = false;       /* sequences uploaded as bytes: non-ACGT input or a wildcard (scalar tiers only) */
+  bool byte_mode = false;       /* every pair is uploaded as bytes (the wildcard is one of ACGT): scalar tiers only */
+  int64_t n_side = 0;           /* pairs holding a non-ACGT byte: uploaded as bytes in a side buffer, scalar tiers */
+  int64_t total_words2 = 0;
   KParams kp;
   std::vector<Tier> tiers;
-  DevBuf pairs, words, score, status, locs, nruns, runs_base, runs_tmp, retry_a, retry_b, counters,
+  DevBuf pairs, words, words2, score, status, locs, nruns, runs_base, runs_tmp, retry_a, retry_b, counters,
       cig_off, tile_sums, runs_out;
   unsigned long long runs_tmp_cap = 0, runs_bound = 0;
   int64_t seq_bytes = 0;
@@ -183,8 +187,10 @@ size_t group_bytes_of(const KParams& k, bool two_p, int seqw, int wcap, int elem
 
 void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const KParams& k = b->kp;
-  const int bpw = b->byte_mode ? 4 : 16;                  /* bases per sequence word */
-  const int seqw = (b->maxp + bpw - 1) / bpw + (b->maxt + bpw - 1) / bpw + 2;
+  /* words of one pair's sequences: 2-bit codes for the fast tiers, bytes where a scalar tier may meet a byte-mode pair */
+  const bool any_bytes = b->byte_mode || b->n_side > 0;
+  const int seqw2 = (b->maxp + 15) / 16 + (b->maxt + 15) / 16 + 2;
+  const int seqw = any_bytes ? (b->maxp + 3) / 4 + (b->maxt + 3) / 4 + 2 : seqw2;
   const long long wmax = (long long)b->maxp + b->maxt + 1;
   const int wmax2 = pow2_ceil(std::max<long long>(wmax, 32));
   const long long sb = std::min<long long>(score_bound(k, b->maxp, b->maxt), k.max_steps);
@@ -217,7 +223,6 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const bool use_vec = !no_vec && !b->byte_mode && std::max(b->maxp, b->maxt) <= VEC_MAX_LEN;   /* byte mode: scalar tiers */
   if (use_vec) {
     const int nslots = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
-    const long long fixed0 = (long long)k.mr * 48 + 256 + 4ll * seqw;
     const long long nblk_max = (wmax + 63) / 64 + 1;
     long long last_nblk = 0;
     auto add_vec = [&](int nw, long long budget, long long hcap, long long scap) {
@@ -225,14 +230,14 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
        * next to the rings, 2-bit packed words otherwise */
       const long long winw = (long long)b->maxp + b->maxt + 2;
       const bool seqw_t = nw > 1 && 4 * winw <= 16384;          /* (the one-warp kernel is compiled without the window variant) */
-      const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw) + 512;   /* + two step plans */
+      const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw2) + 512;   /* + two step plans */
       long long nblk = (budget - fixed) / ((long long)nslots * 128);
       nblk = std::min(nblk, nblk_max);
       if (nblk < 2 || nblk <= last_nblk) return;
       Tier t;
       t.vec_nw = nw; t.mode = nw == 1 ? 0 : 1;
       t.threads = nw == 1 ? 128 : nw * 32; t.groups_per_block = nw == 1 ? 4 : 1;
-      t.wcap = (int)(64 * nblk); t.seq_words_cap = (int)(seqw_t ? winw : seqw); t.vec_seqw = seqw_t;
+      t.wcap = (int)(64 * nblk); t.seq_words_cap = (int)(seqw_t ? winw : seqw2); t.vec_seqw = seqw_t;
       t.group_bytes = (int)((fixed + nblk * nslots * 128 + 15) & ~15ll);
       t.smem = (size_t)t.group_bytes * t.groups_per_block;
       t.scap = (int)std::min<long long>(scap, scap_bound);
@@ -253,7 +258,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   }
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
-    if (vec_covers_smem || use_vec) return;   /* the vec tiers replace the scalar shared-memory tiers */
+    if ((vec_covers_smem || use_vec) && !any_bytes) return;   /* the vec tiers replace the scalar shared-memory tiers (byte-mode pairs still need them) */
     wcap = std::min(wcap, wmax2);
     if (wcap <= last_wcap) return;
     Tier t;
@@ -281,7 +286,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
     const long long elem = short_reads ? 2 : 4;
     int wcap = avail > elem * ns * 32 ? pow2_floor(avail / (elem * ns)) : 0;
     wcap = std::min(wcap, wmax2);
-    const bool vec_has = use_vec;
+    const bool vec_has = use_vec && !any_bytes;
     if (!vec_has && (wcap > last_wcap || (b->full && wcap >= 32 && wcap == wmax2))) {
       Tier t;
       t.mode = 1; t.threads = wcap > 1024 ? 512 : 256; t.groups_per_block = 1; t.wcap = wcap;
@@ -457,7 +462,7 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& sg : ctx->staging) { sg.words.release(); sg.meta.release(); }
+  for (auto& sg : ctx->staging) { sg.words.release(); sg.meta.release(); sg.words2.release(); }
   ctx->pin_runs.release(); ctx->pin_small.release();
   for (wfagpu_batch* b : ctx->spare) batch_release(b);
   ctx->spare.clear();
@@ -503,7 +508,7 @@ static bool trace_on() {
 namespace {
 
 void batch_release(wfagpu_batch* b) {
-  for (DevBuf* d : {&b->pairs, &b->words, &b->score, &b->status, &b->locs, &b->nruns, &b->runs_base, &b->runs_tmp,
+  for (DevBuf* d : {&b->pairs, &b->words, &b->words2, &b->score, &b->status, &b->locs, &b->nruns, &b->runs_base, &b->runs_tmp,
                     &b->retry_a, &b->retry_b, &b->counters, &b->cig_off, &b->tile_sums, &b->runs_out})
     d->release();
   delete b;
@@ -549,25 +554,28 @@ int batch_pack(wfagpu_ctx* ctx, wfagpu_batch* b, Staging& sg, const wfagpu_confi
       if (rc != WFAGPU_OK) return fail(ctx, rc, "pair %lld: %s", (long long)(first_pair + i), msg);
     }
   }
-  /* 2-bit codes unless a wildcard can match one of ACGT; a batch holding any other byte is packed
-   * again as bytes (byte mode: the extension compares 4 bases per word and honours the wildcard) */
+  /* 2-bit codes unless the wildcard is itself one of ACGT (then every pair goes up as bytes).  Pairs
+   * that hold any other byte are packed a second time as bytes into a small side buffer and routed
+   * to the scalar tiers (byte mode: 4 bases per word, the extension honours the wildcard); the rest
+   * of the batch stays on the fast path. */
   const int wc = cfg->wildcard & 0xff;
-  const bool wc_is_base = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
-  b->byte_mode = wc_is_base;
-  uint32_t* words = nullptr;
-  if (!b->byte_mode) {
-    b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt);
-    if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
-    CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
-    words = sg.words.as<uint32_t>();
-    if (pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes) >= 0) b->byte_mode = true;
-  }
+  b->byte_mode = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
+  b->n_side = 0; b->total_words2 = 0;
+  b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt, b->byte_mode ? 4 : 16);
+  if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
+  CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
+  uint32_t* words = sg.words.as<uint32_t>();
   if (b->byte_mode) {
-    b->total_words = layout_pairs(p_len, t_len, n, meta, &b->maxp, &b->maxt, 4);
-    if ((long long)b->maxp + b->maxt > (1ll << 27)) return fail(ctx, WFAGPU_EUNSUPPORTED, "sequences longer than 2^27 bases");
-    CK(sg.words.ensure(4 * (size_t)(b->total_words + 1)));
-    words = sg.words.as<uint32_t>();
     pack_pairs_bytes(seq, p_off, t_off, meta, n, words, seq_bytes);
+  } else {
+    std::vector<int64_t> side;
+    if (pack_pairs(seq, p_off, t_off, meta, n, words, seq_bytes, &side) >= 0) {
+      b->n_side = (int64_t)side.size();
+      b->total_words2 = layout_side_pairs(side, meta);
+      CK(sg.words2.ensure(4 * (size_t)(b->total_words2 + 1)));
+      pack_side_pairs(seq, p_off, t_off, meta, side, sg.words2.as<uint32_t>());
+      sg.words2.as<uint32_t>()[b->total_words2] = 0;
+    }
   }
   words[b->total_words] = 0;
   return WFAGPU_OK;
@@ -581,6 +589,10 @@ int batch_upload(wfagpu_ctx* ctx, wfagpu_batch* b, const Staging& sg, cudaStream
   CK(b->words.ensure(4 * (size_t)(b->total_words + 1)));
   CK(cudaMemcpyAsync(b->pairs.p, sg.meta.p, sizeof(PairMetaHost) * (size_t)n, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(b->words.p, sg.words.p, 4 * (size_t)(b->total_words + 1), cudaMemcpyHostToDevice, st));
+  if (b->n_side) {
+    CK(b->words2.ensure(4 * (size_t)(b->total_words2 + 1)));
+    CK(cudaMemcpyAsync(b->words2.p, sg.words2.p, 4 * (size_t)(b->total_words2 + 1), cudaMemcpyHostToDevice, st));
+  }
   b->stats.packed_bytes = 4 * b->total_words;
   b->stats.h2d_bytes = (int64_t)(sizeof(PairMetaHost) * (size_t)n + 4 * (size_t)(b->total_words + 1));
   CK(b->score.ensure(4 * n1));
@@ -609,6 +621,7 @@ int batch_upload(wfagpu_ctx* ctx, wfagpu_batch* b, const Staging& sg, cudaStream
   k.wildcard = b->cfg.wildcard & 0xff;
   k.pairs = b->pairs.as<PairMeta>();
   k.words = b->words.as<uint32_t>();
+  k.words2 = b->n_side ? b->words2.as<uint32_t>() : nullptr;
   k.score = b->score.as<int>(); k.status = b->status.as<int>();
   k.locs = b->locs.as<int>(); k.nruns = b->nruns.as<int>(); k.runs_base = b->runs_base.as<long long>();
   k.runs_tmp = b->runs_tmp.as<uint32_t>(); k.runs_tmp_cap = b->runs_tmp_cap;
@@ -713,6 +726,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       k.retry_list = lists[ti & 1];
       k.skip_groups = (ti + 1 < b->tiers.size() && !getenv("WFAGPU_NO_TIER_SKIP")) ? (int)std::min<long long>(groups, INT_MAX / 2) : 0;   /* never on the last tier */
       k.retry_count = &dc->retry[ti];
+      k.done_count = &dc->done[ti]; k.ovf_count = &dc->ovf[ti];
       const double tier_t0 = trace_on() ? now_ms() : 0;
       if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
       else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));

@@ -40,6 +40,7 @@ static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t
   const int wcap = P.wcap;
   GroupMem<OffT> gm;
   gm.pw = pw; gm.tw = tw;
+  gm.wild = P.byte_mode ? P.wildcard : -1;
   gm.ring[CM] = reinterpret_cast<OffT*>(B.ring.data());
   gm.ring[CI1] = gm.ring[CM] + P.rm * wcap;
   gm.ring[CD1] = gm.ring[CI1] + P.r1 * wcap;

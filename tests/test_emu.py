@@ -160,7 +160,7 @@ def _pairs_with_n(seed, n, lo, hi, p_n=0.04, t_n=0.05):
             elif r < 0.08: t[j] = ""
             elif r < 0.11: t[j] += rnd(2)
             elif r < 0.11 + t_n: t[j] = "N"
-            elif r < 0.12 + t_n: t[j] = "r"
+            elif r < 0.11 + 1.2 * t_n: t[j] = "r"
         for j in range(len(p)):
             if rng.random() < p_n: p[j] = "N"
         pairs.append(("".join(p), "".join(t)))

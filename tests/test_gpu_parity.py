@@ -156,6 +156,27 @@ def test_byte_mode_non_acgt_and_wildcard(gpu_ctx, oracle):
             want = oracle.align_batch(cfg, *batch, kind="port")
             got = gpu_ctx.align_batch(cfg, *batch)
             assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"byte mode {kw}")
+    # mostly clean batches: only the pairs that hold an N leave the fast tiers (side buffer of bytes)
+    mixed = _pairs_with_n(23, 6000, 100, 260, p_n=0.0005, t_n=0.0005)
+    n_dirty = sum(1 for p, t in mixed if set(p + t) - set("ACGT"))
+    assert 0.05 * len(mixed) < n_dirty < 0.6 * len(mixed)
+    mb = pairs_from_strings(mixed)
+    for kw in (dict(span="end-to-end"), dict(span="end-to-end", wildcard="N"), dict(distance="affine2p", wildcard="N"),
+               dict(span="end-to-end", scope="score"), dict(heuristic="adaptive", span="end-to-end", wildcard="N")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *mb, kind="port")
+        bt = gpu_ctx.prepare(cfg, *mb)
+        bt.run(); got = bt.fetch()
+        assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"mixed batch {kw}")
+        retried = bt.stats()["retried_pairs"]
+        bt.free()
+        # the same batch with every odd byte replaced by a base: what overflows the first tier anyway
+        clean = pairs_from_strings([("".join(c if c in "ACGT" else "A" for c in p), "".join(c if c in "ACGT" else "A" for c in t))
+                                    for p, t in mixed])
+        bc = gpu_ctx.prepare(cfg, *clean)
+        bc.run()
+        assert retried <= bc.stats()["retried_pairs"] + n_dirty + 64, "clean pairs must stay on the fast tiers"
+        bc.free()
     # a wildcard that never occurs leaves pure-ACGT batches on the 2-bit fast path, with the same result
     plain = generate_pairs(2000, 150, 0.05, seed=5)
     a = gpu_ctx.align_batch(oracle.make_config(span="end-to-end"), *plain)
