@@ -193,7 +193,12 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const int seqw = any_bytes ? (b->maxp + 3) / 4 + (b->maxt + 3) / 4 + 2 : seqw2;
   const long long wmax = (long long)b->maxp + b->maxt + 1;
   const int wmax2 = pow2_ceil(std::max<long long>(wmax, 32));
-  const long long sb = std::min<long long>(score_bound(k, b->maxp, b->maxt), k.max_steps);
+  /* capacity of the score tables: the optimum is bounded by any alignment; with a cut-off the path is
+   * whatever survives the pruning (fuzzing found X-drop alignments at twice the optimum's bound), so
+   * only the trivial bound "every column pays the dearest operation" holds */
+  const long long dearest = std::max<long long>(k.x, std::max<long long>(k.o1 + k.e1, b->two_p ? k.o2 + k.e2 : 0));
+  const long long sb_any = ((long long)b->maxp + b->maxt) * dearest + dearest;
+  const long long sb = std::min<long long>(k.heuristic ? sb_any : score_bound(k, b->maxp, b->maxt), k.max_steps);
   const long long scap_bound = std::min<long long>(sb / k.g + k.rm + 4, INT_MAX / 4);
   const long long cells_bound = std::min<long long>(scap_bound * wmax, (long long)4e18 / 8);
   const int smem_max = ctx->smem_optin;

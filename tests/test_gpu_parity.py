@@ -264,6 +264,19 @@ def test_fastx_streaming(gpu_ctx, oracle, tmp_path):
     assert seen == len(pairs)
 
 
+def test_fuzz_random_configurations(gpu_ctx):
+    """scripts/fuzz_parity.py: random penalties / spans / free ends / cut-offs / step limits on random
+    shapes (incl. unequal lengths and N-holding pairs) against the checker.  (300 rounds were
+    bit-exact in r01 after it found the score-table bound that cut-offs can exceed.)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "40", "3"], cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_empty_batch(gpu_ctx, oracle):
     cfg = oracle.make_config()
     z64, z32 = np.zeros(0, np.int64), np.zeros(0, np.int32)
