@@ -51,6 +51,12 @@ for r in range(rounds):
         length, div = int(rng.integers(20, 600)), float(rng.choice([0.01, 0.05, 0.1, 0.2, 0.4]))
         batch = generate_pairs(int(rng.integers(200, 3000)), length, div, seed=int(rng.integers(1 << 30)))
         minlen = length // 3
+    elif shape < 0.08 + 0.4:
+        # long reads: the 16-warp groups, the scalar shared-memory tiers (> 12 kbp with a cut-off) and the
+        # several-CTAs-per-pair tier
+        length, div = int(rng.integers(5000, 30000)), float(rng.choice([0.02, 0.05, 0.1]))
+        batch = generate_pairs(int(rng.integers(2, 7)), length, div, seed=int(rng.integers(1 << 30)))
+        minlen = length // 3
     elif shape < 0.6:
         length, div = int(rng.integers(600, 4000)), float(rng.choice([0.01, 0.05, 0.1, 0.2]))
         batch = generate_pairs(int(rng.integers(8, 60)), length, div, seed=int(rng.integers(1 << 30)))

@@ -1,2 +1,1 @@
-timeout 900 python scripts/fuzz_parity.py 150 1 2>&1 | tail -14
-timeout 900 python scripts/fuzz_parity.py 150 7 2>&1 | tail -14
+timeout 1500 python scripts/fuzz_parity.py 120 11 2>&1 | tail -8
