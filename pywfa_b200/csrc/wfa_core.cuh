@@ -235,22 +235,24 @@ WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
 }
 
 /*
- * Adaptive tier skipping: once at least 256 pairs of this launch have left the tier and three quarters
- * of them exceeded its capacity, the remaining pairs are forwarded to the next tier
+ * Adaptive tier skipping: once a sample of at least 64 pairs this launch tried has left the tier and three
+ * quarters of it exceeded the tier's capacity, the remaining pairs are forwarded to the next tier
  * unprocessed (their partial work would be thrown away).  w = index of the work item just fetched.
  */
-WFA_DEV bool tier_gives_up(const KParams& P, int w) {
-  if (P.skip_groups <= 0 || w < 256) return false;
-  const int done = ld_cg(P.done_count);
-  if (done < 256) return false;
-  return 4ll * ld_cg(P.ovf_count) > 3ll * done;
+WFA_DEV bool tier_gives_up(const KParams& P, int w, bool& gave_up) {
+  /* `gave_up` is the group's cached verdict: final once true, re-examined at every 4th work item otherwise */
+  if (gave_up || P.skip_groups <= 0 || w < 512 || (w & 3) != 0) return gave_up;
+  const int done = ld_cg(P.done_count);               /* sampled: every 8th work item reports (tier_pair_note) */
+  if (done >= 64 && 4ll * ld_cg(P.ovf_count) > 3ll * done) gave_up = true;
+  return gave_up;
 }
 /* one pair this tier actually tried left it (one thread of the group); pairs that were forwarded
  * untried -- given up on, or byte-mode pairs on a 2-bit tier -- do not count: they finish at once
- * and would dominate the first 256 */
-WFA_DEV void tier_pair_note(const KParams& P, bool overflowed) {
+ * and would dominate the first samples.  Every 8th work item reports, so that the two counters are
+ * not an atomic hot spot next to the work queue. */
+WFA_DEV void tier_pair_note(const KParams& P, int w, bool overflowed) {
 #ifdef __CUDA_ARCH__
-  if (P.skip_groups > 0) { atomicAdd(P.done_count, 1); if (overflowed) atomicAdd(P.ovf_count, 1); }
+  if (P.skip_groups > 0 && (w & 7) == 0) { atomicAdd(P.done_count, 1); if (overflowed) atomicAdd(P.ovf_count, 1); }
 #endif
 }
 

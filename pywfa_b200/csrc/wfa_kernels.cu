@@ -126,7 +126,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
 
   const int n_work = *P.n_work;
   long long cells_acc = 0;
-
+  bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
     int w = 0;
     if (g.rank == 0) w = atomicAdd(P.work_counter, 1);
@@ -141,7 +141,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     gm.wild = pbytes ? P.wildcard : -1;
     int rc;
     PairResult res;
-    const bool tried = !tier_gives_up(P, w);
+    const bool tried = !tier_gives_up(P, w, gave_up);
     if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || !tried) {
       rc = PAIR_OVERFLOW;
     } else {
@@ -159,7 +159,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
       g.sync();
       rc = align_pair<G, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
     }
-    if (g.rank == 0 && tried) tier_pair_note(P, rc == PAIR_OVERFLOW);
+    if (g.rank == 0 && tried) tier_pair_note(P, w, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
   g.sync();
   const int n_work = *P.n_work;
   long long cells_acc = 0;
+  bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
     int w = 0;
     if (g.rank == 0) w = atomicAdd(P.work_counter, 1);
@@ -402,8 +403,9 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
     const int pwn = (plen + 15) >> 4;
     int rc = PAIR_OVERFLOW;
     PairResult res;
-    const bool tried = pm.woff >= 0 && !tier_gives_up(K, w);
-    if (tried && plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN) {   /* (woff < 0: byte-mode pair, scalar tiers) */
+    /* (woff < 0: byte-mode pair, scalar tiers.  No adaptive tier skipping here: the pairs this tier cannot
+     * hold cost it little, and this loop is sensitive to every extra live register) */
+    if (pm.woff >= 0 && plen + tlen + 2 <= K.seq_words_cap && plen <= REG_MAX_LEN && tlen <= REG_MAX_LEN) {
       /* packed words in HBM (the batch buffer carries one pad word) -> per-base windows in smem */
       const uint32_t* gp = K.words + pm.woff;
       const uint32_t* gt = gp + pwn;
@@ -414,7 +416,6 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
       rc = align_pair_reg<P, DX, DOE, FULL>(R, gp, gt, lv::make_seqref(sp), lv::make_seqref(st), plen, tlen, hist, ops,
                                             stage, lane == 0, res);
     }
-    if (lane == 0 && tried) tier_pair_note(K, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (lane == 0) { const int idx = atomicAdd(K.retry_count, 1); K.retry_list[idx] = pid; }
     } else {
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
 
   const int n_work = *P.n_work;
   long long cells_acc = 0;
+  bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
     int w = 0;
     if (rank == 0) w = atomicAdd(P.work_counter, 1);
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     int rc = PAIR_OVERFLOW;
     PairResult res;
     const int need_words = P.vec_seqw ? plen + tlen + 2 : pwn + twn + 2;
-    const bool tried = pm.woff >= 0 && !tier_gives_up(P, w);
+    const bool tried = pm.woff >= 0 && !tier_gives_up(P, w, gave_up);
     if (tried && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {   /* (woff < 0: byte-mode pair, scalar tiers) */
       const uint32_t* gw = P.words + pm.woff;
       vm.bpw = gw; vm.btw = gw + pwn; vm.seqw = P.vec_seqw;
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
       vec::gsync<NW>();
       rc = vec::align_pair_vec<TWO_P, FULL, NW, HEUR>(P, vm, plen, tlen, res);
     }
-    if (rank == 0 && tried) tier_pair_note(P, rc == PAIR_OVERFLOW);
+    if (rank == 0 && tried) tier_pair_note(P, w, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
