@@ -370,8 +370,9 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
 }
 
 #ifndef WFA_REG_MINB
-#define WFA_REG_MINB 6      /* resident CTAs per SM the register tier is compiled for (register budget;
-                               measured r01: 5 -> 41.6, 6 -> 42.8, 7 -> 37.3, 8 -> 35.2 M pairs/s on cfg2) */
+#define WFA_REG_MINB 7      /* resident CTAs per SM the register tier is compiled for (register budget; measured r01 with
+                               the 192-diagonal window on cfg2 / cfg1: 6 -> 46.1 / 115.2, 7 -> 46.5 / 117.1, 8 -> 40.6 / 111.1
+                               M pairs/s; with the 256-diagonal window only: 5 -> 41.6, 6 -> 42.8, 7 -> 37.3) */
 #endif
 /* ---- the register-resident tier (wfa_reg.cuh): warp-per-pair, wavefronts in registers ---- */
 /* shared memory of one warp: the sequence windows of the pair (seq_words_cap words, one per base + 2) */
