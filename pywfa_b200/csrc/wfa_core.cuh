@@ -248,11 +248,11 @@ WFA_DEV bool tier_gives_up(const KParams& P, int w, bool& gave_up) {
 }
 /* one pair this tier actually tried left it (one thread of the group); pairs that were forwarded
  * untried -- given up on, or byte-mode pairs on a 2-bit tier -- do not count: they finish at once
- * and would dominate the first samples.  Every 8th work item reports, so that the two counters are
+ * and would dominate the first samples.  Callers report every 8th pair, so that the two counters are
  * not an atomic hot spot next to the work queue. */
-WFA_DEV void tier_pair_note(const KParams& P, int w, bool overflowed) {
+WFA_DEV void tier_pair_note(const KParams& P, bool overflowed) {
 #ifdef __CUDA_ARCH__
-  if (P.skip_groups > 0 && (w & 7) == 0) { atomicAdd(P.done_count, 1); if (overflowed) atomicAdd(P.ovf_count, 1); }
+  if (P.skip_groups > 0) { atomicAdd(P.done_count, 1); if (overflowed) atomicAdd(P.ovf_count, 1); }
 #endif
 }
 

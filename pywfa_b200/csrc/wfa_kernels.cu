@@ -141,8 +141,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     gm.wild = pbytes ? P.wildcard : -1;
     int rc;
     PairResult res;
-    const bool tried = !tier_gives_up(P, w, gave_up);
-    if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || !tried) {
+    if ((P.seq_words_cap > 0 && pwn + twn + 2 > P.seq_words_cap) || tier_gives_up(P, w, gave_up)) {
       rc = PAIR_OVERFLOW;
     } else {
       const uint32_t* gw = pm.woff < 0 ? P.words2 + ~pm.woff : P.words + pm.woff;
@@ -159,7 +158,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
       g.sync();
       rc = align_pair<G, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
     }
-    if (g.rank == 0 && tried) tier_pair_note(P, w, rc == PAIR_OVERFLOW);
+    if (g.rank == 0 && !gave_up && (pid & 7) == 0) tier_pair_note(P, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (g.rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
@@ -507,8 +506,9 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     int rc = PAIR_OVERFLOW;
     PairResult res;
     const int need_words = P.vec_seqw ? plen + tlen + 2 : pwn + twn + 2;
-    const bool tried = pm.woff >= 0 && !tier_gives_up(P, w, gave_up);
-    if (tried && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {   /* (woff < 0: byte-mode pair, scalar tiers) */
+    /* (woff < 0: byte-mode pair, scalar tiers).  Only `gave_up` and `pid` stay live across the alignment:
+     * the step loop runs at the register limit */
+    if (pm.woff >= 0 && !tier_gives_up(P, w, gave_up) && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {
       const uint32_t* gw = P.words + pm.woff;
       vm.bpw = gw; vm.btw = gw + pwn; vm.seqw = P.vec_seqw;
       if (P.vec_seqw) {
@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
       vec::gsync<NW>();
       rc = vec::align_pair_vec<TWO_P, FULL, NW, HEUR>(P, vm, plen, tlen, res);
     }
-    if (rank == 0 && tried) tier_pair_note(P, w, rc == PAIR_OVERFLOW);
+    if (rank == 0 && !gave_up && (pid & 7) == 0 && P.pairs[pid].woff >= 0) tier_pair_note(P, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
