@@ -508,7 +508,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     const int need_words = P.vec_seqw ? plen + tlen + 2 : pwn + twn + 2;
     /* (woff < 0: byte-mode pair, scalar tiers).  Only `gave_up` and `pid` stay live across the alignment:
      * the step loop runs at the register limit */
-    if (pm.woff >= 0 && !tier_gives_up(P, w, gave_up) && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {
+    if (pm.woff >= 0 && !(NW == 1 && HEUR == 0 && tier_gives_up(P, w, gave_up)) && need_words <= P.seq_words_cap && plen <= VEC_MAX_LEN && tlen <= VEC_MAX_LEN) {
       const uint32_t* gw = P.words + pm.woff;
       vm.bpw = gw; vm.btw = gw + pwn; vm.seqw = P.vec_seqw;
       if (P.vec_seqw) {
@@ -529,7 +529,9 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
       vec::gsync<NW>();
       rc = vec::align_pair_vec<TWO_P, FULL, NW, HEUR>(P, vm, plen, tlen, res);
     }
-    if (rank == 0 && !gave_up && (pid & 7) == 0 && P.pairs[pid].woff >= 0) tier_pair_note(P, rc == PAIR_OVERFLOW);
+    /* (adaptive tier skipping only where it pays: the warp-per-pair tier without cut-offs is the one whole
+     * batches overflow; elsewhere its live state costs the step loop registers: cfg3 -4 %, cfg4-adaptive -6 %) */
+    if (NW == 1 && HEUR == 0 && rank == 0 && !gave_up && (pid & 7) == 0 && P.pairs[pid].woff >= 0) tier_pair_note(P, rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) {
       if (rank == 0) { const int idx = atomicAdd(P.retry_count, 1); P.retry_list[idx] = pid; }
     } else {
