@@ -167,12 +167,15 @@ void set_err(char* err, size_t errlen, const char* fmt, ...) {
                   "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-long long score_bound(const KParams& k, long long p, long long t) {
-  /* any alignment bounds the optimum: min(p,t) mismatches plus one gap */
-  const long long d = p > t ? p - t : t - p;
-  long long b = (long long)k.x * std::min(p, t) + (d ? k.o1 + (long long)k.e1 * d : 0);
-  const long long gaps = (p ? k.o1 + (long long)k.e1 * p : 0) + (t ? k.o1 + (long long)k.e1 * t : 0);
-  return std::min(b, gaps);
+long long score_bound(const KParams& k, long long maxp, long long maxt) {
+  /* Bound of the optimum of EVERY pair with plen <= maxp, tlen <= maxt (the batch maxima come from
+   * different pairs: a 305 x 61 pair in a batch whose longest text has 320 bases needs 244 gap
+   * extensions -- found by the fuzzer).  Any alignment bounds the optimum; both candidates below are
+   * monotone in the lengths: "mismatch the shorter sequence, one gap for the rest" at its worst
+   * (shorter = min of the maxima, rest = the longer maximum) and "delete everything, insert everything". */
+  const long long one_gap = (long long)k.x * std::min(maxp, maxt) + k.o1 + (long long)k.e1 * std::max(maxp, maxt);
+  const long long gaps = (maxp ? k.o1 + (long long)k.e1 * maxp : 0) + (maxt ? k.o1 + (long long)k.e1 * maxt : 0);
+  return std::min(one_gap, gaps);
 }
 
 int pow2_floor(long long v) { int p = 1; while (2ll * p <= v) p <<= 1; return p; }

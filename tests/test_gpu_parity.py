@@ -264,6 +264,27 @@ def test_fastx_streaming(gpu_ctx, oracle, tmp_path):
     assert seen == len(pairs)
 
 
+def test_capacity_bounds_hold_for_every_pair_of_a_batch(gpu_ctx, oracle):
+    """Two planner bugs the fuzzer found: (1) the score-table bound was computed from the batch's longest
+    pattern and longest text as if they formed one pair -- a 305 x 61 pair with cheap mismatches costs far
+    more than a 320 x 326 pair; (2) under a cut-off the path that survives can cost more than any bound of
+    the optimum.  Both ended in status -200 instead of an alignment."""
+    rng = np.random.default_rng(4)
+    rnd = lambda m: "".join("ACGT"[i] for i in rng.integers(0, 4, m))
+    pairs = _ragged_pairs(23, 300, 20, 330)
+    pairs += [(rnd(305), rnd(61)), (rnd(40), rnd(320)), (rnd(326), rnd(318))]
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(distance="affine2p", mismatch=1, gap_opening=3, gap_extension=3, gap_opening2=32, gap_extension2=3),
+               dict(span="end-to-end", mismatch=1, gap_opening=2, gap_extension=4),
+               dict(distance="affine2p", span="end-to-end", mismatch=2, gap_opening=5, gap_extension=3, gap_opening2=22,
+                    gap_extension2=1, heuristic="X-drop", xdrop=127, steps_between_cutoffs=3)):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = gpu_ctx.align_batch(cfg, *batch)
+        assert -200 not in got["status"].tolist()
+        assert_same(got, want, what=f"capacity bounds {kw}")
+
+
 def test_fuzz_random_configurations(gpu_ctx):
     """scripts/fuzz_parity.py: random penalties / spans / free ends / cut-offs / step limits on random
     shapes (incl. unequal lengths and N-holding pairs) against the checker.  (300 rounds were
