@@ -194,7 +194,9 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b) {
   const bool any_bytes = b->byte_mode || b->n_side > 0;
   const int seqw2 = (b->maxp + 15) / 16 + (b->maxt + 15) / 16 + 2;
   const int seqw = any_bytes ? (b->maxp + 3) / 4 + (b->maxt + 3) / 4 + 2 : seqw2;
-  const long long wmax = (long long)b->maxp + b->maxt + 1;
+  /* widest computed wavefront: the DP matrix has plen + tlen + 1 diagonals and a step's range reaches one
+   * diagonal beyond either side before it is trimmed (compute.c:40-86 on trimmed sources) */
+  const long long wmax = (long long)b->maxp + b->maxt + 3;
   const int wmax2 = pow2_ceil(std::max<long long>(wmax, 32));
   /* capacity of the score tables: the optimum is bounded by any alignment; with a cut-off the path is
    * whatever survives the pruning (fuzzing found X-drop alignments at twice the optimum's bound), so

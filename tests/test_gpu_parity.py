@@ -274,6 +274,13 @@ def test_capacity_bounds_hold_for_every_pair_of_a_batch(gpu_ctx, oracle):
     pairs = _ragged_pairs(23, 300, 20, 330)
     pairs += [(rnd(305), rnd(61)), (rnd(40), rnd(320)), (rnd(326), rnd(318))]
     batch = pairs_from_strings(pairs)
+    # unrelated sequences whose matrix has 2^k - 1 diagonals: the wavefront spans it all, plus one either side
+    wide = pairs_from_strings([(rnd(255), rnd(255)) for _ in range(40)] + [(rnd(127), rnd(128)) for _ in range(40)])
+    for kw in (dict(span="end-to-end"), dict(distance="affine2p"), dict(span="end-to-end", mismatch=9, gap_opening=1, gap_extension=1)):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *wide, kind="port")
+        got = gpu_ctx.align_batch(cfg, *wide)
+        assert_same(got, want, what=f"full-width wavefronts {kw}")
     for kw in (dict(distance="affine2p", mismatch=1, gap_opening=3, gap_extension=3, gap_opening2=32, gap_extension2=3),
                dict(span="end-to-end", mismatch=1, gap_opening=2, gap_extension=4),
                dict(distance="affine2p", span="end-to-end", mismatch=2, gap_opening=5, gap_extension=3, gap_opening2=22,
