@@ -116,8 +116,12 @@ const char* wfagpu_strerror(int code);
  * called at pywfa/align.pyx:439) plus the result read-back pywfa does from
  * aligner->cigar / ->align_status (pywfa/align.pyx:443,463,731-833).
  *
- * Inputs are HOST buffers: `seq` holds ASCII bases (any case); pair i is
+ * Inputs: `seq` holds ASCII bases (any case); pair i is
  * pattern = seq[p_off[i] .. +p_len[i]), text = seq[t_off[i] .. +t_len[i]).
+ * `seq` may be plain host memory, pinned host memory (wfagpu_host_alloc /
+ * wfagpu_host_register: the copy engine then reads it directly and no host
+ * core touches a base) or memory of the context's device (packed in place,
+ * no upload).  The offset / length arrays are host memory, pinned or not.
  * Outputs (host, caller-allocated, n entries each; any may be NULL):
  *   score[i]   cigar->score            (align.pyx:443)
  *   status[i]  align_status.status     (align.pyx:463)
@@ -129,9 +133,15 @@ const char* wfagpu_strerror(int code);
  * cig_off must have n+1 entries.  The memory stays valid until the next
  * align call on this ctx or wfagpu_destroy.
  *
- * Large batches are processed in chunks: the calling thread packs chunk c+1
- * (2 bits per base, all host cores) into pinned staging while a second host
- * thread drives upload, kernels and download of chunk c.
+ * Result arrays in pinned memory are written by the copy engine directly.
+ *
+ * The bases are uploaded as they are and packed (2 bits per base) and
+ * bucketed by length on the device; this replaces the per-alignment copy of
+ * wavefront_sequences_init_ascii (W/wavefront/wavefront_sequences.c:141-170).
+ * Large batches are processed in chunks: the calling thread stages chunk c+1
+ * while a second host thread drives the kernels of chunk c and a third hands
+ * finished downloads to the caller.  One call at a time per context (calls
+ * from several threads are serialised inside the library).
  */
 int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
                        const uint8_t* seq,
@@ -144,7 +154,7 @@ int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
 /*
  * Staged form of the same path, for callers that keep batches resident in HBM
  * (bench.py's device-resident `value`, pipelined streaming).
- *   prepare : 2-bit pack on the host into pinned memory, bucket, H2D
+ *   prepare : H2D of the raw bases, 2-bit packing and length bucketing on the device
  *   run     : kernels only, on `stream` (a cudaStream_t; NULL = ctx stream)
  *   fetch   : D2H of results into the caller's arrays (same layout as above)
  */
@@ -159,12 +169,24 @@ int wfagpu_batch_fetch(wfagpu_ctx* ctx, wfagpu_batch* b,
                        int64_t* cig_off, const uint32_t** cig_runs);
 void wfagpu_batch_free(wfagpu_ctx* ctx, wfagpu_batch* b);
 
+/*
+ * Pinned host memory for callers.  Batches built in it (and result arrays
+ * allocated from it) move by DMA without any host-side copy; this is what
+ * the reference's "inputs are copied" step (W/wavefront/wavefront_sequences.c:97)
+ * becomes when the consumer is a GPU.  wfagpu_host_register pins memory the
+ * caller already owns (e.g. a numpy array) in place.
+ */
+void* wfagpu_host_alloc(size_t bytes);                 /* NULL on failure */
+void wfagpu_host_free(void* p);
+int wfagpu_host_register(void* p, size_t bytes);
+int wfagpu_host_unregister(void* p);
+
 /* Counters of the last run on this batch (for bench.py / roofline maths). */
 typedef struct wfagpu_batch_stats {
   int64_t n_pairs;
-  int64_t kernel_launches;     /* launches of OUR kernels in the last run     */
+  int64_t kernel_launches;     /* launches of OUR kernels in the last run (the first run counts the packing kernels) */
   int64_t packed_bytes;        /* 2-bit input bytes resident in HBM           */
-  int64_t h2d_bytes;           /* bytes copied host->device by prepare        */
+  int64_t h2d_bytes;           /* bytes copied host->device by the staging    */
   int64_t d2h_bytes;           /* bytes copied device->host by the last fetch */
   int64_t cells;               /* sum of computed wavefront cells (device counter) */
   int64_t history_bytes;       /* scope=full backtrace history written to HBM */
@@ -173,6 +195,17 @@ typedef struct wfagpu_batch_stats {
 int wfagpu_batch_get_stats(const wfagpu_batch* b, wfagpu_batch_stats_t* out);
 /* Kernel launches issued by the last wfagpu_align_batch call on this context. */
 int64_t wfagpu_last_launches(const wfagpu_ctx* ctx);
+
+/*
+ * Destination of the CIGAR runs of wfagpu_align_batch.  By default *cig_runs
+ * points at library-owned pinned memory (the analogue of aligner->cigar, which
+ * WFA2-lib owns and overwrites on the next call, pywfa/align.pyx:737-756).  A
+ * caller that gathers the results of several contexts into one array (one
+ * context per GPU) hands each context its slice of that array
+ * instead (pinned memory: written by DMA); a call whose runs do not fit fails
+ * with WFAGPU_ENOMEM.  buf = NULL restores the default.
+ */
+int wfagpu_set_run_buffer(wfagpu_ctx* ctx, uint32_t* buf, int64_t capacity_words);
 
 #ifdef __cplusplus
 }

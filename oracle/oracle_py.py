@@ -79,6 +79,12 @@ def have_ref() -> bool:
     return os.path.exists(REF_SO)
 
 
+def checker_kind() -> str:
+    """The strongest checker available: the unmodified reference when its build travelled with
+    the snapshot (oracle/_ref), else the restatement."""
+    return "reference" if have_ref() else "port"
+
+
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")

@@ -89,12 +89,72 @@ def lib():
     L.wfagpu_batch_get_stats.restype = C.c_int
     L.wfagpu_last_launches.argtypes = [vp]
     L.wfagpu_last_launches.restype = C.c_int64
+    L.wfagpu_set_run_buffer.argtypes = [vp, vp, i64]
+    L.wfagpu_set_run_buffer.restype = C.c_int
+    L.wfagpu_host_alloc.argtypes = [C.c_size_t]
+    L.wfagpu_host_alloc.restype = vp
+    L.wfagpu_host_free.argtypes = [vp]
+    L.wfagpu_host_free.restype = None
+    L.wfagpu_host_register.argtypes = [vp, C.c_size_t]
+    L.wfagpu_host_register.restype = C.c_int
+    L.wfagpu_host_unregister.argtypes = [vp]
+    L.wfagpu_host_unregister.restype = C.c_int
     _lib = L
     return L
 
 
-def _ptr(a: np.ndarray):
+def _ptr(a):
+    if isinstance(a, _DevicePtr):
+        return C.c_void_p(a.ptr)
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _DevicePtr:
+    """Address of a tensor that exposes ``data_ptr()`` (kept alive for the duration of the call)."""
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+        self.ptr = int(tensor.data_ptr())
+
+    def __len__(self):
+        return int(self.tensor.numel())
+
+
+class _PinnedBlock:
+    """Owner of one ``wfagpu_host_alloc`` allocation; freed when the last array viewing it dies."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = max(int(nbytes), 1)
+        self.ptr = lib().wfagpu_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError(f"wfagpu_host_alloc({self.nbytes}) failed")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().wfagpu_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """A numpy array in pinned host memory (``wfagpu_host_alloc``): batches built in such arrays
+    and results written to them move by DMA, without a host-side staging copy."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+    block = _PinnedBlock(n * dtype.itemsize)
+    buf = (C.c_uint8 * block.nbytes).from_address(block.ptr)
+    buf._wfagpu_owner = block           # arr.base -> buf -> block: the allocation lives as long as any view
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
+def pinned_copy(a) -> np.ndarray:
+    a = np.asarray(a)
+    out = pinned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
 
 
 class Context:
@@ -127,7 +187,14 @@ class Context:
 
     @staticmethod
     def _inputs(seq, p_off, p_len, t_off, t_len, check=True):
-        seq = np.ascontiguousarray(seq, np.uint8)
+        if hasattr(seq, "data_ptr"):
+            # a torch tensor (uint8, contiguous): bases already resident on the device are packed in place
+            if not seq.is_contiguous() or seq.element_size() != 1:
+                raise ValueError("sequence tensor must be contiguous uint8")
+            seq = _DevicePtr(seq)
+            check = False
+        else:
+            seq = np.ascontiguousarray(seq, np.uint8)
         p_off = np.ascontiguousarray(p_off, np.int64)
         t_off = np.ascontiguousarray(t_off, np.int64)
         p_len = np.ascontiguousarray(p_len, np.int32)
@@ -171,6 +238,18 @@ class Context:
         else:
             runs = np.zeros(0, np.uint32)
         return dict(score=score, status=status, locs=locs, cig_off=cig_off, runs=runs)
+
+    def set_run_buffer(self, buf=None):
+        """CIGAR runs of later ``align_batch`` calls land in ``buf`` (uint32, ideally pinned: e.g. this
+        context's slice of a gathered array) instead of library-owned memory; ``None`` restores it."""
+        if buf is None:
+            self._run_buf = None
+            self._check(lib().wfagpu_set_run_buffer(self._h, None, 0))
+            return
+        if buf.dtype != np.uint32 or not buf.flags.c_contiguous:
+            raise ValueError("run buffer must be a contiguous uint32 array")
+        self._run_buf = buf
+        self._check(lib().wfagpu_set_run_buffer(self._h, _ptr(buf), buf.size))
 
     def last_launches(self) -> int:
         return int(lib().wfagpu_last_launches(self._h))

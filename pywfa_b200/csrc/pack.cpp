@@ -1,11 +1,17 @@
 /*
- * pack.cpp -- host side of the batch layout: ASCII bases -> 2-bit words in pinned memory.
+ * pack.cpp -- host side of the batch staging.
  *
- * Replaces wavefront_sequences_init_ascii (W/wavefront/wavefront_sequences.c:141-170), which
- * copies both sequences into one sentinel-padded byte buffer per alignment.  Here every pair is
- * packed once, 16 bases per 32-bit word (base j of a word in bits 2j..2j+1, code = (c>>1)&3 so
- * upper and lower case map alike: A=0 C=1 T=2 G=3), pattern words first, text words after.
- * Bytes other than ACGT/acgt are reported (the 2-bit path cannot represent them).
+ * The bases themselves are packed on the device (wfa_pack.cu); the host only (1) reduces the
+ * caller's offset / length arrays of a chunk to the few numbers the planner needs (scan_pairs:
+ * byte range, longest sequences, word count, length-bucket histogram), (2) moves bytes from
+ * pageable memory into pinned staging (parallel_copy, gather_pairs) when the caller did not hand
+ * over pinned or device memory.  All of it runs on a small persistent thread pool whose size is
+ * capped per process (host_threads).
+ *
+ * pack_sequence is the host statement of the 2-bit layout (16 bases per 32-bit word, base j in bits
+ * 2j..2j+1, code = (c>>1)&3 so upper and lower case map alike: A=0 C=1 T=2 G=3); the CPU test-suite
+ * feeds the host-compiled kernel sources with it and the GPU tests pin the device packer to it.
+ * Together they replace wavefront_sequences_init_ascii (W/wavefront/wavefront_sequences.c:141-170).
  */
 #include <immintrin.h>
 #include <stdint.h>
@@ -102,14 +108,26 @@ bool pack_sequence(const uint8_t* s, int len, uint32_t* out) {
   return ok;
 }
 
-int pack_threads(int64_t n_items, int64_t bytes) {
+#include <sched.h>
+
+int host_threads() {
   static int hw = [] {
-    const char* e = getenv("WFAGPU_THREADS");
-    int t = e ? atoi(e) : (int)std::thread::hardware_concurrency();
-    return std::max(1, std::min(t, 256));
+    /* WFAGPU_THREADS wins; else the cores this process may run on, shared evenly between the ranks
+     * torchrun placed on this node (8 ranks must not each start one thread per core) */
+    if (const char* e = getenv("WFAGPU_THREADS")) return std::max(1, std::min(atoi(e), 256));
+    int t = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof set, &set) == 0) t = std::min(t > 0 ? t : 1 << 20, CPU_COUNT(&set));
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+    return std::max(1, std::min(t / ranks, 64));
   }();
+  return hw;
+}
+
+int pack_threads(int64_t n_items, int64_t bytes) {
   if (bytes < (1 << 20) || n_items < 64) return 1;
-  return (int)std::min<int64_t>(hw, std::max<int64_t>(1, bytes >> 19));
+  return (int)std::min<int64_t>(host_threads(), std::max<int64_t>(1, bytes >> 19));
 }
 
 /* A small persistent pool: chunked batches call parallel_for dozens of times per second, so
@@ -179,94 +197,69 @@ static void parallel_for(int nthreads, int64_t n, F&& fn) {
   Pool::get().run(nthreads, body);
 }
 
-int64_t layout_pairs(const int32_t* p_len, const int32_t* t_len, int64_t n, PairMetaHost* meta,
-                     int32_t* max_plen, int32_t* max_tlen, int bases_per_word) {
+
+/* fixed length classes (max(plen, tlen) <= limit): the capacity steps of the alignment tiers */
+static const int32_t kClassLimit[MAX_LEN_CLASSES] = {192, 320, 512, 1024, 2048, 4096, 12000, INT32_MAX};
+int32_t length_class_limit(int c) { return kClassLimit[c]; }
+
+void scan_pairs(const int64_t* p_off, const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
+                int bases_per_word, PairScan* out) {
   const int64_t bpw = bases_per_word;
-  const int nt = pack_threads(n, n * 16);
-  std::vector<int64_t> part(nt + 1, 0);
-  std::vector<int32_t> mp(nt, 0), mt(nt, 0);
+  const int nt = pack_threads(n, n * 24);
+  std::vector<PairScan> part(nt);
   parallel_for(nt, n, [&](int t, int64_t a, int64_t b) {
-    int64_t s = 0; int32_t xp = 0, xt = 0;
+    PairScan r;
     for (int64_t i = a; i < b; ++i) {
-      s += ((int64_t)p_len[i] + bpw - 1) / bpw + ((int64_t)t_len[i] + bpw - 1) / bpw;
-      xp = std::max(xp, p_len[i]); xt = std::max(xt, t_len[i]);
+      const int32_t pl = p_len[i], tl = t_len[i];
+      if ((pl | tl) < 0) { if (r.first_negative < 0) r.first_negative = i; continue; }
+      r.seq_bytes += (int64_t)pl + tl;
+      r.total_words += ((int64_t)pl + bpw - 1) / bpw + ((int64_t)tl + bpw - 1) / bpw;
+      if (pl) { r.lo = std::min(r.lo, p_off[i]); r.hi = std::max(r.hi, p_off[i] + pl); }
+      if (tl) { r.lo = std::min(r.lo, t_off[i]); r.hi = std::max(r.hi, t_off[i] + tl); }
+      r.maxp = std::max(r.maxp, pl); r.maxt = std::max(r.maxt, tl);
+      r.minp = std::min(r.minp, pl); r.mint = std::min(r.mint, tl);
+      const int32_t L = std::max(pl, tl);
+      int c = 0;
+      while (L > kClassLimit[c]) ++c;
+      r.cls_n[c]++; r.cls_maxp[c] = std::max(r.cls_maxp[c], pl); r.cls_maxt[c] = std::max(r.cls_maxt[c], tl);
     }
-    part[t + 1] = s; mp[t] = xp; mt[t] = xt;
+    part[t] = r;
+  });
+  PairScan r;
+  for (const PairScan& q : part) {
+    if (q.first_negative >= 0 && (r.first_negative < 0 || q.first_negative < r.first_negative)) r.first_negative = q.first_negative;
+    r.seq_bytes += q.seq_bytes; r.total_words += q.total_words;
+    r.lo = std::min(r.lo, q.lo); r.hi = std::max(r.hi, q.hi);
+    r.maxp = std::max(r.maxp, q.maxp); r.maxt = std::max(r.maxt, q.maxt);
+    r.minp = std::min(r.minp, q.minp); r.mint = std::min(r.mint, q.mint);
+    for (int c = 0; c < MAX_LEN_CLASSES; ++c) {
+      r.cls_n[c] += q.cls_n[c];
+      r.cls_maxp[c] = std::max(r.cls_maxp[c], q.cls_maxp[c]); r.cls_maxt[c] = std::max(r.cls_maxt[c], q.cls_maxt[c]);
+    }
+  }
+  if (r.lo > r.hi) r.lo = r.hi = 0;
+  *out = r;
+}
+
+void gather_pairs(const uint8_t* seq, const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
+                  const int32_t* t_len, int64_t n, uint8_t* dst, int64_t* new_p_off, int64_t* new_t_off) {
+  const int nt = pack_threads(n, n * 64);
+  std::vector<int64_t> part(nt + 1, 0);
+  parallel_for(nt, n, [&](int t, int64_t a, int64_t b) {
+    int64_t s = 0;
+    for (int64_t i = a; i < b; ++i) s += (int64_t)p_len[i] + t_len[i];
+    part[t + 1] = s;
   });
   for (int t = 0; t < nt; ++t) part[t + 1] += part[t];
   parallel_for(nt, n, [&](int t, int64_t a, int64_t b) {
     int64_t off = part[t];
     for (int64_t i = a; i < b; ++i) {
-      meta[i].woff = off; meta[i].plen = p_len[i]; meta[i].tlen = t_len[i];
-      off += ((int64_t)p_len[i] + bpw - 1) / bpw + ((int64_t)t_len[i] + bpw - 1) / bpw;
-    }
-  });
-  *max_plen = *std::max_element(mp.begin(), mp.end());
-  *max_tlen = *std::max_element(mt.begin(), mt.end());
-  return part[nt];
-}
-
-int64_t pack_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
-                   const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint,
-                   std::vector<int64_t>* bad) {
-  const int nt = pack_threads(n, seq_bytes_hint);
-  std::atomic<int64_t> first_bad(INT64_MAX);
-  std::vector<std::vector<int64_t>> bad_t(nt);
-  parallel_for(nt, n, [&](int tid, int64_t a, int64_t b) {
-    for (int64_t i = a; i < b; ++i) {
-      uint32_t* w = words + meta[i].woff;
-      const int pw = (meta[i].plen + 15) / 16;
-      bool ok = pack_sequence(seq + p_off[i], meta[i].plen, w);
-      ok &= pack_sequence(seq + t_off[i], meta[i].tlen, w + pw);
-      if (!ok) {
-        int64_t cur = first_bad.load();
-        while (i < cur && !first_bad.compare_exchange_weak(cur, i)) {}
-        if (bad) bad_t[tid].push_back(i);
-      }
-    }
-  });
-  if (bad) {
-    bad->clear();
-    for (auto& v : bad_t) bad->insert(bad->end(), v.begin(), v.end());     /* threads own ascending ranges */
-    std::sort(bad->begin(), bad->end());
-  }
-  const int64_t fb = first_bad.load();
-  return fb == INT64_MAX ? -1 : fb;
-}
-
-static void put_bytes(const uint8_t* s, int len, uint32_t* out) {
-  /* upper-case a-z like pywfa does before the C call (pywfa/align.pyx:431-435); byte j of a word in bits 8j.. */
-  uint8_t* o = reinterpret_cast<uint8_t*>(out);
-  for (int i = 0; i < len; ++i) { const uint8_t c = s[i]; o[i] = (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
-  for (int i = len; i < ((len + 3) & ~3); ++i) o[i] = 0;
-}
-
-int64_t layout_side_pairs(const std::vector<int64_t>& ids, PairMetaHost* meta) {
-  int64_t off = 0;
-  for (int64_t i : ids) {
-    meta[i].woff = ~off;
-    off += ((int64_t)meta[i].plen + 3) / 4 + ((int64_t)meta[i].tlen + 3) / 4;
-  }
-  return off;
-}
-
-void pack_side_pairs(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off, const PairMetaHost* meta,
-                     const std::vector<int64_t>& ids, uint32_t* words2) {
-  for (int64_t i : ids) {
-    uint32_t* w = words2 + ~meta[i].woff;
-    put_bytes(seq + p_off[i], meta[i].plen, w);
-    put_bytes(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
-  }
-}
-
-void pack_pairs_bytes(const uint8_t* seq, const int64_t* p_off, const int64_t* t_off,
-                      const PairMetaHost* meta, int64_t n, uint32_t* words, int64_t seq_bytes_hint) {
-  const int nt = pack_threads(n, seq_bytes_hint);
-  parallel_for(nt, n, [&](int, int64_t a, int64_t b) {
-    for (int64_t i = a; i < b; ++i) {
-      uint32_t* w = words + meta[i].woff;
-      put_bytes(seq + p_off[i], meta[i].plen, w);
-      put_bytes(seq + t_off[i], meta[i].tlen, w + (meta[i].plen + 3) / 4);
+      new_p_off[i] = off;
+      memcpy(dst + off, seq + p_off[i], (size_t)p_len[i]);
+      off += p_len[i];
+      new_t_off[i] = off;
+      memcpy(dst + off, seq + t_off[i], (size_t)t_len[i]);
+      off += t_len[i];
     }
   });
 }

@@ -7,6 +7,38 @@
 namespace wfagpu {
 
 struct KParams;
+struct PairMeta;
+
+/* ---- batch staging on the device (wfa_pack.cu) ---- */
+constexpr int MAX_BUCKETS = 8;
+struct PackCounters {                 /* in HBM, read back by the host after the pack kernels */
+  unsigned long long n_side;          /* pairs holding a byte other than ACGT/acgt */
+  unsigned long long side_words;      /* words of the byte side buffer they need */
+};
+struct BucketArgs {                   /* work lists by max(plen, tlen); nbuckets <= 1: none */
+  int nbuckets;
+  int max_len[MAX_BUCKETS];           /* bucket q takes pairs with max(plen, tlen) <= max_len[q] (the last one: the rest) */
+  int list_base[MAX_BUCKETS];         /* first slot of bucket q in `list` (host-side histogram) */
+  int* cursor;                        /* [MAX_BUCKETS] zeroed */
+  int* list;                          /* n pair ids */
+};
+struct PackArgs {
+  const uint8_t* ascii;               /* device address of byte `base` of the caller's sequence buffer */
+  long long base;
+  const int64_t* p_off; const int64_t* t_off;     /* offsets into the caller's buffer (device copies) */
+  long long n;
+  PairMeta* pairs;
+  uint32_t* words; uint32_t* words2;
+  PackCounters* counters;
+};
+int layout_tiles(long long n);
+/* exclusive scan of the per-pair word counts -> pairs[i] = {woff, plen, tlen}; tile_sums: layout_tiles(n) + 1 entries */
+cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long n, int bases_per_word,
+                          long long* tile_sums, PairMeta* pairs, const BucketArgs& B, cudaStream_t st);
+/* ASCII -> 2-bit words (or bytes when byte_mode); flags pairs with other bytes (PackCounters) */
+cudaError_t launch_pack(const PackArgs& A, bool byte_mode, int max_len, int sms, cudaStream_t st);
+/* bytes of the flagged pairs -> words2 */
+cudaError_t launch_pack_side(const PackArgs& A, int sms, cudaStream_t st);
 
 /* mode 0: warp-per-pair (smem ring), 1: block-per-pair (smem ring), 2: block-per-pair (HBM ring) */
 cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool off16, int grid, int block,

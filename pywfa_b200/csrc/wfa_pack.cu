@@ -1,0 +1,275 @@
+/*
+ * wfa_pack.cu -- device side of the batch staging: raw ASCII bases in HBM -> the batch layout the
+ * alignment kernels read (PairMeta + 2-bit packed words), plus the per-length-bucket work lists.
+ *
+ * Replaces wavefront_sequences_init_ascii (W/wavefront/wavefront_sequences.c:141-170: one
+ * sentinel-padded byte copy of both sequences per alignment, on the CPU) for the whole batch.
+ * The caller's bases are uploaded as they are (straight from pinned memory when the caller
+ * provides it) and packed here, so no host core touches a base:
+ *
+ *   layout_count / layout_scan / layout_apply   exclusive scan of the per-pair word counts
+ *        -> PairMeta{woff, plen, tlen}; optional bucket work lists (pair ids by max(plen, tlen))
+ *   pack2_kernel        16 bases per 32-bit word, base j in bits 2j..2j+1, code = (c >> 1) & 3
+ *        (A=0 C=1 T=2 G=3, either case); pairs holding any other byte get a slot in the byte side
+ *        buffer (PairMeta::woff = ~offset) and are counted
+ *   pack_bytes_kernel   upper-cased bytes, 4 per word (byte mode / the side buffer)
+ *
+ * All kernels are HBM streaming kernels (read 1 B, write 0.25 B per base); the bound that matters
+ * for them is the PCIe link feeding the bytes, two orders of magnitude below HBM.
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "wfa_core.cuh"
+#include "wfa_launch.h"
+
+namespace wfagpu {
+
+namespace {
+
+constexpr int LAY_THREADS = 256;
+constexpr int LAY_ITEMS = 16;
+constexpr int LAY_TILE = LAY_THREADS * LAY_ITEMS;
+
+__device__ __forceinline__ long long words_of(int plen, int tlen, int bpw) {
+  return (long long)((plen + bpw - 1) / bpw) + (long long)((tlen + bpw - 1) / bpw);
+}
+
+__global__ void layout_count_kernel(const int32_t* __restrict__ p_len, const int32_t* __restrict__ t_len, long long n,
+                                    int bpw, long long* __restrict__ tile_sums) {
+  __shared__ long long wsum[LAY_THREADS / 32];
+  const long long t0 = (long long)blockIdx.x * LAY_TILE;
+  long long acc = 0;
+  for (int j = 0; j < LAY_ITEMS; ++j) {
+    const long long i = t0 + j * LAY_THREADS + threadIdx.x;
+    if (i < n) acc += words_of(p_len[i], t_len[i], bpw);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long s = 0;
+    for (int i = 0; i < LAY_THREADS / 32; ++i) s += wsum[i];
+    tile_sums[blockIdx.x] = s;
+  }
+}
+
+/* single block: exclusive scan of the tile sums in place; total -> tile_sums[ntiles] */
+__global__ void layout_scan_kernel(long long* tile_sums, int ntiles) {
+  __shared__ long long carry;
+  __shared__ long long wtot[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int b = 0; b < ntiles; b += blockDim.x) {
+    const int i = b + threadIdx.x;
+    const long long v = (i < ntiles) ? tile_sums[i] : 0;
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
+    const long long excl = carry + woff + inc - v;
+    if (i < ntiles) tile_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+
+/* per tile: word offset of every pair -> PairMeta; bucket work lists when nbuckets > 1 */
+__global__ void layout_apply_kernel(const int32_t* __restrict__ p_len, const int32_t* __restrict__ t_len, long long n,
+                                    int bpw, const long long* __restrict__ tile_sums, PairMeta* __restrict__ pairs,
+                                    BucketArgs B) {
+  __shared__ long long wtot[LAY_THREADS / 32];
+  __shared__ long long carry_s;
+  const long long t0 = (long long)blockIdx.x * LAY_TILE;
+  if (threadIdx.x == 0) carry_s = tile_sums[blockIdx.x];
+  __syncthreads();
+  for (int j = 0; j < LAY_ITEMS; ++j) {
+    const long long i = t0 + j * LAY_THREADS + threadIdx.x;
+    const int pl = (i < n) ? p_len[i] : 0, tl = (i < n) ? t_len[i] : 0;
+    const long long v = words_of(pl, tl, bpw);
+    long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    long long woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
+    const long long excl = carry_s + woff + inc - v;
+    if (i < n) {
+      PairMeta m;
+      m.woff = excl; m.plen = pl; m.tlen = tl;
+      pairs[i] = m;
+    }
+    if (B.nbuckets > 1) {
+      /* one atomic per bucket and warp: the lanes of a bucket take consecutive list slots */
+      const int L = pl > tl ? pl : tl;
+      int bk = B.nbuckets - 1;
+      for (int q = B.nbuckets - 2; q >= 0; --q) if (L <= B.max_len[q]) bk = q;
+      if (i >= n) bk = -1;
+      const unsigned peers = __match_any_sync(0xffffffffu, bk);
+      const int lane = threadIdx.x & 31;
+      const int leader = __ffs(peers) - 1;
+      int base = 0;
+      if (lane == leader && bk >= 0) base = atomicAdd(&B.cursor[bk], __popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (bk >= 0) B.list[B.list_base[bk] + base + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == LAY_THREADS - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+/* 16 bases -> one word.  `s` may have any alignment: two aligned 16-byte loads (only chunks that
+ * hold at least one of the wanted bytes are touched, so nothing outside the caller's bytes' own
+ * 16-byte lines is ever read) and a funnel shift.  Returns the packed word; `bad` is raised when a
+ * byte other than ACGT/acgt was seen. */
+__device__ __forceinline__ uint32_t pack16(const uint8_t* s, int nb, bool& bad) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
+  const uint4* al = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+  const int sh = (int)(a & 15);
+  const uint4 lo = __ldg(al);
+  uint4 hi = make_uint4(0, 0, 0, 0);
+  if (sh + nb > 16) hi = __ldg(al + 1);
+  const int r = (sh & 3) * 8;
+  uint32_t w0, w1, w2, w3;
+  switch (sh >> 2) {
+    case 0: w0 = __funnelshift_r(lo.x, lo.y, r); w1 = __funnelshift_r(lo.y, lo.z, r); w2 = __funnelshift_r(lo.z, lo.w, r); w3 = __funnelshift_r(lo.w, hi.x, r); break;
+    case 1: w0 = __funnelshift_r(lo.y, lo.z, r); w1 = __funnelshift_r(lo.z, lo.w, r); w2 = __funnelshift_r(lo.w, hi.x, r); w3 = __funnelshift_r(hi.x, hi.y, r); break;
+    case 2: w0 = __funnelshift_r(lo.z, lo.w, r); w1 = __funnelshift_r(lo.w, hi.x, r); w2 = __funnelshift_r(hi.x, hi.y, r); w3 = __funnelshift_r(hi.y, hi.z, r); break;
+    default: w0 = __funnelshift_r(lo.w, hi.x, r); w1 = __funnelshift_r(hi.x, hi.y, r); w2 = __funnelshift_r(hi.y, hi.z, r); w3 = __funnelshift_r(hi.z, hi.w, r); break;
+  }
+  uint32_t w[4] = {w0, w1, w2, w3};
+  uint32_t out = 0, ok = 0xffffffffu;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    /* bytes of this word that exist: nb - 4q of them (clamped to 0..4) */
+    const int live = min(max(nb - 4 * q, 0), 4);
+    const uint32_t keep = live >= 4 ? 0xffffffffu : ((1u << (8 * live)) - 1u);
+    const uint32_t x = w[q] & keep;
+    const uint32_t u = x & 0xDFDFDFDFu;
+    const uint32_t good = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+    ok &= good | ~keep;
+    uint32_t c = (x >> 1) & 0x03030303u;
+    c |= c >> 6;
+    c = (c | (c >> 12)) & 0xffu;
+    out |= c << (8 * q);
+  }
+  bad |= ok != 0xffffffffu;
+  return out;
+}
+
+/* One warp (BLOCK = false) or one CTA (long reads) per pair. */
+template <bool BLOCK>
+__global__ void __launch_bounds__(256) pack2_kernel(PackArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int gsize = BLOCK ? (int)blockDim.x : 32;
+  const int grank = BLOCK ? (int)threadIdx.x : lane;
+  const long long gid = BLOCK ? (long long)blockIdx.x : (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long ngroups = BLOCK ? (long long)gridDim.x : (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long i = gid; i < A.n; i += ngroups) {
+    const PairMeta m = A.pairs[i];
+    const uint8_t* ps = A.ascii + (A.p_off[i] - A.base);
+    const uint8_t* ts = A.ascii + (A.t_off[i] - A.base);
+    const int pw = (m.plen + 15) >> 4, tw = (m.tlen + 15) >> 4;
+    uint32_t* out = A.words + m.woff;
+    bool bad = false;
+    for (int w = grank; w < pw + tw; w += gsize) {
+      const bool is_t = w >= pw;
+      const int j = is_t ? w - pw : w;
+      const int len = is_t ? m.tlen : m.plen;
+      out[w] = pack16((is_t ? ts : ps) + 16 * j, min(16, len - 16 * j), bad);
+    }
+    const bool any_bad = BLOCK ? (__syncthreads_or(bad) != 0) : __any_sync(0xffffffffu, bad);
+    if (any_bad && grank == 0) {
+      /* byte side buffer slot: the scalar tiers read this pair as bytes (4 per word) */
+      const long long bw = words_of(m.plen, m.tlen, 4);
+      const unsigned long long off = atomicAdd(&A.counters->side_words, (unsigned long long)bw);
+      atomicAdd(&A.counters->n_side, 1ull);
+      A.pairs[i].woff = ~(long long)off;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t upper4(const uint8_t* s, int nb) {
+  uint32_t w = 0;
+  for (int b = 0; b < 4; ++b) {
+    if (b < nb) {
+      uint32_t c = s[b];
+      if (c >= 'a' && c <= 'z') c -= 32;     /* pywfa upper-cases before the C call (pywfa/align.pyx:431-435) */
+      w |= c << (8 * b);
+    }
+  }
+  return w;
+}
+
+/* Upper-cased bytes, 4 per word.  side = true: only the pairs flagged by pack2_kernel, into words2
+ * at ~woff; side = false (byte mode): every pair, into words at woff. */
+__global__ void __launch_bounds__(256) pack_bytes_kernel(PackArgs A, bool side) {
+  const int lane = threadIdx.x & 31;
+  const long long gid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long ngroups = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long i = gid; i < A.n; i += ngroups) {
+    const PairMeta m = A.pairs[i];
+    if (side && m.woff >= 0) continue;
+    const uint8_t* ps = A.ascii + (A.p_off[i] - A.base);
+    const uint8_t* ts = A.ascii + (A.t_off[i] - A.base);
+    const int pw = (m.plen + 3) >> 2, tw = (m.tlen + 3) >> 2;
+    uint32_t* out = side ? A.words2 + ~m.woff : A.words + m.woff;
+    for (int w = lane; w < pw + tw; w += 32) {
+      const bool is_t = w >= pw;
+      const int j = is_t ? w - pw : w;
+      const int len = is_t ? m.tlen : m.plen;
+      out[w] = upper4((is_t ? ts : ps) + 4 * j, min(4, len - 4 * j));
+    }
+  }
+}
+
+}  // namespace
+
+int layout_tiles(long long n) { return (int)((n + LAY_TILE - 1) / LAY_TILE); }
+
+cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long n, int bases_per_word,
+                          long long* tile_sums, PairMeta* pairs, const BucketArgs& B, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int tiles = layout_tiles(n);
+  layout_count_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums);
+  layout_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tiles);
+  layout_apply_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums, pairs, B);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const PackArgs& A, bool byte_mode, int max_len, int sms, cudaStream_t st) {
+  if (A.n <= 0) return cudaSuccess;
+  if (byte_mode) {
+    const long long blocks = std::min<long long>((A.n + 7) / 8, (long long)sms * 8);
+    pack_bytes_kernel<<<(int)blocks, 256, 0, st>>>(A, false);
+  } else if (max_len > 4096) {
+    const long long blocks = std::min<long long>(A.n, (long long)sms * 8);
+    pack2_kernel<true><<<(int)blocks, 256, 0, st>>>(A);
+  } else {
+    const long long blocks = std::min<long long>((A.n + 7) / 8, (long long)sms * 8);
+    pack2_kernel<false><<<(int)blocks, 256, 0, st>>>(A);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_side(const PackArgs& A, int sms, cudaStream_t st) {
+  if (A.n <= 0) return cudaSuccess;
+  const long long blocks = std::min<long long>((A.n + 7) / 8, (long long)sms * 8);
+  pack_bytes_kernel<<<(int)blocks, 256, 0, st>>>(A, true);
+  return cudaGetLastError();
+}
+
+}  // namespace wfagpu

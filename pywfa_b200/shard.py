@@ -8,6 +8,9 @@ is no collective on the data path.  Two drivers share the same planning / mergin
   results are gathered with ``torch.distributed`` object collectives on a host (gloo) group.
 * ``align_multi_device``   one process, one host thread and one ``wfagpu_ctx`` per device (the
   C library releases the GIL while it runs).
+* ``SharedResults``   the zero-copy form of the host-side gather for one process per GPU: the
+  job's result arrays live in ONE shared-memory segment that every rank maps and pins, so each
+  rank's copy engine writes its shard's results straight into the gathered arrays.
 """
 from __future__ import annotations
 
@@ -15,7 +18,7 @@ import threading
 
 import numpy as np
 
-__all__ = ["plan_shards", "slice_batch", "merge_results", "align_sharded", "align_multi_device"]
+__all__ = ["plan_shards", "slice_batch", "merge_results", "align_sharded", "align_multi_device", "SharedResults"]
 
 
 def plan_shards(p_len, t_len, n_shards: int):
@@ -118,3 +121,113 @@ def align_multi_device(cfg, batch, devices, contexts=None):
         if e is not None:
             raise e
     return merge_results(parts)
+
+
+class SharedResults:
+    """Result arrays of a whole job (``n_total`` pairs over ``world`` ranks) in one shared-memory file.
+
+    Rank 0 creates ``/dev/shm/<tag>-<MASTER_PORT>`` (score, status and -- ``full`` -- locs, cig_off),
+    the other ranks map it after a barrier of ``torch.distributed``; with a visible GPU every rank pins
+    the mapping (``wfagpu_host_register``), so ``Context.align_batch(..., out=shared.slices(start, n))``
+    downloads by DMA into the gathered arrays and the host-side gather costs no copy.  With
+    ``world == 1`` these are plain pinned (or, without a GPU, ordinary) arrays.  CIGAR runs are
+    gathered by giving each rank's context its slice of ``runs`` (``Context.set_run_buffer``);
+    ``cig_off`` values are relative to the owning rank's slice, whose first word is ``run_base(rank)``.
+    """
+
+    def __init__(self, n_total: int, full: bool, rank: int = 0, world: int = 1, tag: str = "wfagpu", runs_per_rank: int = 0,
+                 pin: bool = True):
+        import os
+        self.n, self.full, self.rank, self.world = int(n_total), bool(full), rank, world
+        self.runs_per_rank = int(runs_per_rank) if full else 0
+        fields = [("score", np.int32, (self.n,)), ("status", np.int32, (self.n,))]
+        if full:
+            fields += [("cig_off", np.int64, (self.n + world,)), ("locs", np.int32, (self.n, 4))]
+            if self.runs_per_rank:
+                fields.append(("runs", np.uint32, (self.runs_per_rank * world,)))
+        sizes = [int(np.prod(shape)) * np.dtype(dt).itemsize for _, dt, shape in fields]
+        offs = np.concatenate(([0], np.cumsum([(sz + 4095) // 4096 * 4096 for sz in sizes])))
+        total = int(offs[-1]) or 4096
+        self._path = None
+        self._registered = False
+        self._map = None
+        if world > 1:
+            import mmap
+            import torch.distributed as dist
+            self._path = f"/dev/shm/{tag}-{os.environ.get('MASTER_PORT', '0')}"
+            if rank == 0:
+                with open(self._path, "wb") as fh:
+                    fh.truncate(total)
+            dist.barrier()
+            fh = open(self._path, "r+b")
+            self._map = mmap.mmap(fh.fileno(), total)
+            fh.close()
+            buf = np.frombuffer(self._map, np.uint8)
+            if pin:
+                from . import _ffi
+                import ctypes as C
+                if _ffi.lib().wfagpu_device_count() > 0:
+                    self._addr = buf.ctypes.data
+                    self._registered = _ffi.lib().wfagpu_host_register(C.c_void_p(self._addr), total) == 0
+        else:
+            buf = None
+            if pin:
+                try:
+                    from . import _ffi
+                    if _ffi.lib().wfagpu_device_count() > 0:
+                        buf = _ffi.pinned_empty(total, np.uint8)
+                except Exception:
+                    buf = None
+            if buf is None:
+                buf = np.empty(total, np.uint8)
+        self._buf = buf
+        for (name, dt, shape), off, sz in zip(fields, offs[:-1], sizes):
+            setattr(self, name, buf[int(off):int(off) + sz].view(dt).reshape(shape))
+        if not hasattr(self, "runs"):
+            self.runs = None
+
+    def slices(self, start: int, n: int, rank=None):
+        """``out=`` arrays for the shard ``[start, start + n)`` owned by ``rank`` (default: this rank)."""
+        r = self.rank if rank is None else rank
+        out = {"score": self.score[start:start + n], "status": self.status[start:start + n]}
+        if self.full:
+            out["locs"] = self.locs[start:start + n]
+            out["cig_off"] = self.cig_off[start + r:start + r + n + 1]      # n + 1 entries per shard
+        else:
+            out["locs"] = np.empty((n, 4), np.int32)
+            out["cig_off"] = np.empty(n + 1, np.int64)
+        return out
+
+    def run_slice(self, rank=None):
+        r = self.rank if rank is None else rank
+        return None if self.runs is None else self.runs[r * self.runs_per_rank:(r + 1) * self.runs_per_rank]
+
+    def touch(self) -> int:
+        """The consumer's side of the gather: read across all shards of the gathered arrays."""
+        return int(self.status[::1024].sum()) + int(self.score[::1024].sum())
+
+    def close(self):
+        import os
+        for name in ("score", "status", "cig_off", "locs", "runs"):
+            if hasattr(self, name):
+                setattr(self, name, None)
+        if self._registered:
+            from . import _ffi
+            import ctypes as C
+            _ffi.lib().wfagpu_host_unregister(C.c_void_p(self._addr))
+            self._registered = False
+        self._buf = None
+        if self._map is not None:
+            try:
+                self._map.close()
+            except BufferError:
+                pass                     # a caller still holds a view; the mapping goes with it
+            self._map = None
+        if self._path and self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            if self.rank == 0:
+                try:
+                    os.unlink(self._path)
+                except OSError:
+                    pass
