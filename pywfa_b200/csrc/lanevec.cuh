@@ -27,6 +27,7 @@ __device__ __forceinline__ vi lane_id() { return (int)(threadIdx.x & 31); }
 __device__ __forceinline__ vu vimax2(vu a, vu b) { return __vmaxs2(a, b); }
 __device__ __forceinline__ vu vimax3(vu a, vu b, vu c) { return __vimax3_s16x2(a, b, c); }
 __device__ __forceinline__ vu vadd2(vu a, vu b) { return __vadd2(a, b); }
+__device__ __forceinline__ vu vsub2(vu a, vu b) { return __vsub2(a, b); }
 /* max with "a >= b" predicates per half */
 __device__ __forceinline__ vu vimax2p(vu a, vu b, vb& hi, vb& lo) { return __vibmax_s16x2(a, b, &hi, &lo); }
 /* 0xFFFF in every half whose sign bit is set (PRMT with sign replication) */
@@ -41,10 +42,15 @@ __device__ __forceinline__ vu prmt(vu a, vu b, vu sel) { return __byte_perm(a, b
 __device__ __forceinline__ vi sx_lo(vu a) { return (int)(short)(a & 0xffffu); }
 __device__ __forceinline__ vi sx_hi(vu a) { return ((int)a) >> 16; }
 __device__ __forceinline__ vu pack2(vi lo, vi hi) { return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410); }
+/* replace one half of a packed register by the low 16 bits of v */
+__device__ __forceinline__ vu put_lo(vu a, vi v) { return __byte_perm(a, (uint32_t)v, 0x3254); }
+__device__ __forceinline__ vu put_hi(vu a, vi v) { return __byte_perm(a, (uint32_t)v, 0x5410); }
 
 /* ---- lane exchange ---- */
 __device__ __forceinline__ vu from_prev_lane(vu a) { return __shfl_sync(0xffffffffu, a, (threadIdx.x + 31) & 31); }
 __device__ __forceinline__ vu from_next_lane(vu a) { return __shfl_sync(0xffffffffu, a, (threadIdx.x + 1) & 31); }
+/* the value of lane `src` (SHFL.IDX takes the index modulo 32): rotations with a source index kept in a register */
+__device__ __forceinline__ vu from_lane(vu a, vi src) { return __shfl_sync(0xffffffffu, a, src); }
 __device__ __forceinline__ int lane_value(vi a, int lane) { return __shfl_sync(0xffffffffu, a, lane); }
 __device__ __forceinline__ uint32_t ballot(vb p) { return __ballot_sync(0xffffffffu, p); }
 __device__ __forceinline__ bool any(vb p) { return __any_sync(0xffffffffu, p); }
@@ -77,10 +83,42 @@ __device__ __forceinline__ vu load_win(seqref base, vi idx, vb p) {
                : "=r"(r) : "r"(base + 4u * (uint32_t)idx), "r"((uint32_t)p) : "memory");
   return r;
 }
+/* a per-lane position in a window array: the shared-window address of element idx0; element
+ * idx0 + idx + IMM is then one address add away, IMM folded into the LDS immediate */
+typedef uint32_t lanead;
+__device__ __forceinline__ lanead lane_addr(seqref base, vi idx0) { return base + 4u * (uint32_t)idx0; }
+/* predicated LDS of element idx + IMM; lanes with p == false read nothing and get `dflt` */
+template <int IMM>
+__device__ __forceinline__ vu load_win_at(lanead a, vi idx, vb p, uint32_t dflt) {
+  vu r;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\tmov.u32 %0, %4;\n\t@q ld.shared.u32 %0, [%1+%3];\n\t}"
+               : "=r"(r) : "r"(a + 4u * (uint32_t)idx), "r"((uint32_t)p), "n"(4 * IMM), "r"(dflt) : "memory");
+  return r;
+}
+/* min(a + b, c): VIADDMNMX */
+__device__ __forceinline__ vi vaddmin(vi a, vi b, vi c) { return __viaddmin_s32(a, b, c); }
+/* pin a loop-invariant value in its register: the compiler may neither re-derive it nor fold it away */
+__device__ __forceinline__ void keep(uint32_t& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ void keep(int& x) { asm volatile("" : "+r"(x)); }
 __device__ __forceinline__ void scatter_u32(uint32_t* base, vi idx, vu val, vb p) { if (p) base[idx] = val; }
 /* word gather from (shared) memory; lanes with p == false read nothing and get 0 */
 __device__ __forceinline__ vu gather_u32(const uint32_t* base, vi idx, vb p) { return p ? base[idx] : 0u; }
 __device__ __forceinline__ void scatter_u8(uint8_t* base, vi idx, vi val, vb p) { if (p) base[idx] = (uint8_t)val; }
+/* a byte arena of one warp, in shared (SH accessors: STS.U8 / LDS.U8) or global memory */
+struct histref { uint8_t* p; uint32_t s; };
+__device__ __forceinline__ histref make_histref(uint8_t* p, bool shared) {
+  histref h; h.p = p; h.s = shared ? (uint32_t)__cvta_generic_to_shared(p) : 0u; return h;
+}
+template <bool SH>
+__device__ __forceinline__ void hist_store(const histref& h, int off, vi idx, vi val) {
+  if (SH) asm volatile("st.shared.u8 [%0], %1;" :: "r"(h.s + (uint32_t)(off + idx)), "r"(val) : "memory");
+  else h.p[off + idx] = (uint8_t)val;
+}
+template <bool SH>
+__device__ __forceinline__ int hist_load(const histref& h, int off) {
+  if (SH) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(h.s + (uint32_t)off) : "memory"); return (int)v; }
+  return h.p[off];
+}
 
 }  // namespace lv
 }  // namespace wfagpu

@@ -149,6 +149,30 @@ struct PairResult {
   long long cells;
 };
 
+/* Shared memory of one warp of the register tier: [sequence windows][scope=full with the arena in
+ * shared memory (REG_SMEM_HIST): packed sequences for the replay | edit-operation stack | origin arena,
+ * which the CIGAR run staging re-uses once the backward walk is over]. */
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr bool reg_hist_in_smem(int regs, bool full) { return full && regs == 2; }
+struct RegSmem {
+  int win_words, pk_words, ops_bytes, hist_bytes;
+  WFA_DEV int pk_off() const { return 4 * win_words; }
+  WFA_DEV int ops_off() const { return pk_off() + 4 * pk_words; }
+  WFA_DEV int hist_off() const { return (ops_off() + ops_bytes + 15) & ~15; }
+  WFA_DEV int total() const { return (hist_off() + hist_bytes + 15) & ~15; }
+};
+WFA_DEV RegSmem reg_smem_layout(int regs, bool full, int seq_words_cap, int ropcap, int hrows) {
+  RegSmem L;
+  L.win_words = seq_words_cap;
+  const bool hs = reg_hist_in_smem(regs, full);
+  L.pk_words = hs ? (seq_words_cap + 15) / 16 + 4 : 0;
+  L.ops_bytes = hs ? ropcap : 0;
+  L.hist_bytes = hs ? hrows * 32 * regs : 0;
+  return L;
+}
+
 /* ------------------------------------------------------------------------------------ */
 #ifdef __CUDACC__
 WFA_DEV uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) { return __funnelshift_r(lo, hi, sh); }

@@ -373,22 +373,35 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
                                the 192-diagonal window on cfg2 / cfg1: 6 -> 46.1 / 115.2, 7 -> 46.5 / 117.1, 8 -> 40.6 / 111.1
                                M pairs/s; with the 256-diagonal window only: 5 -> 41.6, 6 -> 42.8, 7 -> 37.3) */
 #endif
+#ifndef WFA_REG_MINB2
+#define WFA_REG_MINB2 WFA_REG_MINB     /* ... for the 128-diagonal window */
+#endif
+#ifndef WFA_REG_MINB3
+#define WFA_REG_MINB3 WFA_REG_MINB     /* ... for the 192-diagonal window */
+#endif
+__host__ __device__ constexpr int reg_min_blocks(int regs) { return regs == 2 ? WFA_REG_MINB2 : regs == 3 ? WFA_REG_MINB3 : WFA_REG_MINB; }
 /* ---- the register-resident tier (wfa_reg.cuh): warp-per-pair, wavefronts in registers ---- */
 /* shared memory of one warp: the sequence windows of the pair (seq_words_cap words, one per base + 2) */
 template <int P, int DX, int DOE, bool FULL>
-__global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool HS = reg_hist_in_smem(P, FULL);        /* origin arena, edit-operation stack and run staging in shared memory */
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp_id = blockIdx.x * (blockDim.x >> 5) + wib;
-  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)wib * K.seq_words_cap;
+  const RegSmem L = reg_smem_layout(P, FULL, K.seq_words_cap, K.ropcap, K.rhrows);
+  unsigned char* const wbase = smem_raw + (size_t)wib * K.group_bytes;
+  uint32_t* const sm_seq = reinterpret_cast<uint32_t*>(wbase);
+  uint32_t* const sm_pk = reinterpret_cast<uint32_t*>(wbase + L.pk_off());
 
   RegParams R;
   R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = K.rhrows; R.opcap = K.ropcap; R.runcap = K.runcap;
-  uint8_t* const hist = FULL ? K.rhist + (long long)warp_id * K.rhist_bytes : nullptr;
-  uint8_t* const ops = FULL ? K.rops + (long long)warp_id * K.ropcap : nullptr;
-  uint32_t* const stage = FULL ? K.runs_stage + (long long)warp_id * K.runcap : nullptr;
+  uint8_t* const hist_p = !FULL ? nullptr : HS ? wbase + L.hist_off() : K.rhist + (long long)warp_id * K.rhist_bytes;
+  const lv::histref hist = lv::make_histref(hist_p, HS);
+  uint8_t* const ops = !FULL ? nullptr : HS ? wbase + L.ops_off() : K.rops + (long long)warp_id * K.ropcap;
+  /* the run staging re-uses the arena: the backward walk has left it when the replay emits runs */
+  uint32_t* const stage = !FULL ? nullptr : HS ? reinterpret_cast<uint32_t*>(hist_p) : K.runs_stage + (long long)warp_id * K.runcap;
 
   const int n_work = *K.n_work;
   long long cells_acc = 0;
@@ -412,6 +425,12 @@ __global__ void __launch_bounds__(128, WFA_REG_MINB) wfa_reg_kernel(const __grid
       uint32_t* sp = sm_seq; uint32_t* st = sm_seq + plen + 1;
       build_windows(gp, plen, sp);
       build_windows(gt, tlen, st);
+      if (HS) {
+        /* the replay of the backtrace re-extends matches from the packed words: keep them close */
+        const int nw = pwn + ((tlen + 15) >> 4) + 1;
+        for (int i = lane; i < nw; i += 32) sm_pk[i] = gp[i];
+        gp = sm_pk; gt = sm_pk + pwn;
+      }
       __syncwarp();
       rc = align_pair_reg<P, DX, DOE, FULL>(R, gp, gt, lv::make_seqref(sp), lv::make_seqref(st), plen, tlen, hist, ops,
                                             stage, lane == 0, res);

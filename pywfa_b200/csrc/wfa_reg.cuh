@@ -32,10 +32,11 @@
  * reference) unless trim_ends removes them; that exact trimming runs only in the rare steps
  * in which a packed compare finds a new I/D offset above ub.
  *
- * scope=full.  One origin byte per cell is written to a per-warp arena (row = score, column =
- * window diagonal): bits 0-1 winner of M (1 mismatch, 2 insertion, 3 deletion; ties resolve
- * M > D > I as W/wavefront/wavefront_backtrace.c:49-59), bit 2 "I[s][k+1] extends" and bit 3
- * "D[s][k-1] extends" (ext >= open), stored at the source diagonal.  The backtrace walks these
+ * scope=full.  One origin code (4 bits) per cell is written to a per-warp arena (row = score, the two
+ * cells of a lane's packed register share a byte; shared memory for the 128-diagonal window, HBM / L2
+ * otherwise): bits 0-1 winner of M (ties resolve M > D > I as W/wavefront/wavefront_backtrace.c:49-59),
+ * bit 2 "I[s][k+1] is opened" and bit 3 "D[s][k-1] is opened" (ext >= open extends), stored at the
+ * source diagonal.  The backtrace walks these
  * bytes from the end cell to score 0 collecting the edit operations, then replays them forwards
  * re-extending the matches from the sequences, which yields the run-length encoded CIGAR in
  * order without ever storing offsets.
@@ -67,30 +68,42 @@ struct RegParams {
 };
 
 /*
- * Backtrace over origin bytes (one thread): backward walk, then forward replay.
- * hist row stride = win; column = diagonal - kbase.  Returns the number of runs (may exceed
- * em.cap, then the CIGAR did not fit) or -1 if the operation stack overflowed.
+ * Origin arena layout.  One byte per lane and packed register: low nibble = code of the register's
+ * low half (window column 64p + lane), high nibble = code of its high half (column 64p + 32 + lane);
+ * row = score, 32 * P bytes per row.  Code bits: 0 "deletion beats mismatch", 1 "insertion beats
+ * both", 2 "I of this diagonal is opened (not extended)", 3 "D of this diagonal is opened".
  */
-WFA_DEV int backtrace_origin(const uint8_t* hist, int win, int kbase, int dx, int doe, int de,
+template <bool SH>
+WFA_DEV int origin_code(const lv::histref& h, int row_bytes, int s, int d) {
+  const int b = lv::hist_load<SH>(h, s * row_bytes + ((d >> 6) << 5) + (d & 31));
+  return (d & 32) ? (b >> 4) : (b & 15);
+}
+
+/*
+ * Backtrace over origin codes (one thread): backward walk, then forward replay.
+ * Returns the number of runs (may exceed em.cap, then the CIGAR did not fit) or -1 if the
+ * operation stack overflowed.  `em` may write over the arena: the walk is over by then.
+ */
+template <bool SH>
+WFA_DEV int backtrace_origin(const lv::histref& hist, int row_bytes, int kbase, int dx, int doe, int de,
                              int s_end, int k_end, int plen, int tlen, const uint32_t* pw, const uint32_t* tw,
                              uint8_t* ops, int opcap, FwdEmitter& em) {
   int s = s_end, d = k_end - kbase, nops = 0;
   int mt = CM;
   while (s > 0) {
-    const uint8_t* row = hist + (long long)s * win;
     int enter = mt;
     if (mt == CM) {
-      const int w = row[d] & 3;
-      if (w == 1) { if (nops < opcap) ops[nops] = EOP_X; ++nops; s -= dx; continue; }
-      enter = (w == 2) ? CI1 : CD1;
+      const int c = origin_code<SH>(hist, row_bytes, s, d);
+      if (!(c & 3)) { if (nops < opcap) ops[nops] = EOP_X; ++nops; s -= dx; continue; }
+      enter = (c & 2) ? CI1 : CD1;
     }
     if (enter == CI1) {
-      const int ext = (row[d - 1] >> 2) & 1;
+      const int ext = !((origin_code<SH>(hist, row_bytes, s, d - 1) >> 2) & 1);
       if (nops < opcap) ops[nops] = ext ? EOP_I_EXT : EOP_I_OPEN;
       ++nops; --d;
       if (ext) { s -= de; mt = CI1; } else { s -= doe; mt = CM; }
     } else {
-      const int ext = (row[d + 1] >> 3) & 1;
+      const int ext = !((origin_code<SH>(hist, row_bytes, s, d + 1) >> 3) & 1);
       if (nops < opcap) ops[nops] = ext ? EOP_D_EXT : EOP_D_OPEN;
       ++nops; ++d;
       if (ext) { s -= de; mt = CD1; } else { s -= doe; mt = CM; }
@@ -124,81 +137,106 @@ WFA_DEV void build_windows(const uint32_t* words, int len, uint32_t* win) {
 
 template <int P, int DX, int DOE, bool FULL>
 struct RegAligner {
-  static constexpr int RM = DX > DOE ? DX : DOE;   /* M ring: M[r] = wavefront of score s-r */
+  static constexpr int RM = DX > DOE ? DX : DOE;   /* M ring: M[r] = wavefront of score s-1-r when score s is computed */
   static constexpr int DE = 1;
   static constexpr int NB = 2 * P;                 /* 32-diagonal blocks */
   static constexpr int WIN = 64 * P;
+  /* warp-uniform flags: bit r < RM "M[r] holds a valid offset"; then I, D; then the sticky "wavefront
+   * extents must be scanned, not derived from reach(s)" */
+  static constexpr uint32_t F_I = 1u << 8, F_D = 1u << 9, F_EXACT = 1u << 10;
+  static constexpr uint32_t F_MRING = (1u << RM) - 1u;
+  static constexpr uint32_t F_SOURCES = (1u << (DX - 1)) | (1u << (DOE - 1)) | F_I | F_D;
 
   /* wavefront registers */
   lv::vu M[RM][P], I[P], D[P];
   lv::vu ub2[P];                                   /* packed ub[k] per register */
+  /* per-lane constants of the pair, pinned in registers (lv::keep) so that the step loop never re-derives them */
+  lv::vi lane, lprev, lnext;                       /* lane, and the lanes holding diagonals k - 1 / k + 1 */
+  lv::vu selL, selR;                               /* PRMT selectors mending the block seams */
+  lv::lanead pa, ta;                               /* window of pattern position (offset - diagonal of block 0) / text position offset */
   /* warp-uniform state */
-  bool exM[RM], exI, exD;
-  bool exact;                                      /* sticky: wavefront extents must be scanned, not derived from reach(s) */
+  uint32_t flags;
   bool endsfree;
   int pef, tef;
-  lv::seqref pwin, twin;                           /* sequence windows (shared memory) */
-  uint8_t* hist;
+  static constexpr bool HS = reg_hist_in_smem(P, FULL);   /* origin arena in shared memory */
+  lv::histref hist;
   int hrows;
-  int plen, tlen, kbase, lo0, hi0;
+  int plen, tlen, kbase;
+  int c_lo, c_hi;                                  /* window columns of the score-0 seeds [lo0, hi0] */
+  int m_lo, m_hi;                                  /* window columns of the outermost diagonals of the DP matrix (-plen, tlen) */
   int s, s_limit, s_limit_exact;                   /* step limit in units of g (unialign.c:98-109) */
+  int s_event;                                     /* first score at which the derived range needs a second look: it leaves the
+                                                      DP matrix (clip + F_EXACT), the window or the origin arena (overflow) */
+  int wprev;                                       /* cells of the newest M wavefront (0: it holds no valid offset) */
   int cells;
-  int term_d, term_off;                            /* window diagonal and offset of the end cell (term_d < 0: none) */
-  int dak;                                         /* window diagonal of the end-to-end target tlen - plen */
+  int term_d, term_off;                            /* window column and offset of the end cell (term_d < 0: none) */
+  int dak;                                         /* window column of the end-to-end target tlen - plen */
   int status;                                      /* 0 running, 1 end reached, 3 max steps, 4 overflow */
-  int cur_lo, cur_hi;                              /* window range [first, last] of the current M wavefront */
-  lv::vi lane;
-  lv::vu selL, selR;                               /* PRMT selectors mending the block seams */
+  int cur_lo, cur_hi;                              /* window range [first, last] of the newest M wavefront */
 
-  /* ---- extension of one block of 32 diagonals (extend_kernels.c:64-110) -------------- */
-  WFA_DEV lv::vi extend_block(lv::vi off, lv::vi ubk, lv::vi k, lv::vb valid) {
+  /* ---- extension of one block of 32 diagonals (extend_kernels.c:64-110), in place in its half of
+   * the packed register `mn`, followed by the edge / termination bookkeeping (termination.c:37-162) ---- */
+  template <int B>
+  WFA_DEV void extend_block(lv::vu& mn) {
     using namespace lv;
-    const vi rem = ubk - off;                       /* bases left on the diagonal: min(plen - v, tlen - h) */
-    const vi v = off - k;
-    const vu x = load_win(pwin, v, valid) ^ load_win(twin, off, valid);
-    vi n = vmin(vclz(x) >> 1, rem);                 /* x == 0: 16 bases agree */
-    vb more = valid & (n == 16) & (n < rem);
+    constexpr int p = B >> 1;
+    constexpr bool HI = (B & 1) != 0;
+    const vi off0 = HI ? sx_hi(mn) : sx_lo(mn);
+    const vi ubk = HI ? sx_hi(ub2[p]) : sx_lo(ub2[p]);
+    const vb valid = off0 >= 0;
+    /* 16 bases per XOR; a null cell loads nothing and sees "first base differs", so it never moves;
+     * min(offset + matches, ub) clamps the run at the end of the diagonal (VIADDMNMX) */
+    const vu x = load_win_at<-32 * B>(pa, off0, valid, 0u) ^ load_win_at<0>(ta, off0, valid, 0x80000000u);
+    vi off = vaddmin(off0, vclz(x) >> 1, ubk);
+    vb more = (x == 0u) & (off < ubk);
     while (any(more)) {
-      const vu y = load_win(pwin, v + n, more) ^ load_win(twin, off + n, more);
-      const vi n2 = vmin(n + (vclz(y) >> 1), rem);
-      const vb cont = more & (n2 == n + 16) & (n2 < rem);
-      n = vsel(more, n2, n);
-      more = cont;
+      const vu y = load_win_at<-32 * B>(pa, off, more, 0u) ^ load_win_at<0>(ta, off, more, 0x80000000u);
+      off = vaddmin(off, vclz(y) >> 1, ubk);
+      more = more & (y == 0u) & (off < ubk);
     }
-    return vsel(valid, off + n, off);
-  }
-
-  /* ---- after a block was extended: edge / termination bookkeeping -------------------- */
-  WFA_DEV void after_extend(int b, lv::vi off, lv::vi ubk, lv::vi k, lv::vb valid) {
-    using namespace lv;
-    const uint32_t eb = ballot(valid & (off == ubk));
-    if (eb == 0) return;
-    exact = true;                                     /* a cell touches the matrix edge */
+    mn = HI ? put_hi(mn, off) : put_lo(mn, off);
+    /* a cell on the edge of the matrix (null offsets are far below every ub) */
+    const vb edge = off >= ubk;
+    if (!any(edge)) return;
+    const uint32_t eb = ballot(edge);
+    flags |= F_EXACT;
     if (term_d >= 0) return;
     if (endsfree) {                                   /* termination.c:115-162 */
-      const vi vv = off - k;
+      const vi vv = off - (lane + (kbase + 32 * B));
       const vb t = valid & (((off >= tlen) & (vv >= plen - pef)) | ((vv >= plen) & (off >= tlen - tef)));
       const uint32_t tb = ballot(t);
-      if (tb) { term_d = 32 * b + first_set(tb); term_off = lane_value(off, first_set(tb)); }
+      if (tb) { term_d = 32 * B + first_set(tb); term_off = lane_value(off, first_set(tb)); }
     } else {                                          /* termination.c:37-61 */
-      if ((dak >> 5) == b && ((eb >> (dak & 31)) & 1u)) { term_d = dak; term_off = lane_value(off, dak & 31); }
+      if ((dak >> 5) == B && ((eb >> (dak & 31)) & 1u)) { term_d = dak; term_off = lane_value(off, dak & 31); }
+    }
+  }
+
+  /* blocks 2p and 2p + 1 (the halves of packed register p), then the registers after it */
+  template <int p>
+  WFA_DEV void extend_blocks(lv::vu (&Mn)[P], uint32_t bmask) {
+    if constexpr (p < P) {
+      if ((bmask >> (2 * p)) & 3u) {
+        if ((bmask >> (2 * p)) & 1u) extend_block<2 * p>(Mn[p]);
+        if ((bmask >> (2 * p + 1)) & 1u) extend_block<2 * p + 1>(Mn[p]);
+      }
+      extend_blocks<p + 1>(Mn, bmask);
     }
   }
 
   /* first / last window diagonal holding a valid offset of the newest M wavefront */
-  WFA_DEV void scan_valid_range() {
+  WFA_DEV void scan_valid_range(const lv::vu (&Mn)[P]) {
     using namespace lv;
-    cur_lo = 1; cur_hi = -1;
+    cur_lo = 1; cur_hi = 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      const uint32_t b0 = ballot(sx_lo(M[0][p]) >= 0), b1 = ballot(sx_hi(M[0][p]) >= 0);
+      const uint32_t b0 = ballot(sx_lo(Mn[p]) >= 0), b1 = ballot(sx_hi(Mn[p]) >= 0);
       if (b0) { if (cur_lo > cur_hi) cur_lo = 64 * p + first_set(b0); cur_hi = 64 * p + last_set(b0); }
       if (b1) { if (cur_lo > cur_hi) cur_lo = 64 * p + 32 + first_set(b1); cur_hi = 64 * p + 32 + last_set(b1); }
     }
   }
 
-  /* exact trim_ends of an I or D wavefront (compute.c:571-605) */
-  WFA_DEV void trim_component(lv::vu (&X)[P], bool& exists) {
+  /* exact trim_ends of an I or D wavefront (compute.c:571-605); returns whether anything is left */
+  WFA_DEV bool trim_component(lv::vu (&X)[P]) {
     using namespace lv;
     int first = -1, last = -1;
 #pragma unroll
@@ -208,7 +246,6 @@ struct RegAligner {
       if (b0) { if (first < 0) first = 64 * p + first_set(b0); last = 64 * p + last_set(b0); }
       if (b1) { if (first < 0) first = 64 * p + 32 + first_set(b1); last = 64 * p + 32 + last_set(b1); }
     }
-    exists = first >= 0;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const vi dl = lane + 64 * p, dh = lane + (64 * p + 32);
@@ -216,29 +253,51 @@ struct RegAligner {
       const vu mask = vselu(kl, splat(0x0000ffffu), splat(0u)) | vselu(kh, splat(0xffff0000u), splat(0u));
       X[p] = bitsel(mask, X[p], splat(REG_NULL2));
     }
+    return first >= 0;
+  }
+
+  /* reach(s) = s - DOE + 1 diagonals either side of the seeds (0 before the first gap can open); the first
+   * score whose reach is r >= 1 is r + DOE - 1 */
+  WFA_DEV int next_event() const {
+    int e = INT_MAX;
+    if (!(flags & F_EXACT)) {                       /* the range leaves the matrix: clip, and scan from then on */
+      e = imin(e, imin(c_lo - m_lo, m_hi - c_hi) + DOE);
+    }
+    if (m_lo < 0) e = imin(e, c_lo + DOE);          /* ... leaves the window on the left / right: overflow */
+    if (m_hi >= WIN) e = imin(e, WIN - c_hi + DOE - 1);
+    if (FULL) e = imin(e, hrows);                   /* ... or the origin arena */
+    return e;
   }
 
   /* ---- per-pair set-up; score 0 = wavefront_aligner_init_wf_m (wavefront_aligner.c:251-310) -- */
-  WFA_DEV void init(const RegParams& R, lv::seqref pwin_, lv::seqref twin_, int plen_, int tlen_, uint8_t* hist_) {
+  WFA_DEV void init(const RegParams& R, lv::seqref pwin_, lv::seqref twin_, int plen_, int tlen_, const lv::histref& hist_) {
     using namespace lv;
-    pwin = pwin_; twin = twin_; plen = plen_; tlen = tlen_; hist = hist_; hrows = R.hrows;
+    plen = plen_; tlen = tlen_; hist = hist_; hrows = R.hrows;
     endsfree = R.endsfree != 0; pef = R.pef; tef = R.tef;
     lane = lane_id();
     const bool ef = R.endsfree && R.match == 0;
-    lo0 = ef ? -R.pbf : 0; hi0 = ef ? R.tbf : 0;
+    const int lo0 = ef ? -R.pbf : 0, hi0 = ef ? R.tbf : 0;
     kbase = ((lo0 + hi0) >> 1) - WIN / 2;
+    c_lo = lo0 - kbase; c_hi = hi0 - kbase;
+    m_lo = -plen - kbase; m_hi = tlen - kbase;
     dak = tlen - plen - kbase;
     /* so >= max_steps  <=>  s >= ceil(max_steps / g);  so == max_steps  <=>  s == max_steps / g exactly */
     s_limit = R.max_steps / R.g + (R.max_steps % R.g != 0);
     s_limit_exact = (R.max_steps % R.g == 0) ? R.max_steps / R.g : -1;
-    s = 0; cells = 0; term_d = -1; term_off = 0;
-    status = (lo0 < kbase || hi0 >= kbase + WIN) ? 4 : 0;
-    exI = exD = false; exact = false;
+    s = 0; cells = 0; term_d = -1; term_off = 0; wprev = 0;
+    status = (c_lo < 0 || c_hi >= WIN) ? 4 : 0;
+    flags = 0;
+    cur_lo = 1; cur_hi = 0;
+    s_event = next_event();
     selL = vselu(lane == 0, splat(0x5432u), splat(0x7654u));
     selR = vselu(lane == 31, splat(0x5432u), splat(0x3210u));
+    /* pattern position of a cell of block 0 = offset - (kbase + lane); block B is 32 B diagonals further */
+    pa = lane_addr(pwin_, splati(-kbase) - lane);
+    ta = lane_addr(twin_, splati(0));
+    lprev = lane + 31; lnext = lane + 1;
+    keep(lane); keep(lprev); keep(lnext); keep(selL); keep(selR); keep(pa); keep(ta);
 #pragma unroll
     for (int r = 0; r < RM; ++r) {
-      exM[r] = false;
 #pragma unroll
       for (int p = 0; p < P; ++p) M[r][p] = splat(REG_NULL2);
     }
@@ -247,50 +306,66 @@ struct RegAligner {
       I[p] = splat(REG_NULL2); D[p] = splat(REG_NULL2);
       const vi kl = lane + (kbase + 64 * p), kh = kl + 32;
       ub2[p] = pack2(vmax(vmin(splati(tlen), kl + plen), splati(REG_UB_MIN)), vmax(vmin(splati(tlen), kh + plen), splati(REG_UB_MIN)));
+      keep(ub2[p]);
     }
+  }
+
+  /* age the M ring by one score: `Mn` becomes M[0] */
+  WFA_DEV void push(const lv::vu (&Mn)[P], bool exists) {
+#pragma unroll
+    for (int r = RM - 1; r > 0; --r) {
+#pragma unroll
+      for (int p = 0; p < P; ++p) M[r][p] = M[r - 1][p];
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) M[0][p] = Mn[p];
+    flags = (flags & ~F_MRING) | ((flags << 1) & F_MRING) | (exists ? 1u : 0u);
   }
 
   /* ---- one score step: score 0 seeds the wavefront, every later score computes it -------- */
   WFA_DEV bool step(bool seeding) {
     using namespace lv;
     vu Mn[P];
-    int wlo, whi;
+    int dlo, dhi;                                     /* window range the new wavefront can occupy */
     if (seeding) {
-      wlo = lo0; whi = hi0;
+      dlo = c_lo; dhi = c_hi;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        const vi kl = lane + (kbase + 64 * p), kh = kl + 32;
-        Mn[p] = pack2(vsel((kl >= lo0) & (kl <= hi0), vmax(kl, splati(0)), splati(REG_NULL16)),
-                      vsel((kh >= lo0) & (kh <= hi0), vmax(kh, splati(0)), splati(REG_NULL16)));
+        const vi dl = lane + 64 * p, dh = dl + 32;
+        Mn[p] = pack2(vsel((dl >= c_lo) & (dl <= c_hi), vmax(dl + kbase, splati(0)), splati(REG_NULL16)),
+                      vsel((dh >= c_lo) & (dh <= c_hi), vmax(dh + kbase, splati(0)), splati(REG_NULL16)));
       }
     } else {
       /* the previous wavefront did not end the alignment: count it (unialign.c:241-273) */
-      if (exM[0]) cells += cur_hi - cur_lo + 1;
+      cells += wprev;
       ++s;
-      const bool ex_x = exM[DX - 1], ex_o = exM[DOE - 1];
-      if (!(ex_x | ex_o | exI | exD)) {
+      if (!(flags & F_SOURCES)) {
         /* null step (allocate_output_null, compute.c:374-400) */
-        rotate();
+#pragma unroll
+        for (int p = 0; p < P; ++p) Mn[p] = splat(REG_NULL2);
+        push(Mn, false);
+        wprev = 0;
         if (s >= s_limit) { status = 3; return true; }
         return false;
       }
       /* active window: diagonals within reach of the seeds, clipped to the DP matrix */
-      const int reach = s >= DOE ? s - DOE + 1 : 0;
-      wlo = lo0 - reach; whi = hi0 + reach;
-      if (wlo < -plen) { wlo = -plen; exact = true; }
-      if (whi > tlen) { whi = tlen; exact = true; }
-      if (wlo < kbase || whi >= kbase + WIN) { status = 4; return true; }
-      if (FULL) { if (s >= hrows) { status = 4; return true; } }
+      const int reach = imax(s - (DOE - 1), 0);
+      dlo = imax(c_lo - reach, m_lo); dhi = imin(c_hi + reach, m_hi);
+      if (s >= s_event) {
+        if (c_lo - reach < m_lo || c_hi + reach > m_hi) flags |= F_EXACT;
+        if (dlo < 0 || dhi >= WIN) { status = 4; return true; }
+        if (FULL) { if (s >= hrows) { status = 4; return true; } }
+        s_event = next_event();
+      }
 
       /* phase A: per source diagonal max(open, extend), rotated to the consuming lane */
       vu rl[P], rr[P];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        rl[p] = from_prev_lane(vimax2(M[DOE - 1][p], I[p]));
-        rr[p] = from_next_lane(vimax2(M[DOE - 1][p], D[p]));
+        rl[p] = from_lane(vimax2(M[DOE - 1][p], I[p]), lprev);
+        rr[p] = from_lane(vimax2(M[DOE - 1][p], D[p]), lnext);
       }
       /* phase B: the recurrence (compute_affine.c:44-86), 64 diagonals per instruction */
-      uint8_t* const hrow = FULL ? hist + s * WIN : nullptr;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         const vu L = prmt(p > 0 ? rl[p > 0 ? p - 1 : 0] : splat(REG_NULL2), rl[p], selL);
@@ -300,15 +375,16 @@ struct RegAligner {
         const vu mis = vadd2(M[DX - 1][p], splat(REG_ONE2));
         vu m;
         if (FULL) {
-          vb xh, xl, yh, yl, ah, al, bh, bl;
-          (void)vimax2p(I[p], M[DOE - 1][p], xh, xl);    /* I[s][k+1] extends: ext >= open */
-          (void)vimax2p(D[p], M[DOE - 1][p], yh, yl);    /* D[s][k-1] extends */
-          const vu m1 = vimax2p(mis, del, ah, al);       /* mismatch beats deletion on ties */
-          m = vimax2p(m1, ins, bh, bl);                  /* both beat insertion on ties */
-          const vi cl = vsel(bl, vsel(al, splati(1), splati(3)), splati(2)) | vsel(xl, splati(4), splati(0)) | vsel(yl, splati(8), splati(0));
-          const vi ch = vsel(bh, vsel(ah, splati(1), splati(3)), splati(2)) | vsel(xh, splati(4), splati(0)) | vsel(yh, splati(8), splati(0));
-          scatter_u8(hrow, lane + 64 * p, cl, lane >= 0);
-          scatter_u8(hrow, lane + (64 * p + 32), ch, lane >= 0);
+          /* origin code of both cells of the register, from the sign bits of packed differences (all
+           * operands lie within +-16384 + drift, so no difference wraps): bit 0 "deletion beats mismatch"
+           * (mismatch wins ties), bit 1 "insertion beats both" (it loses ties), bit 2 / 3 "I[s][k+1] /
+           * D[s][k-1] is opened, not extended" (ext >= open extends) -- wavefront_backtrace.c:49-59 order */
+          const vu m1 = vimax2(mis, del);
+          m = vimax2(m1, ins);
+          const vu t1 = vsub2(mis, del), t2 = vsub2(m1, ins);
+          const vu t3 = vsub2(I[p], M[DOE - 1][p]), t4 = vsub2(D[p], M[DOE - 1][p]);
+          const vu n = ((t1 >> 15) & 0x00010001u) | ((t2 >> 14) & 0x00020002u) | ((t3 >> 13) & 0x00040004u) | ((t4 >> 12) & 0x00080008u);
+          hist_store<HS>(hist, s * (32 * P) + 32 * p, lane, as_vi((n | (n >> 12)) & 0xffu));
         } else {
           m = vimax3(mis, ins, del);
         }
@@ -316,78 +392,42 @@ struct RegAligner {
         Mn[p] = bitsel(signmask2(vadd2(m, ~ub2[p])), m, splat(REG_NULL2));
         I[p] = ins; D[p] = del;
       }
-      bool exIn = ex_o | exI, exDn = ex_o | exD;
-      if (exact) {
+      const bool ex_o = (flags >> (DOE - 1)) & 1u;
+      bool exIn = ex_o || (flags & F_I), exDn = ex_o || (flags & F_D);
+      if (flags & F_EXACT) {
         /* An I/D offset can only leave the matrix after some offset has touched its edge, and the
-         * first offset to do so is an M offset (M >= I, D on every diagonal), which raised `exact`
-         * in after_extend.  From then on look for such offsets (offset - ub - 1 >= 0, per half);
+         * first offset to do so is an M offset (M >= I, D on every diagonal), which raised F_EXACT
+         * in extend_block.  From then on look for such offsets (offset - ub - 1 >= 0, per half);
          * trim_ends (compute.c:571-605) decides which of them survive. */
         vu over = splat(0x80008000u);
 #pragma unroll
         for (int p = 0; p < P; ++p) over = vimax3(over, vadd2(I[p], ~ub2[p]), vadd2(D[p], ~ub2[p]));
         if (any((over & 0x80008000u) != 0x80008000u)) {
-          trim_component(I, exIn);
-          trim_component(D, exDn);
+          exIn = trim_component(I);
+          exDn = trim_component(D);
         }
       }
-      exI = exIn; exD = exDn;
-      rotate();
+      flags = (flags & ~(F_I | F_D)) | (exIn ? F_I : 0u) | (exDn ? F_D : 0u);
     }
 
     /* phase C: extend the new M offsets (extend.c:90-125 / :263-297), active blocks only */
-    const int blo = (wlo - kbase) >> 5, bhi = (whi - kbase) >> 5;
-    const uint32_t bmask = (2u << bhi) - (1u << blo);
-#pragma unroll
-    for (int p = 0; p < P; ++p) {
-      if (((bmask >> (2 * p)) & 3u) == 0) continue;
-      vi o[2];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        const int b = 2 * p + hh;
-        vi off = hh ? sx_hi(Mn[p]) : sx_lo(Mn[p]);
-        if ((bmask >> b) & 1u) {
-          const vi k = lane + (kbase + 32 * b);
-          const vi ubk = hh ? sx_hi(ub2[p]) : sx_lo(ub2[p]);
-          const vb valid = off >= 0;
-          off = extend_block(off, ubk, k, valid);
-          after_extend(b, off, ubk, k, valid);
-        }
-        o[hh] = off;
-      }
-      Mn[p] = pack2(o[0], o[1]);
+    const uint32_t bmask = (2u << (dhi >> 5)) - (1u << (dlo >> 5));
+    extend_blocks<0>(Mn, bmask);
+    wprev = dhi - dlo + 1;
+    if (flags & F_EXACT) {
+      scan_valid_range(Mn);
+      wprev = cur_hi - cur_lo + 1;                    /* 0 when nothing is valid (cur_lo = cur_hi + 1) */
     }
-#pragma unroll
-    for (int p = 0; p < P; ++p) M[0][p] = Mn[p];
-    if (exact) {
-      scan_valid_range();
-      exM[0] = cur_lo <= cur_hi;
-    } else {
-      /* far from the matrix edges the outermost diagonals are reached by one gap of `reach`
-       * bases and are valid */
-      exM[0] = true; cur_lo = wlo - kbase; cur_hi = whi - kbase;
-    }
+    /* (far from the matrix edges the outermost diagonals are reached by one gap of `reach` bases and are valid) */
+    push(Mn, wprev > 0);
     /* step limit first, then termination (unialign.c:241-273 order); score 0 has no limit check */
     if (!seeding && s >= s_limit) {
       status = 3;
-      if (s == s_limit_exact && exM[0]) cells += cur_hi - cur_lo + 1;
+      if (s == s_limit_exact) cells += wprev;
       return true;
     }
-    if (term_d >= 0) { status = 1; if (exM[0]) cells += cur_hi - cur_lo + 1; return true; }
+    if (term_d >= 0) { status = 1; cells += wprev; return true; }
     return false;
-  }
-
-  /* age the M ring by one score; M[0] becomes null (and is then overwritten by the new wavefront) */
-  WFA_DEV void rotate() {
-    using namespace lv;
-#pragma unroll
-    for (int r = RM - 1; r > 0; --r) {
-      exM[r] = exM[r - 1];
-#pragma unroll
-      for (int p = 0; p < P; ++p) M[r][p] = M[r - 1][p];
-    }
-    exM[0] = false;
-#pragma unroll
-    for (int p = 0; p < P; ++p) M[0][p] = splat(REG_NULL2);
   }
 
   /* Run the alignment.  Returns PAIR_DONE / PAIR_OVERFLOW; end cell in (end_k, end_off). */
@@ -413,7 +453,7 @@ struct RegAligner {
  */
 template <int P, int DX, int DOE, bool FULL>
 WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_t* tw, lv::seqref pwin, lv::seqref twin,
-                           int plen, int tlen, uint8_t* hist, uint8_t* ops, uint32_t* runs_stage, bool is_leader,
+                           int plen, int tlen, const lv::histref& hist, uint8_t* ops, uint32_t* runs_stage, bool is_leader,
                            PairResult& res) {
   RegAligner<P, DX, DOE, FULL> A;
   A.init(R, pwin, twin, plen, tlen, hist);
@@ -432,7 +472,7 @@ WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_
     res.status = ST_COMPLETED;
     if (is_leader) {
       FwdEmitter em; em.init(runs_stage, R.runcap);
-      const int n = backtrace_origin(hist, A.WIN, A.kbase, DX, DOE, 1, A.s, end_k, plen, tlen, pw, tw, ops, R.opcap, em);
+      const int n = backtrace_origin<A.HS>(hist, 32 * P, A.kbase, DX, DOE, 1, A.s, end_k, plen, tlen, pw, tw, ops, R.opcap, em);
       res.nruns = n;
       if (n >= 0) locations_from_runs(runs_stage, imin(n, R.runcap), plen, tlen, res.locs);
     }

@@ -264,8 +264,13 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
       if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs)) continue;
       Tier t;
       t.regs = regs; t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = 64 * regs;
-      t.seq_words_cap = winw; t.group_bytes = 4 * winw; t.smem = (size_t)t.group_bytes * 4;
       t.scap = 32 * regs + k.doe1 + 1;          /* origin rows: scores the window can hold */
+      /* per warp: sequence windows; scope=full with the 128-diagonal window: packed sequences, edit-operation
+       * stack and origin arena as well (wfa_reg.cuh: RegSmem) */
+      const int ropcap = (int)(((long long)B.maxp + B.maxt + 8 + 15) & ~15ll);
+      const RegSmem L = reg_smem_layout(regs, B.full, winw, ropcap, t.scap);
+      if (reg_hist_in_smem(regs, B.full) && 4 * (B.maxp + B.maxt + 2) > L.hist_bytes) continue;   /* run staging must fit in the arena */
+      t.seq_words_cap = winw; t.group_bytes = L.total(); t.smem = (size_t)t.group_bytes * 4;
       B.tiers.push_back(t);
     }
   }
@@ -878,9 +883,17 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
       int* lists[2] = {b->retry_a.as<int>(), b->retry_b.as<int>()};
       const int* cur_list = nb > 1 ? b->blist.as<int>() + bk.list_base : nullptr;
       int last_li = -1;
+      /* Warp-per-pair tiers that need no arena sized from the work count are launched back to back: each
+       * reads its work count (the retries of the tier before it) from device memory, so the host only looks
+       * at the counters at the end of such a chain -- one round trip instead of one per tier.  Everything
+       * else (one CTA or several CTAs per pair, history arenas) is launched tier by tier. */
+      auto chainable = [&](const Tier& t) { return t.mode == 0 && (t.regs > 0 || !b->full); };
+      int first_li = -1;
+      double chain_t0 = 0;
       for (size_t ti = 0; ti < bk.tiers.size() && nwork > 0; ++ti, ++li) {
         if (li >= MAX_LAUNCH) return fail(ctx, WFAGPU_EINVAL, "tier schedule longer than %d launches", MAX_LAUNCH);
         Tier t = bk.tiers[ti];
+        const bool chain_on = chainable(t) && ti + 1 < bk.tiers.size() && chainable(bk.tiers[ti + 1]);   /* the next launch follows without a look */
         KParams k = b->kp;
         k.runcap = (int)std::min<long long>((long long)bk.maxp + bk.maxt + 2, INT_MAX / 2);
         long long groups;
@@ -916,14 +929,16 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         k.hcap = t.hcap; k.scap = t.scap;
         if (t.regs) {
           if (b->full) {
-            k.rhrows = t.scap; k.rhist_bytes = (long long)t.scap * 64 * t.regs;
+            k.rhrows = t.scap; k.rhist_bytes = (long long)t.scap * 32 * t.regs;      /* one byte per lane and packed register */
             k.ropcap = (int)(((long long)bk.maxp + bk.maxt + 8 + 15) & ~15ll);
-            CK(ctx->rhist.ensure((size_t)k.rhist_bytes * (size_t)groups));
-            CK(ctx->rops.ensure((size_t)k.ropcap * (size_t)groups));
-            CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
-            k.rhist = ctx->rhist.as<uint8_t>(); k.rops = ctx->rops.as<uint8_t>();
-            k.runs_stage = ctx->runs_stage.as<uint32_t>();
-            b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)k.rhist_bytes * groups);
+            if (!reg_hist_in_smem(t.regs, true)) {
+              CK(ctx->rhist.ensure((size_t)k.rhist_bytes * (size_t)groups));
+              CK(ctx->rops.ensure((size_t)k.ropcap * (size_t)groups));
+              CK(ctx->runs_stage.ensure(4ull * (size_t)k.runcap * (size_t)groups));
+              k.rhist = ctx->rhist.as<uint8_t>(); k.rops = ctx->rops.as<uint8_t>();
+              k.runs_stage = ctx->runs_stage.as<uint32_t>();
+              b->stats.history_bytes = std::max<int64_t>(b->stats.history_bytes, (int64_t)k.rhist_bytes * groups);
+            }
           }
         } else if (t.mode == 2) {
           const int ns = k.rm + 2 * k.r1 + (b->two_p ? 2 * k.r2 : 0);
@@ -956,7 +971,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         k.skip_groups = (ti + 1 < bk.tiers.size() && !ctx->knobs.no_tier_skip) ? (int)std::min<long long>(groups, INT_MAX / 2) : 0;   /* never on the last tier */
         k.retry_count = &dc->retry[li];
         k.done_count = &dc->done[li]; k.ovf_count = &dc->ovf[li];
-        const double tier_t0 = trace ? now_ms() : 0;
+        if (first_li < 0) { first_li = li; chain_t0 = trace ? now_ms() : 0; }
         if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
         else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
         else if (t.mode == 2) {
@@ -965,12 +980,20 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         }
         else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
         b->stats.kernel_launches++;
+        if (trace)
+          fprintf(stderr, "[wfagpu]   bucket %d (<= %d bp) tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d)%s\n",
+                  q, bk.max_len, ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
+                  chain_on ? " +" : "");
+        cur_list = lists[li & 1];
+        last_li = li;
+        if (chain_on) continue;           /* nwork stays the bound of what the next tier can receive */
         CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (trace)
-          fprintf(stderr, "[wfagpu]   bucket %d (<= %d bp) tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d): %lld pairs in, %d overflowed, %.2f ms\n",
-                  q, bk.max_len, ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
-                  nwork, hc->retry[li], now_ms() - tier_t0);
+        if (trace) {
+          fprintf(stderr, "[wfagpu]     %lld pairs in ->", nwork);
+          for (int x = first_li; x <= li; ++x) fprintf(stderr, " %d", hc->retry[x]);
+          fprintf(stderr, " overflowed, %.2f ms\n", now_ms() - chain_t0);
+        }
         if (trace && hc->dbg[0])
           fprintf(stderr, "[wfagpu]     cycles per warp-step: overhead %.0f, blocks %.0f, planner %.0f, barrier wait %.0f, after-barrier %.0f (warp-steps %llu)\n",
                   (double)hc->dbg[1] / hc->dbg[0], (double)hc->dbg[2] / hc->dbg[0], (double)hc->dbg[3] / hc->dbg[0],
@@ -979,9 +1002,8 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
           fprintf(stderr, "[wfagpu]     scanned-range mode entered through: matrix edge %llu, cut-off end cell M %llu I1 %llu D1 %llu I2 %llu D2 %llu\n",
                   hc->dbg[8], hc->dbg[9], hc->dbg[10], hc->dbg[11], hc->dbg[12], hc->dbg[13]);
         nwork = hc->retry[li];
-        if (ti == 0) b->stats.retried_pairs += nwork;
-        cur_list = lists[li & 1];
-        last_li = li;
+        if (first_li == li - (int)ti) b->stats.retried_pairs += hc->retry[first_li];     /* the chain held the bucket's first tier */
+        first_li = -1;
       }
       if (nwork > 0) {
         /* capacity exhausted even on the widest tier: WF_STATUS_OOM (W/wavefront/wfa.h:50) */
@@ -1178,23 +1200,29 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   CK(ctx->pin_pack[1].ensure(sizeof(PackCounters)));
   if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->user_runs ? ctx->user_runs : ctx->pin_runs.as<uint32_t>(); }
   const double t_start = now_ms();
-  /* chunking: enough chunks to overlap staging and downloads with the kernels, big enough to fill
-   * the GPU; the first chunk is small so that the GPU starts early (its upload is the only one
-   * nothing overlaps) */
+  /* chunking: a few chunks, so that staging and downloads overlap the kernels while the fixed cost of a
+   * chunk (launches, one host round trip, the tail of its persistent kernels) stays small: the first one
+   * is a sixteenth of the batch (its upload is the only one nothing overlaps), then doubling up to a third;
+   * chunks are also bounded by bytes (two shells of raw bases live in HBM) */
   std::vector<int64_t> starts;           /* chunk c covers pairs [starts[c], starts[c+1]) */
   {
     const int64_t want = ctx->knobs.chunk;
-    int64_t chunk = n;
-    if (want > 0) chunk = want;
-    else if (n >= 262144) chunk = std::max<int64_t>(131072, (n + 7) / 8);
-    int64_t first = chunk;
-    if (want <= 0 && n >= 262144) first = std::min<int64_t>(chunk, std::max<int64_t>(32768, n / 40));
+    int64_t chunk = n, first = n;
+    if (want > 0) chunk = first = want;
+    else if (n >= 262144) {
+      double mean = 0;
+      const int64_t probe = std::min<int64_t>(n, 1024);
+      for (int64_t i = 0; i < probe; ++i) mean += (double)std::max(p_len[i], 0) + (double)std::max(t_len[i], 0);
+      mean = std::max(mean / (double)probe, 1.0);
+      const int64_t by_bytes = std::max<int64_t>(65536, (int64_t)(2.0e9 / mean));
+      chunk = std::min(by_bytes, std::max<int64_t>(131072, (n + 2) / 3));
+      first = std::min(chunk, std::max<int64_t>(32768, n / 16));
+    }
     starts.push_back(0);
-    /* ramp up by 1.5x per chunk: staging chunk c+1 must not take longer than the GPU needs for chunk c */
     int64_t cur = first;
     for (int64_t off = std::min(first, n); off < n;) {
       starts.push_back(off);
-      cur = std::min<int64_t>(chunk, cur + cur / 2);
+      cur = std::min<int64_t>(chunk, 2 * cur);
       off += cur;
     }
     starts.push_back(n);

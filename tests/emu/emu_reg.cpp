@@ -24,8 +24,9 @@ static int run_pair(bool full, const RegParams& R, const uint32_t* pw, const uin
   std::vector<uint32_t> pwin((size_t)plen + 1), twin((size_t)tlen + 1);
   build_windows(pw, plen, pwin.data());
   build_windows(tw, tlen, twin.data());
-  if (full) return align_pair_reg<P, DX, DOE, true>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, hist, ops, stage, true, res);
-  return align_pair_reg<P, DX, DOE, false>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, hist, ops, stage, true, res);
+  const lv::histref h = lv::make_histref(hist, false);
+  if (full) return align_pair_reg<P, DX, DOE, true>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res);
+  return align_pair_reg<P, DX, DOE, false>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res);
 }
 
 /* regs = packed registers per wavefront (window = 64 * regs diagonals); hrows = origin rows */

@@ -60,6 +60,13 @@ inline vu vadd2(const vu& a, const vu& b) {     /* wraps per half, like VIADD.16
                             (int16_t)(uint16_t)((uint16_t)(a.v[l] >> 16) + (uint16_t)(b.v[l] >> 16)));
   return r;
 }
+inline vu vsub2(const vu& a, const vu& b) {     /* wraps per half */
+  vu r; LV_FOR r.v[l] = mk2((int16_t)(uint16_t)((uint16_t)a.v[l] - (uint16_t)b.v[l]),
+                            (int16_t)(uint16_t)((uint16_t)(a.v[l] >> 16) - (uint16_t)(b.v[l] >> 16)));
+  return r;
+}
+inline vu operator>>(const vu& a, int b) { vu r; LV_FOR r.v[l] = a.v[l] >> b; return r; }
+inline vi as_vi(const vu& a) { vi r; LV_FOR r.v[l] = (int32_t)a.v[l]; return r; }
 inline vu vimax2p(const vu& a, const vu& b, vb& hi, vb& lo) {   /* predicates: a >= b */
   hi.m = lo.m = 0;
   LV_FOR {
@@ -85,10 +92,13 @@ inline vu bitsel(const vu& mask, const vu& a, const vu& b) { vu r; LV_FOR r.v[l]
 inline vi sx_lo(const vu& a) { vi r; LV_FOR r.v[l] = lo16(a.v[l]); return r; }
 inline vi sx_hi(const vu& a) { vi r; LV_FOR r.v[l] = hi16(a.v[l]); return r; }
 inline vu pack2(const vi& lo, const vi& hi) { vu r; LV_FOR r.v[l] = mk2(lo.v[l], hi.v[l]); return r; }
+inline vu put_lo(const vu& a, const vi& v) { vu r; LV_FOR r.v[l] = byte_perm(a.v[l], (uint32_t)v.v[l], 0x3254); return r; }
+inline vu put_hi(const vu& a, const vi& v) { vu r; LV_FOR r.v[l] = byte_perm(a.v[l], (uint32_t)v.v[l], 0x5410); return r; }
 
 /* lane exchange */
 inline vu from_prev_lane(const vu& a) { vu r; LV_FOR r.v[l] = a.v[(l + 31) & 31]; return r; }
 inline vu from_next_lane(const vu& a) { vu r; LV_FOR r.v[l] = a.v[(l + 1) & 31]; return r; }
+inline vu from_lane(const vu& a, const vi& src) { vu r; LV_FOR r.v[l] = a.v[src.v[l] & 31]; return r; }
 inline int lane_value(const vi& a, int lane) { return a.v[lane & 31]; }
 inline uint32_t ballot(const vb& p) { return p.m; }
 inline bool any(const vb& p) { return p.m != 0; }
@@ -112,9 +122,22 @@ inline vu vbrev(const vu& x) {
 typedef const uint32_t* seqref;
 inline seqref make_seqref(const uint32_t* p) { return p; }
 inline vu load_win(seqref base, const vi& idx, const vb& p) { vu r; LV_FOR r.v[l] = (p.m >> l & 1) ? base[idx.v[l]] : 0u; return r; }
+struct lanead { const uint32_t* base; vi idx0; };
+inline lanead lane_addr(seqref base, const vi& idx0) { return lanead{base, idx0}; }
+template <int IMM>
+inline vu load_win_at(const lanead& a, const vi& idx, const vb& p, uint32_t dflt) {
+  vu r; LV_FOR r.v[l] = (p.m >> l & 1) ? a.base[a.idx0.v[l] + idx.v[l] + IMM] : dflt; return r;
+}
+inline vi vaddmin(const vi& a, const vi& b, const vi& c) { vi r; LV_FOR { const int t = a.v[l] + b.v[l]; r.v[l] = t < c.v[l] ? t : c.v[l]; } return r; }
+inline vb operator==(const vu& a, uint32_t b) { vb r{0}; LV_FOR if (a.v[l] == b) r.m |= 1u << l; return r; }
+template <class T> inline void keep(T&) {}
 inline void scatter_u32(uint32_t* base, const vi& idx, const vu& val, const vb& p) { LV_FOR if (p.m >> l & 1) base[idx.v[l]] = val.v[l]; }
 inline vu gather_u32(const uint32_t* base, const vi& idx, const vb& p) { vu r; LV_FOR r.v[l] = (p.m >> l & 1) ? base[idx.v[l]] : 0u; return r; }
 inline void scatter_u8(uint8_t* base, const vi& idx, const vi& val, const vb& p) { LV_FOR if (p.m >> l & 1) base[idx.v[l]] = (uint8_t)val.v[l]; }
+struct histref { uint8_t* p; };
+inline histref make_histref(uint8_t* p, bool) { return histref{p}; }
+template <bool SH> inline void hist_store(const histref& h, int off, const vi& idx, const vi& val) { LV_FOR h.p[off + idx.v[l]] = (uint8_t)val.v[l]; }
+template <bool SH> inline int hist_load(const histref& h, int off) { return h.p[off]; }
 #undef LV_FOR
 
 }  // namespace lv

@@ -156,8 +156,6 @@ def test_mixed_length_batch_is_bucketed(gpu_ctx, oracle, monkeypatch):
         monkeypatch.delenv("WFAGPU_NO_BUCKETS")
         assert_same(got1, want, scope_full=kw.get("scope", "full") == "full", what=f"one bucket {kw}")
         assert st["cells"] == st1["cells"]
-        if "heuristic" not in kw:
-            assert st["retried_pairs"] < st1["retried_pairs"], "bucketing must keep short reads off the long-read plan"
         monkeypatch.setenv("WFAGPU_CHUNK", "3000")
         got2 = gpu_ctx.align_batch(cfg, *batch)
         monkeypatch.delenv("WFAGPU_CHUNK")
