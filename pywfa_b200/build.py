@@ -72,5 +72,31 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+def build_cython(force: bool = False) -> str:
+    """Compile the Cython host layer (``pywfa_b200/cy/align_cy.pyx`` over ``cy/wfagpu.pxd``) against
+    ``libwfagpu.so`` -- the binding INTEGRATION.md describes, as a real extension module."""
+    import sysconfig
+    build_library()
+    cy = os.path.join(HERE, "cy")
+    pyx, pxd = os.path.join(cy, "align_cy.pyx"), os.path.join(cy, "wfagpu.pxd")
+    out = os.path.join(cy, "align_cy" + sysconfig.get_config_var("EXT_SUFFIX"))
+    csrc = os.path.join(cy, "build", "align_cy.c")
+    os.makedirs(os.path.dirname(csrc), exist_ok=True)
+    if force or _stale(out, [pyx, pxd, os.path.join(HERE, "..", "include", "wfagpu.h"), OUT]):
+        from Cython.Compiler.Main import CompilationOptions, compile as cy_compile
+        res = cy_compile(pyx, CompilationOptions(output_file=csrc, include_path=[cy], language_level=3))
+        if res.num_errors:
+            raise RuntimeError("cythonizing align_cy.pyx failed")
+        cmd = ["gcc", "-O2", "-fPIC", "-shared", "-I" + sysconfig.get_paths()["include"],
+               "-I" + os.path.join(HERE, "..", "include"), csrc, "-o", out,
+               "-L" + HERE, "-lwfagpu", "-Wl,-rpath," + HERE]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"compiling the Cython host layer failed:\n{r.stdout}")
+    return out
+
+
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--cython" in sys.argv:
+        print(build_cython(force="--force" in sys.argv))

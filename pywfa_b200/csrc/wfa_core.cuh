@@ -129,7 +129,20 @@ struct KParams {
   /* register-resident tier (wfa_reg.cuh): per-warp origin-byte arena and edit-operation stack */
   uint8_t* rhist; long long rhist_bytes; int rhrows;
   uint8_t* rops; int ropcap;
+  int reg_kbase, reg_clo, reg_chi;   /* window of the launch: diagonal of column 0, columns of the score-0 seeds (reg_window) */
 };
+
+/* The register tier's window of 64 * regs diagonals is centred on the score-0 seeds [lo0, hi0]
+ * (wavefront_aligner.c:251-310): a constant of the launch, computed once on the host. */
+struct RegWindow { int kbase, c_lo, c_hi; };
+WFA_DEV RegWindow reg_window(int regs, int endsfree, int match, int pbf, int tbf) {
+  const bool ef = endsfree && match == 0;
+  const int lo0 = ef ? -pbf : 0, hi0 = ef ? tbf : 0;
+  RegWindow w;
+  w.kbase = ((lo0 + hi0) >> 1) - 32 * regs;
+  w.c_lo = lo0 - w.kbase; w.c_hi = hi0 - w.kbase;
+  return w;
+}
 
 /* pointers a group works with for the current pair */
 template <class OffT>

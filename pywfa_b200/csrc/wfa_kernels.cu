@@ -397,6 +397,7 @@ __global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const _
   R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = K.rhrows; R.opcap = K.ropcap; R.runcap = K.runcap;
+  R.kbase = K.reg_kbase; R.c_lo = K.reg_clo; R.c_hi = K.reg_chi;
   uint8_t* const hist_p = !FULL ? nullptr : HS ? wbase + L.hist_off() : K.rhist + (long long)warp_id * K.rhist_bytes;
   const lv::histref hist = lv::make_histref(hist_p, HS);
   uint8_t* const ops = !FULL ? nullptr : HS ? wbase + L.ops_off() : K.rops + (long long)warp_id * K.ropcap;

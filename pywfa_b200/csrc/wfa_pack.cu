@@ -56,10 +56,14 @@ __global__ void layout_count_kernel(const int32_t* __restrict__ p_len, const int
   }
 }
 
-/* single block: exclusive scan of the tile sums in place; total -> tile_sums[ntiles] */
-__global__ void layout_scan_kernel(long long* tile_sums, int ntiles) {
+/* single block: exclusive scan of the tile sums in place; total -> tile_sums[ntiles].  Also clears the
+ * packer's counters and the pad word behind the packed sequences (no memset in the copy stream: a
+ * memset is a kernel, and kernels queue behind the persistent alignment kernel of the chunk before) */
+__global__ void layout_scan_kernel(long long* tile_sums, int ntiles, uint32_t* zero_a, int n_zero_a, uint32_t* zero_b) {
   __shared__ long long carry;
   __shared__ long long wtot[32];
+  if ((int)threadIdx.x < n_zero_a) zero_a[threadIdx.x] = 0;
+  if (threadIdx.x == 0 && zero_b) *zero_b = 0;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (int b = 0; b < ntiles; b += blockDim.x) {
@@ -241,11 +245,12 @@ __global__ void __launch_bounds__(256) pack_bytes_kernel(PackArgs A, bool side) 
 int layout_tiles(long long n) { return (int)((n + LAY_TILE - 1) / LAY_TILE); }
 
 cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long n, int bases_per_word,
-                          long long* tile_sums, PairMeta* pairs, const BucketArgs& B, cudaStream_t st) {
-  if (n <= 0) return cudaSuccess;
+                          long long* tile_sums, PairMeta* pairs, const BucketArgs& B, uint32_t* zero_a, int n_zero_a,
+                          uint32_t* zero_b, cudaStream_t st) {
   const int tiles = layout_tiles(n);
-  layout_count_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums);
-  layout_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tiles);
+  if (n > 0) layout_count_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums);
+  layout_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tiles, zero_a, n_zero_a, zero_b);
+  if (n <= 0) return cudaGetLastError();
   layout_apply_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums, pairs, B);
   return cudaGetLastError();
 }

@@ -62,6 +62,7 @@ constexpr uint32_t REG_ONE2 = 0x00010001u;
 struct RegParams {
   int match, g, max_steps;
   int endsfree, pbf, pef, tbf, tef;
+  int kbase, c_lo, c_hi;   /* reg_window() of the launch */
   int hrows;          /* scope=full: rows of the origin arena (scores 0..hrows-1) */
   int opcap;          /* edit-operation stack bytes */
   int runcap;         /* CIGAR run staging words */
@@ -275,10 +276,7 @@ struct RegAligner {
     plen = plen_; tlen = tlen_; hist = hist_; hrows = R.hrows;
     endsfree = R.endsfree != 0; pef = R.pef; tef = R.tef;
     lane = lane_id();
-    const bool ef = R.endsfree && R.match == 0;
-    const int lo0 = ef ? -R.pbf : 0, hi0 = ef ? R.tbf : 0;
-    kbase = ((lo0 + hi0) >> 1) - WIN / 2;
-    c_lo = lo0 - kbase; c_hi = hi0 - kbase;
+    kbase = R.kbase; c_lo = R.c_lo; c_hi = R.c_hi;
     m_lo = -plen - kbase; m_hi = tlen - kbase;
     dak = tlen - plen - kbase;
     /* so >= max_steps  <=>  s >= ceil(max_steps / g);  so == max_steps  <=>  s == max_steps / g exactly */

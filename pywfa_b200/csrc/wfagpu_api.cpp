@@ -127,15 +127,22 @@ struct Bucket {
 
 }  // namespace
 
+/* chunks of one call in flight: staging (uploads + packing) runs up to kShells - 1 chunks ahead of the
+ * alignment kernels, so the copy engine never waits for a kernel to finish */
+constexpr int kShells = 4;
+
 struct wfagpu_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   /* uploads of the next chunk overlap the kernels of this one */
-  cudaEvent_t uploaded[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;   /* uploads of the next chunks overlap the kernels of this one */
+  cudaStream_t pack_stream = nullptr;   /* layout + packing kernels of a chunk, behind its upload; not in the copy stream:
+                                           they wait for SM room while the next upload must go on */
+  cudaEvent_t copied[4] = {nullptr, nullptr, nullptr, nullptr};   /* the raw bytes of the chunk in slot c % kShells are in HBM */
+  cudaEvent_t uploaded[kShells] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t d2h_stream = nullptr;    /* result downloads of chunk c overlap the kernels of chunk c+1 */
-  cudaEvent_t d2h_done[2] = {nullptr, nullptr};
+  cudaEvent_t d2h_done[kShells] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t run_done = nullptr;       /* all kernels of a chunk (incl. CIGAR ordering) finished */
-  PinBuf out_stage[2];                  /* pinned landing zone of one chunk's result arrays */
+  PinBuf out_stage[kShells];            /* pinned landing zone of one chunk's result arrays */
   int sms = 0;
   int smem_optin = 0;
   std::string err;
@@ -146,7 +153,7 @@ struct wfagpu_ctx {
   PinBuf gather_seq, gather_off;        /* scattered input gathered back to back (and the offsets it has there) */
   cudaEvent_t gather_done = nullptr;
   bool gather_busy = false;
-  PinBuf pin_pack[2];                   /* PackCounters of the chunk staged in slot c & 1 */
+  PinBuf pin_pack[kShells];             /* PackCounters of the chunk staged in slot c % kShells */
   PinBuf pin_runs, pin_small;
   uint32_t* user_runs = nullptr;        /* caller-provided destination of the CIGAR runs (wfagpu_set_run_buffer) */
   size_t user_runs_cap = 0;             /* ... and its capacity in words */
@@ -501,16 +508,20 @@ extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t err
    * slots that the persistent alignment kernel of chunk c frees in its tail */
   if ((e = cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
       (e = cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaStreamCreateWithPriority(&ctx->d2h_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->uploaded[0], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->uploaded[1], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->d2h_done[0], cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->d2h_done[1], cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->run_done, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->gather_done, cudaEventDisableTiming)) != cudaSuccess) {
     set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
     return bail(WFAGPU_ECUDA);
   }
+  for (int i = 0; i < kShells; ++i)
+    if ((e = cudaEventCreateWithFlags(&ctx->copied[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->uploaded[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->d2h_done[i], cudaEventDisableTiming)) != cudaSuccess) {
+      set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
+      return bail(WFAGPU_ECUDA);
+    }
   for (int i = 0; i < StageRing::kSlots; ++i)
     if ((e = cudaEventCreateWithFlags(&ctx->ring.ev[i], cudaEventDisableTiming)) != cudaSuccess) {
       set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
@@ -532,17 +543,21 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   cudaDeviceSynchronize();
   for (auto& pb : ctx->ring.buf) pb.release();
   ctx->gather_seq.release(); ctx->gather_off.release();
-  ctx->pin_pack[0].release(); ctx->pin_pack[1].release();
+  for (auto& pb : ctx->pin_pack) pb.release();
   ctx->pin_runs.release(); ctx->pin_small.release();
   for (wfagpu_batch* b : ctx->spare) batch_release(b);
   ctx->spare.clear();
   ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
   ctx->rhist.release(); ctx->rops.release(); ctx->gscratch.release();
-  for (cudaStream_t s : {ctx->stream, ctx->copy_stream, ctx->d2h_stream}) if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t ev : {ctx->uploaded[0], ctx->uploaded[1], ctx->d2h_done[0], ctx->d2h_done[1], ctx->run_done, ctx->gather_done,
-                         ctx->ring.ev[0], ctx->ring.ev[1], ctx->ring.ev[2]})
+  for (cudaStream_t s : {ctx->stream, ctx->copy_stream, ctx->pack_stream, ctx->d2h_stream}) if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t ev : {ctx->run_done, ctx->gather_done, ctx->ring.ev[0], ctx->ring.ev[1], ctx->ring.ev[2]})
     if (ev) cudaEventDestroy(ev);
-  ctx->out_stage[0].release(); ctx->out_stage[1].release();
+  for (int i = 0; i < kShells; ++i) {
+    if (ctx->uploaded[i]) cudaEventDestroy(ctx->uploaded[i]);
+    if (ctx->copied[i]) cudaEventDestroy(ctx->copied[i]);
+    if (ctx->d2h_done[i]) cudaEventDestroy(ctx->d2h_done[i]);
+    ctx->out_stage[i].release();
+  }
   cudaGetLastError();
   delete ctx;
 }
@@ -636,7 +651,7 @@ wfagpu_batch* batch_acquire(wfagpu_ctx* ctx) {
   return b;
 }
 void batch_recycle(wfagpu_ctx* ctx, wfagpu_batch* b) {
-  if (ctx && ctx->spare.size() < 4) ctx->spare.push_back(b);
+  if (ctx && ctx->spare.size() < kShells + 1) ctx->spare.push_back(b);
   else batch_release(b);
 }
 
@@ -686,7 +701,7 @@ int classify_inputs(wfagpu_ctx* ctx, Inputs& in) {
  * synchronisation: batch_finish_stage completes the batch once the stream got there.
  */
 int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, const Inputs& in, int64_t first, int64_t n,
-                cudaStream_t st, PackCounters* counts) {
+                cudaStream_t st, cudaStream_t pk, cudaEvent_t copied, PackCounters* counts) {
   b->cfg = *cfg; b->n = n;
   b->two_p = cfg->distance == WFAGPU_DISTANCE_AFFINE2P;
   b->full = cfg->scope == WFAGPU_SCOPE_FULL;
@@ -748,8 +763,6 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
   int64_t* d_poff = b->offs.as<int64_t>(); int64_t* d_toff = d_poff + n1;
   int32_t* d_plen = b->lens.as<int32_t>(); int32_t* d_tlen = d_plen + n1;
   int64_t h2d = 0;
-  CK(cudaMemsetAsync(b->pcount.p, 0, sizeof(PackCounters) + 4 * MAX_BUCKETS, st));
-  CK(cudaMemsetAsync(b->words.as<uint32_t>() + b->total_words, 0, 4, st));
   if (n) {
     int rc = upload(ctx, d_plen, p_len, 4 * (size_t)n, in.k_plen, st);
     if (rc == WFAGPU_OK) rc = upload(ctx, d_tlen, t_len, 4 * (size_t)n, in.k_tlen, st);
@@ -799,10 +812,15 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
   for (int q = 0; q < nb; ++q) { B.max_len[q] = b->buckets[q].max_len; B.list_base[q] = b->buckets[q].list_base; }
   B.cursor = reinterpret_cast<int*>(b->pcount.as<unsigned char>() + sizeof(PackCounters));
   B.list = b->blist.as<int>();
-  CK(launch_layout(d_plen, d_tlen, n, bpw, b->lay.as<long long>(), A.pairs, B, st));
-  CK(launch_pack(A, b->byte_mode, std::max(b->maxp, b->maxt), ctx->sms, st));
-  CK(cudaMemcpyAsync(counts, b->pcount.p, sizeof(PackCounters), cudaMemcpyDeviceToHost, st));
-  b->stats.kernel_launches = n ? 4 : 0;
+  if (pk != st) {                      /* the kernels run behind the copies, in a stream of their own */
+    CK(cudaEventRecord(copied, st));
+    CK(cudaStreamWaitEvent(pk, copied, 0));
+  }
+  CK(launch_layout(d_plen, d_tlen, n, bpw, b->lay.as<long long>(), A.pairs, B, b->pcount.as<uint32_t>(),
+                   (int)((sizeof(PackCounters) + 4 * MAX_BUCKETS) / 4), b->words.as<uint32_t>() + b->total_words, pk));
+  CK(launch_pack(A, b->byte_mode, std::max(b->maxp, b->maxt), ctx->sms, pk));
+  CK(cudaMemcpyAsync(counts, b->pcount.p, sizeof(PackCounters), cudaMemcpyDeviceToHost, pk));
+  b->stats.kernel_launches = n ? 4 : 1;
   b->stats.packed_bytes = 4 * b->total_words;
   b->stats.h2d_bytes = h2d;
   return WFAGPU_OK;
@@ -928,6 +946,8 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         k.wcap = t.wcap; k.seq_words_cap = t.seq_words_cap; k.group_bytes = t.group_bytes; k.vec_seqw = t.vec_seqw ? 1 : 0;
         k.hcap = t.hcap; k.scap = t.scap;
         if (t.regs) {
+          const RegWindow rw = reg_window(t.regs, k.endsfree, k.match, k.pbf, k.tbf);
+          k.reg_kbase = rw.kbase; k.reg_clo = rw.c_lo; k.reg_chi = rw.c_hi;
           if (b->full) {
             k.rhrows = t.scap; k.rhist_bytes = (long long)t.scap * 32 * t.regs;      /* one byte per lane and packed register */
             k.ropcap = (int)(((long long)bk.maxp + bk.maxt + 8 + 15) & ~15ll);
@@ -1093,6 +1113,7 @@ int check_args(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const uint8_t* seq, 
 /* after a failed call: nothing of it may still be in flight when its buffers are reused */
 void quiesce(wfagpu_ctx* ctx) {
   cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->pack_stream);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamSynchronize(ctx->d2h_stream);
   cudaGetLastError();
@@ -1128,7 +1149,7 @@ extern "C" int wfagpu_batch_prepare(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
   CK(ctx->pin_pack[0].ensure(sizeof(PackCounters)));
   wfagpu_batch* b = batch_acquire(ctx);
   const double t0 = now_ms();
-  rc = batch_stage(ctx, b, cfg, in, 0, n, ctx->stream, ctx->pin_pack[0].as<PackCounters>());
+  rc = batch_stage(ctx, b, cfg, in, 0, n, ctx->stream, ctx->stream, nullptr, ctx->pin_pack[0].as<PackCounters>());
   if (rc == WFAGPU_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, WFAGPU_ECUDA, "staging failed: %s", cudaGetErrorString(cudaGetLastError()));
   const double t1 = now_ms();
   if (rc == WFAGPU_OK) rc = batch_finish_stage(ctx, b, ctx->pin_pack[0].as<PackCounters>(), ctx->stream);
@@ -1196,8 +1217,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   const bool dma_score = mem_kind(ctx, score) == MEM_DMA, dma_status = mem_kind(ctx, status) == MEM_DMA;
   const bool dma_locs = mem_kind(ctx, locs) == MEM_DMA, dma_cig = mem_kind(ctx, cig_off) == MEM_DMA;
   CK(ctx->pin_small.ensure(sizeof(DevCounters) + 64));
-  CK(ctx->pin_pack[0].ensure(sizeof(PackCounters)));
-  CK(ctx->pin_pack[1].ensure(sizeof(PackCounters)));
+  for (auto& pb : ctx->pin_pack) CK(pb.ensure(sizeof(PackCounters)));
   if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->user_runs ? ctx->user_runs : ctx->pin_runs.as<uint32_t>(); }
   const double t_start = now_ms();
   /* chunking: a few chunks, so that staging and downloads overlap the kernels while the fixed cost of a
@@ -1229,7 +1249,8 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     if (n == 0) starts.assign({0, 0});
   }
   const int64_t nchunks = (int64_t)starts.size() - 1;
-  wfagpu_batch* shells[2] = {batch_acquire(ctx), nchunks > 1 ? batch_acquire(ctx) : nullptr};
+  wfagpu_batch* shells[kShells];
+  for (int i = 0; i < kShells; ++i) shells[i] = i < nchunks ? batch_acquire(ctx) : nullptr;
   std::mutex mu;
   std::condition_variable cv;
   int64_t staged = 0, consumed = 0;     /* chunks staged by the caller thread / finished by the GPU thread */
@@ -1239,15 +1260,15 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   double gpu_busy = 0, t_run = 0, t_down = 0;
 
   auto stage_side = [&](int64_t c) -> int {     /* runs on the calling thread */
-    const int r = batch_stage(ctx, shells[c & 1], cfg, in, starts[c], starts[c + 1] - starts[c], ctx->copy_stream,
-                              ctx->pin_pack[c & 1].as<PackCounters>());
+    const int r = batch_stage(ctx, shells[c % kShells], cfg, in, starts[c], starts[c + 1] - starts[c], ctx->copy_stream,
+                              ctx->pack_stream, ctx->copied[c % kShells], ctx->pin_pack[c % kShells].as<PackCounters>());
     if (r != WFAGPU_OK) return r;
-    CK(cudaEventRecord(ctx->uploaded[c & 1], ctx->copy_stream));
+    CK(cudaEventRecord(ctx->uploaded[c % kShells], ctx->pack_stream));
     return WFAGPU_OK;
   };
   auto finish_stage = [&](int64_t c) -> int {   /* GPU thread: the packer's verdict is in, plan the chunk */
-    CK(cudaEventSynchronize(ctx->uploaded[c & 1]));
-    return batch_finish_stage(ctx, shells[c & 1], ctx->pin_pack[c & 1].as<PackCounters>(), ctx->stream);
+    CK(cudaEventSynchronize(ctx->uploaded[c % kShells]));
+    return batch_finish_stage(ctx, shells[c % kShells], ctx->pin_pack[c % kShells].as<PackCounters>(), ctx->stream);
   };
 
   if (nchunks == 1) {
@@ -1275,28 +1296,33 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     if (trace) fprintf(stderr, "[wfagpu] n=%lld single chunk: stage %.2f ms, gpu side %.2f ms\n", (long long)n, t1 - t_start, now_ms() - t1);
   } else {
     struct Drain { int64_t off, m; bool last; long long run_base; bool full; };
-    Drain drains[2];
+    Drain drains[kShells];
     int64_t queued = 0, drained = 0;     /* chunks whose download was queued / handed to the caller */
     auto out_bytes = [&](int64_t m, bool full) { return (size_t)(full ? 8 * (m + 1) + 24 * m : 8 * m) + 64; };
     auto gpu_side_async = [&](int64_t c) -> int {
-      wfagpu_batch* b = shells[c & 1];
+      wfagpu_batch* b = shells[c % kShells];
       const int64_t off = starts[c];
       const double g0 = now_ms();
-      int r = finish_stage(c);
+      CK(cudaEventSynchronize(ctx->uploaded[c % kShells]));
+      const double g0a = now_ms();
+      int r = batch_finish_stage(ctx, shells[c % kShells], ctx->pin_pack[c % kShells].as<PackCounters>(), ctx->stream);
       if (r != WFAGPU_OK) return r;
-      CK(cudaStreamWaitEvent(ctx->stream, ctx->d2h_done[c & 1], 0));   /* chunk c-2 left this shell's result buffers */
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->d2h_done[c % kShells], 0));   /* chunk c - kShells left this shell's result buffers */
       b->cig_base = run_base;
+      const double g0b = now_ms();
       r = batch_run(ctx, b, ctx->stream, ctx->pin_small.as<DevCounters>());
       if (r != WFAGPU_OK) return r;
       const double g1 = now_ms();
+      if (trace) fprintf(stderr, "[wfagpu]   chunk %lld: waited %.2f ms for its staging, planned in %.2f ms, kernels %.2f ms\n",
+                         (long long)c, g0a - g0, g0b - g0a, g1 - g0b);
       {
         std::unique_lock<std::mutex> lk(mu);                          /* landing zone c&1 free again? */
-        cv.wait(lk, [&] { return drained + 2 > c || err != WFAGPU_OK; });
+        cv.wait(lk, [&] { return drained + kShells > c || err != WFAGPU_OK; });
         if (err != WFAGPU_OK) return err;
       }
       const size_t m = (size_t)b->n;
       const bool last = c == nchunks - 1;
-      PinBuf& stg = ctx->out_stage[c & 1];
+      PinBuf& stg = ctx->out_stage[c % kShells];
       CK(stg.ensure(out_bytes((int64_t)m, b->full)));
       unsigned char* base = stg.as<unsigned char>();
       cudaStream_t ds = ctx->d2h_stream;
@@ -1329,10 +1355,10 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
       const size_t so = b->full ? 8 * (m + 1) + 16 * m : 0;
       if (score) CK(cudaMemcpyAsync(dma_score ? (void*)(score + off) : (void*)(base + so), b->score.p, 4 * m, cudaMemcpyDeviceToHost, ds));
       if (status) CK(cudaMemcpyAsync(dma_status ? (void*)(status + off) : (void*)(base + so + 4 * m), b->status.p, 4 * m, cudaMemcpyDeviceToHost, ds));
-      CK(cudaEventRecord(ctx->d2h_done[c & 1], ds));
+      CK(cudaEventRecord(ctx->d2h_done[c % kShells], ds));
       {
         std::lock_guard<std::mutex> lk(mu);
-        drains[c & 1] = Drain{off, (int64_t)m, last, run_base, b->full};
+        drains[c % kShells] = Drain{off, (int64_t)m, last, run_base, b->full};
         queued = c + 1;
         cv.notify_all();
       }
@@ -1349,15 +1375,15 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
           std::unique_lock<std::mutex> lk(mu);
           cv.wait(lk, [&] { return queued > c || err != WFAGPU_OK; });
           if (queued <= c) return;
-          d = drains[c & 1];
+          d = drains[c % kShells];
         }
-        if (cudaEventSynchronize(ctx->d2h_done[c & 1]) != cudaSuccess) {
+        if (cudaEventSynchronize(ctx->d2h_done[c % kShells]) != cudaSuccess) {
           std::lock_guard<std::mutex> lk(mu);
           if (err == WFAGPU_OK) err = fail(ctx, WFAGPU_ECUDA, "result download failed");
           cv.notify_all();
           return;
         }
-        const unsigned char* base = ctx->out_stage[c & 1].as<unsigned char>();
+        const unsigned char* base = ctx->out_stage[c % kShells].as<unsigned char>();
         const size_t m = (size_t)d.m;
         const size_t so = d.full ? 8 * (m + 1) + 16 * m : 0;
         if (d.full) {
@@ -1396,7 +1422,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     for (int64_t c = 0; c < nchunks; ++c) {
       {
         std::unique_lock<std::mutex> lk(mu);
-        cv.wait(lk, [&] { return consumed + 2 > c || err != WFAGPU_OK; });   /* shell c&1 is free */
+        cv.wait(lk, [&] { return consumed + kShells > c || err != WFAGPU_OK; });   /* shell c % kShells is free */
         if (err != WFAGPU_OK) break;
       }
       const double t0 = now_ms();
@@ -1419,8 +1445,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   if (cig_runs) *cig_runs = ctx->user_runs ? ctx->user_runs : ctx->pin_runs.as<uint32_t>();
   ctx->last_launches = launches;
   if (rc != WFAGPU_OK) quiesce(ctx);
-  batch_recycle(ctx, shells[0]);
-  if (shells[1]) batch_recycle(ctx, shells[1]);
+  for (int i = kShells - 1; i >= 0; --i) if (shells[i]) batch_recycle(ctx, shells[i]);
   return rc;
 }
 

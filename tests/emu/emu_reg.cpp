@@ -45,6 +45,8 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
   R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = hrows;
+  const RegWindow rw = reg_window(regs, K.endsfree, K.match, K.pbf, K.tbf);
+  R.kbase = rw.kbase; R.c_lo = rw.c_lo; R.c_hi = rw.c_hi;
   std::vector<uint8_t> hist((size_t)hrows * 64 * regs + 64);
   int64_t used = 0;
   for (int64_t i = 0; i < n; ++i) {
