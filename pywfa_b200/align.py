@@ -11,8 +11,20 @@ through ``libwfagpu.so``; there is no CPU fallback.
 
 Intentional deviations from the reference:
   * configurations the reference ``exit(1)``s on raise ``ValueError`` before any launch;
-  * distances other than ``affine`` / ``affine2p``, ``memory_mode="biwfa"`` (different
-    tie-breaks); non-ACGT bases and the wildcard are aligned in the library's byte mode.
+  * distances other than ``affine`` / ``affine2p`` and ``memory_mode="biwfa"`` (different
+    tie-breaks) raise ``NotImplementedError``; non-ACGT bases and the wildcard are aligned in
+    the library's byte mode;
+  * ``span="end-to-end"`` ignores the ``*_begin_free`` / ``*_end_free`` values.  pywfa copies them
+    into ``alignment_form`` regardless of the span, and WFA2-lib then still seeds wavefront 0 with
+    ``lo = -pattern_begin_free, hi = text_begin_free`` (``wavefront_aligner.c:260-261``) while
+    initialising only offset 0 -- the other seeds are uninitialised memory, so the reference's
+    result for that combination is undefined; here the seed is the single cell ``k = 0``;
+  * ``match < 0`` together with ends-free *begin* gaps (score-dependent seeding,
+    ``wavefront_compute.c:124-254``) raises ``NotImplementedError``.
+
+Thread safety: all aligners of one device share one library context; calls from several threads
+are serialised inside the library (pywfa's aligners are independent objects, one per thread works
+there and here).
 """
 from __future__ import annotations
 

@@ -212,6 +212,7 @@ void scan_pairs(const int64_t* p_off, const int32_t* p_len, const int64_t* t_off
     for (int64_t i = a; i < b; ++i) {
       const int32_t pl = p_len[i], tl = t_len[i];
       if ((pl | tl) < 0) { if (r.first_negative < 0) r.first_negative = i; continue; }
+      if (t_off[i] != p_off[i] + pl || (i + 1 < n && p_off[i + 1] != t_off[i] + tl)) r.back_to_back = false;
       r.seq_bytes += (int64_t)pl + tl;
       r.total_words += ((int64_t)pl + bpw - 1) / bpw + ((int64_t)tl + bpw - 1) / bpw;
       if (pl) { r.lo = std::min(r.lo, p_off[i]); r.hi = std::max(r.hi, p_off[i] + pl); }
@@ -228,6 +229,7 @@ void scan_pairs(const int64_t* p_off, const int32_t* p_len, const int64_t* t_off
   PairScan r;
   for (const PairScan& q : part) {
     if (q.first_negative >= 0 && (r.first_negative < 0 || q.first_negative < r.first_negative)) r.first_negative = q.first_negative;
+    r.back_to_back = r.back_to_back && q.back_to_back;
     r.seq_bytes += q.seq_bytes; r.total_words += q.total_words;
     r.lo = std::min(r.lo, q.lo); r.hi = std::max(r.hi, q.hi);
     r.maxp = std::max(r.maxp, q.maxp); r.maxt = std::max(r.maxt, q.maxt);

@@ -15,6 +15,7 @@ int32_t length_class_limit(int c);      /* class c holds pairs with max(plen, tl
 /* What the planner needs to know about a chunk of pairs, from one parallel pass over the arrays. */
 struct PairScan {
   int64_t first_negative = -1;          /* first pair with a negative length, or -1 */
+  bool back_to_back = true;             /* pattern_0 text_0 pattern_1 text_1 ... without gaps: offsets follow from the lengths */
   int64_t seq_bytes = 0;                /* sum of plen + tlen */
   int64_t total_words = 0;              /* sum of ceil(plen / bpw) + ceil(tlen / bpw) */
   int64_t lo = INT64_MAX, hi = INT64_MIN;   /* byte range [lo, hi) of the sequence buffer the pairs touch */

@@ -32,11 +32,13 @@ struct PackArgs {
   PackCounters* counters;
 };
 int layout_tiles(long long n);
-/* exclusive scan of the per-pair word counts -> pairs[i] = {woff, plen, tlen}; tile_sums: layout_tiles(n) + 1 entries.
- * Also zeroes zero_a[0 .. n_zero_a) (the packer's counters and bucket cursors, n_zero_a <= 1024) and *zero_b. */
+/* exclusive scan of the per-pair word counts -> pairs[i] = {woff, plen, tlen}; tile_sums: 2 * (layout_tiles(n) + 1)
+ * entries.  Also zeroes zero_a[0 .. n_zero_a) (the packer's counters and bucket cursors, n_zero_a <= 1024) and
+ * *zero_b.  gen_poff / gen_toff != nullptr: the pairs lie back to back from byte off_base on; their offsets are
+ * generated here instead of uploaded. */
 cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long n, int bases_per_word,
                           long long* tile_sums, PairMeta* pairs, const BucketArgs& B, uint32_t* zero_a, int n_zero_a,
-                          uint32_t* zero_b, cudaStream_t st);
+                          uint32_t* zero_b, long long* gen_poff, long long* gen_toff, long long off_base, cudaStream_t st);
 /* ASCII -> 2-bit words (or bytes when byte_mode); flags pairs with other bytes (PackCounters) */
 cudaError_t launch_pack(const PackArgs& A, bool byte_mode, int max_len, int sms, cudaStream_t st);
 /* bytes of the flagged pairs -> words2 */

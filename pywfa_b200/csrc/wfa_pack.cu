@@ -33,25 +33,36 @@ constexpr int LAY_THREADS = 256;
 constexpr int LAY_ITEMS = 16;
 constexpr int LAY_TILE = LAY_THREADS * LAY_ITEMS;
 
-__device__ __forceinline__ long long words_of(int plen, int tlen, int bpw) {
+__host__ __device__ __forceinline__ long long words_of(int plen, int tlen, int bpw) {
   return (long long)((plen + bpw - 1) / bpw) + (long long)((tlen + bpw - 1) / bpw);
 }
 
+/* the two running sums of the layout: packed words and raw bases */
+struct Sum2 { long long w, b; };
+__device__ __forceinline__ Sum2 operator+(const Sum2& x, const Sum2& y) { return Sum2{x.w + y.w, x.b + y.b}; }
+__device__ __forceinline__ Sum2 shfl_up2(const Sum2& x, int o) {
+  return Sum2{__shfl_up_sync(0xffffffffu, x.w, o), __shfl_up_sync(0xffffffffu, x.b, o)};
+}
+__device__ __forceinline__ Sum2 shfl_down2(const Sum2& x, int o) {
+  return Sum2{__shfl_down_sync(0xffffffffu, x.w, o), __shfl_down_sync(0xffffffffu, x.b, o)};
+}
+__device__ __forceinline__ Sum2 item_of(int plen, int tlen, int bpw) { return Sum2{words_of(plen, tlen, bpw), (long long)plen + tlen}; }
+
 __global__ void layout_count_kernel(const int32_t* __restrict__ p_len, const int32_t* __restrict__ t_len, long long n,
-                                    int bpw, long long* __restrict__ tile_sums) {
-  __shared__ long long wsum[LAY_THREADS / 32];
+                                    int bpw, Sum2* __restrict__ tile_sums) {
+  __shared__ Sum2 wsum[LAY_THREADS / 32];
   const long long t0 = (long long)blockIdx.x * LAY_TILE;
-  long long acc = 0;
+  Sum2 acc{0, 0};
   for (int j = 0; j < LAY_ITEMS; ++j) {
     const long long i = t0 + j * LAY_THREADS + threadIdx.x;
-    if (i < n) acc += words_of(p_len[i], t_len[i], bpw);
+    if (i < n) acc = acc + item_of(p_len[i], t_len[i], bpw);
   }
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  for (int o = 16; o > 0; o >>= 1) acc = acc + shfl_down2(acc, o);
   if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    long long s = 0;
-    for (int i = 0; i < LAY_THREADS / 32; ++i) s += wsum[i];
+    Sum2 s{0, 0};
+    for (int i = 0; i < LAY_THREADS / 32; ++i) s = s + wsum[i];
     tile_sums[blockIdx.x] = s;
   }
 }
@@ -59,26 +70,26 @@ __global__ void layout_count_kernel(const int32_t* __restrict__ p_len, const int
 /* single block: exclusive scan of the tile sums in place; total -> tile_sums[ntiles].  Also clears the
  * packer's counters and the pad word behind the packed sequences (no memset in the copy stream: a
  * memset is a kernel, and kernels queue behind the persistent alignment kernel of the chunk before) */
-__global__ void layout_scan_kernel(long long* tile_sums, int ntiles, uint32_t* zero_a, int n_zero_a, uint32_t* zero_b) {
-  __shared__ long long carry;
-  __shared__ long long wtot[32];
+__global__ void layout_scan_kernel(Sum2* tile_sums, int ntiles, uint32_t* zero_a, int n_zero_a, uint32_t* zero_b) {
+  __shared__ Sum2 carry;
+  __shared__ Sum2 wtot[32];
   if ((int)threadIdx.x < n_zero_a) zero_a[threadIdx.x] = 0;
   if (threadIdx.x == 0 && zero_b) *zero_b = 0;
-  if (threadIdx.x == 0) carry = 0;
+  if (threadIdx.x == 0) carry = Sum2{0, 0};
   __syncthreads();
   for (int b = 0; b < ntiles; b += blockDim.x) {
     const int i = b + threadIdx.x;
-    const long long v = (i < ntiles) ? tile_sums[i] : 0;
-    long long inc = v;
+    const Sum2 v = (i < ntiles) ? tile_sums[i] : Sum2{0, 0};
+    Sum2 inc = v;
     for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
+      const Sum2 t = shfl_up2(inc, o);
+      if ((threadIdx.x & 31) >= o) inc = inc + t;
     }
     if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
     __syncthreads();
-    long long woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
-    const long long excl = carry + woff + inc - v;
+    Sum2 woff{0, 0};
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff = woff + wtot[w];
+    const Sum2 excl{carry.w + woff.w + inc.w - v.w, carry.b + woff.b + inc.b - v.b};
     if (i < ntiles) tile_sums[i] = excl;
     __syncthreads();
     if (threadIdx.x == blockDim.x - 1) carry = excl + v;
@@ -87,33 +98,37 @@ __global__ void layout_scan_kernel(long long* tile_sums, int ntiles, uint32_t* z
   if (threadIdx.x == 0) tile_sums[ntiles] = carry;
 }
 
-/* per tile: word offset of every pair -> PairMeta; bucket work lists when nbuckets > 1 */
+/* per tile: word offset of every pair -> PairMeta; bucket work lists when nbuckets > 1; when the caller's
+ * pairs lie back to back (pattern, text, pattern, ...: gen_off != nullptr) their byte offsets are written
+ * here instead of being uploaded: pair i starts off_base + (bases before it) */
 __global__ void layout_apply_kernel(const int32_t* __restrict__ p_len, const int32_t* __restrict__ t_len, long long n,
-                                    int bpw, const long long* __restrict__ tile_sums, PairMeta* __restrict__ pairs,
-                                    BucketArgs B) {
-  __shared__ long long wtot[LAY_THREADS / 32];
-  __shared__ long long carry_s;
+                                    int bpw, const Sum2* __restrict__ tile_sums, PairMeta* __restrict__ pairs,
+                                    BucketArgs B, long long* __restrict__ gen_poff, long long* __restrict__ gen_toff,
+                                    long long off_base) {
+  __shared__ Sum2 wtot[LAY_THREADS / 32];
+  __shared__ Sum2 carry_s;
   const long long t0 = (long long)blockIdx.x * LAY_TILE;
   if (threadIdx.x == 0) carry_s = tile_sums[blockIdx.x];
   __syncthreads();
   for (int j = 0; j < LAY_ITEMS; ++j) {
     const long long i = t0 + j * LAY_THREADS + threadIdx.x;
     const int pl = (i < n) ? p_len[i] : 0, tl = (i < n) ? t_len[i] : 0;
-    const long long v = words_of(pl, tl, bpw);
-    long long inc = v;
+    const Sum2 v = item_of(pl, tl, bpw);
+    Sum2 inc = v;
     for (int o = 1; o < 32; o <<= 1) {
-      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
-      if ((threadIdx.x & 31) >= o) inc += t;
+      const Sum2 t = shfl_up2(inc, o);
+      if ((threadIdx.x & 31) >= o) inc = inc + t;
     }
     if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = inc;
     __syncthreads();
-    long long woff = 0;
-    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
-    const long long excl = carry_s + woff + inc - v;
+    Sum2 woff{0, 0};
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff = woff + wtot[w];
+    const Sum2 excl{carry_s.w + woff.w + inc.w - v.w, carry_s.b + woff.b + inc.b - v.b};
     if (i < n) {
       PairMeta m;
-      m.woff = excl; m.plen = pl; m.tlen = tl;
+      m.woff = excl.w; m.plen = pl; m.tlen = tl;
       pairs[i] = m;
+      if (gen_poff) { gen_poff[i] = off_base + excl.b; gen_toff[i] = off_base + excl.b + pl; }
     }
     if (B.nbuckets > 1) {
       /* one atomic per bucket and warp: the lanes of a bucket take consecutive list slots */
@@ -246,12 +261,13 @@ int layout_tiles(long long n) { return (int)((n + LAY_TILE - 1) / LAY_TILE); }
 
 cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long n, int bases_per_word,
                           long long* tile_sums, PairMeta* pairs, const BucketArgs& B, uint32_t* zero_a, int n_zero_a,
-                          uint32_t* zero_b, cudaStream_t st) {
+                          uint32_t* zero_b, long long* gen_poff, long long* gen_toff, long long off_base, cudaStream_t st) {
   const int tiles = layout_tiles(n);
-  if (n > 0) layout_count_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums);
-  layout_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tiles, zero_a, n_zero_a, zero_b);
+  Sum2* sums = reinterpret_cast<Sum2*>(tile_sums);
+  if (n > 0) layout_count_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, sums);
+  layout_scan_kernel<<<1, 1024, 0, st>>>(sums, tiles, zero_a, n_zero_a, zero_b);
   if (n <= 0) return cudaGetLastError();
-  layout_apply_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, tile_sums, pairs, B);
+  layout_apply_kernel<<<tiles, LAY_THREADS, 0, st>>>(p_len, t_len, n, bases_per_word, sums, pairs, B, gen_poff, gen_toff, off_base);
   return cudaGetLastError();
 }
 

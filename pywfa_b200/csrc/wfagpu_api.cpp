@@ -757,7 +757,7 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
   CK(b->words.ensure(4 * (size_t)(b->total_words + 1)));
   CK(b->offs.ensure(16 * n1));
   CK(b->lens.ensure(8 * n1));
-  CK(b->lay.ensure(8 * (size_t)(layout_tiles(n) + 2)));
+  CK(b->lay.ensure(16 * (size_t)(layout_tiles(n) + 2)));
   CK(b->pcount.ensure(sizeof(PackCounters) + 4 * MAX_BUCKETS));
   if (nb > 1) CK(b->blist.ensure(4 * n1));
   int64_t* d_poff = b->offs.as<int64_t>(); int64_t* d_toff = d_poff + n1;
@@ -775,6 +775,7 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
   A.p_off = d_poff; A.t_off = d_toff;
   const int64_t span = hs.hi - hs.lo;
   const bool dense = span <= 2 * hs.seq_bytes + 65536;
+  bool gen_off = false;
   if (n && in.k_seq != MEM_LOCAL && !dense) {
     /* scattered pairs (e.g. one pattern against texts spread over a genome): gather them back to back
      * on the host; the offsets they have there go up instead of the caller's */
@@ -792,10 +793,14 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
     A.ascii = b->ascii.as<uint8_t>(); A.base = 0;
     h2d += hs.seq_bytes + 16 * n;
   } else if (n) {
-    int rc = upload(ctx, d_poff, p_off, 8 * (size_t)n, in.k_poff, st);
-    if (rc == WFAGPU_OK) rc = upload(ctx, d_toff, t_off, 8 * (size_t)n, in.k_toff, st);
-    if (rc != WFAGPU_OK) return rc;
-    h2d += 16 * n;
+    int rc = WFAGPU_OK;
+    gen_off = hs.back_to_back && hs.first_negative < 0;     /* pairs back to back: the layout scan writes their offsets */
+    if (!gen_off) {
+      rc = upload(ctx, d_poff, p_off, 8 * (size_t)n, in.k_poff, st);
+      if (rc == WFAGPU_OK) rc = upload(ctx, d_toff, t_off, 8 * (size_t)n, in.k_toff, st);
+      if (rc != WFAGPU_OK) return rc;
+      h2d += 16 * n;
+    }
     if (in.k_seq == MEM_LOCAL) {
       A.ascii = in.seq; A.base = 0;          /* the bases already live on this device: packed in place */
     } else {
@@ -817,7 +822,8 @@ int batch_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const wfagpu_config_t* cfg, co
     CK(cudaStreamWaitEvent(pk, copied, 0));
   }
   CK(launch_layout(d_plen, d_tlen, n, bpw, b->lay.as<long long>(), A.pairs, B, b->pcount.as<uint32_t>(),
-                   (int)((sizeof(PackCounters) + 4 * MAX_BUCKETS) / 4), b->words.as<uint32_t>() + b->total_words, pk));
+                   (int)((sizeof(PackCounters) + 4 * MAX_BUCKETS) / 4), b->words.as<uint32_t>() + b->total_words,
+                   gen_off ? (long long*)d_poff : nullptr, gen_off ? (long long*)d_toff : nullptr, n ? (long long)p_off[0] : 0, pk));
   CK(launch_pack(A, b->byte_mode, std::max(b->maxp, b->maxt), ctx->sms, pk));
   CK(cudaMemcpyAsync(counts, b->pcount.p, sizeof(PackCounters), cudaMemcpyDeviceToHost, pk));
   b->stats.kernel_launches = n ? 4 : 1;

@@ -119,3 +119,20 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
 
 /* expose the host packer for tests */
 extern "C" int emu_pack(const uint8_t* s, int len, uint32_t* out) { return pack_sequence(s, len, out) ? 1 : 0; }
+
+/* host side of the batch staging (pywfa_b200/csrc/pack.cpp), exposed to the CPU test-suite */
+extern "C" void emu_scan_pairs(const int64_t* p_off, const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
+                               int bpw, int64_t* out /* 9 + 3 * MAX_LEN_CLASSES */) {
+  PairScan r;
+  scan_pairs(p_off, p_len, t_off, t_len, n, bpw, &r);
+  out[0] = r.first_negative; out[1] = r.back_to_back ? 1 : 0; out[2] = r.seq_bytes; out[3] = r.total_words;
+  out[4] = r.lo; out[5] = r.hi; out[6] = r.maxp; out[7] = r.maxt; out[8] = ((int64_t)r.minp << 32) | (uint32_t)r.mint;
+  for (int c = 0; c < MAX_LEN_CLASSES; ++c) {
+    out[9 + c] = r.cls_n[c]; out[9 + MAX_LEN_CLASSES + c] = r.cls_maxp[c]; out[9 + 2 * MAX_LEN_CLASSES + c] = r.cls_maxt[c];
+  }
+}
+extern "C" void emu_gather_pairs(const uint8_t* seq, const int64_t* p_off, const int32_t* p_len, const int64_t* t_off,
+                                 const int32_t* t_len, int64_t n, uint8_t* dst, int64_t* np_off, int64_t* nt_off) {
+  gather_pairs(seq, p_off, p_len, t_off, t_len, n, dst, np_off, nt_off);
+}
+extern "C" int emu_length_class_limit(int c) { return length_class_limit(c); }

@@ -184,3 +184,62 @@ def test_byte_mode_non_acgt_and_wildcard(emu, oracle, kw):
     assert not got["ovf"].any()
     for k in ("score", "status", "cig_off", "runs", "locs"):
         assert np.array_equal(got[k], want[k]), (kw, k)
+
+
+def test_host_staging_scan_and_gather(emu):
+    """The host side of the batch staging (pack.cpp): one parallel pass over the offset / length arrays
+    yields what the planner needs (byte range, longest sequences, word count, length-class histogram,
+    whether the pairs lie back to back), and scattered pairs are gathered back to back."""
+    L = emu.lib
+    i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
+    u8p = np.ctypeslib.ndpointer(np.uint8, flags="C")
+    L.emu_scan_pairs.argtypes = [i64p, i32p, i64p, i32p, C.c_int64, C.c_int, i64p]
+    L.emu_gather_pairs.argtypes = [u8p, i64p, i32p, i64p, i32p, C.c_int64, u8p, i64p, i64p]
+    L.emu_length_class_limit.restype = C.c_int
+    limits = [L.emu_length_class_limit(c) for c in range(8)]
+    assert limits == sorted(limits) and limits[-1] == 2**31 - 1
+    rng = np.random.default_rng(8)
+    for n in (1, 7, 5000, 300_000):
+        p_len = rng.integers(0, 400, n).astype(np.int32)
+        t_len = rng.integers(0, 3000, n).astype(np.int32)
+        rec = p_len.astype(np.int64) + t_len
+        p_off = np.concatenate(([0], np.cumsum(rec)[:-1])).astype(np.int64) + 17
+        t_off = p_off + p_len
+        for scattered in (False, True):
+            if scattered:
+                t_off = t_off + 1_000_000
+            out = np.zeros(9 + 24, np.int64)
+            for bpw in (16, 4):
+                L.emu_scan_pairs(p_off, p_len, t_off, t_len, n, bpw, out)
+                assert out[0] == -1 and out[1] == (0 if scattered else 1)
+                assert out[2] == int(rec.sum())
+                assert out[3] == int(((p_len.astype(np.int64) + bpw - 1) // bpw + (t_len.astype(np.int64) + bpw - 1) // bpw).sum())
+                nz_p, nz_t = p_len > 0, t_len > 0
+                lo = min(int(p_off[nz_p].min()) if nz_p.any() else 2**62, int(t_off[nz_t].min()) if nz_t.any() else 2**62)
+                hi = max(int((p_off + p_len)[nz_p].max()) if nz_p.any() else -1, int((t_off + t_len)[nz_t].max()) if nz_t.any() else -1)
+                if hi >= 0:
+                    assert (out[4], out[5]) == (lo, hi)
+                assert (out[6], out[7]) == (int(p_len.max()), int(t_len.max()))
+                assert (out[8] >> 32, out[8] & 0xffffffff) == (int(p_len.min()), int(t_len.min()))
+                cls = np.searchsorted(limits, np.maximum(p_len, t_len), side="left")
+                assert out[9:17].tolist() == np.bincount(cls, minlength=8).tolist()
+                for c in range(8):
+                    if (cls == c).any():
+                        assert out[17 + c] == p_len[cls == c].max() and out[25 + c] == t_len[cls == c].max()
+    bad = p_len.copy(); bad[123] = -5
+    L.emu_scan_pairs(p_off, bad, t_off, t_len, n, 16, out)
+    assert out[0] == 123
+    # gather: one pattern against texts spread over a buffer
+    seq = rng.integers(65, 91, 200_000).astype(np.uint8)
+    m = 3000
+    g_toff = np.sort(rng.integers(0, 190_000, m)).astype(np.int64)
+    g_tlen = rng.integers(1, 300, m).astype(np.int32)
+    g_poff = np.full(m, 199_000, np.int64); g_plen = np.full(m, 77, np.int32)
+    dst = np.zeros(int(g_plen.sum() + g_tlen.sum()), np.uint8)
+    npo, nto = np.zeros(m, np.int64), np.zeros(m, np.int64)
+    L.emu_gather_pairs(seq, g_poff, g_plen, g_toff, g_tlen, m, dst, npo, nto)
+    for i in (0, 1, m // 2, m - 1):
+        assert np.array_equal(dst[npo[i]:npo[i] + 77], seq[199_000:199_077])
+        assert np.array_equal(dst[nto[i]:nto[i] + g_tlen[i]], seq[g_toff[i]:g_toff[i] + g_tlen[i]])
+    assert nto[-1] + g_tlen[-1] == len(dst) and np.all(nto == npo + 77)
