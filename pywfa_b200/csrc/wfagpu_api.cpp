@@ -1226,10 +1226,11 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   for (auto& pb : ctx->pin_pack) CK(pb.ensure(sizeof(PackCounters)));
   if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->user_runs ? ctx->user_runs : ctx->pin_runs.as<uint32_t>(); }
   const double t_start = now_ms();
-  /* chunking: a few chunks, so that staging and downloads overlap the kernels while the fixed cost of a
-   * chunk (launches, one host round trip, the tail of its persistent kernels) stays small: the first one
-   * is a sixteenth of the batch (its upload is the only one nothing overlaps), then doubling up to a third;
-   * chunks are also bounded by bytes (two shells of raw bases live in HBM) */
+  /* chunking: the first chunk is small (its upload is the only one nothing overlaps), the others are a
+   * twelfth of the batch: when the kernels bind, a chunk costs a fixed ~0.3 ms (launches, one host round
+   * trip, the tail of its persistent kernels); when the upload binds (several GPUs sharing the host's
+   * memory bandwidth), what is not overlapped is the kernel time of the LAST chunk, so chunks must not be
+   * large either.  Chunks are also bounded by bytes (kShells shells of raw bases live in HBM). */
   std::vector<int64_t> starts;           /* chunk c covers pairs [starts[c], starts[c+1]) */
   {
     const int64_t want = ctx->knobs.chunk;
@@ -1240,17 +1241,12 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
       const int64_t probe = std::min<int64_t>(n, 1024);
       for (int64_t i = 0; i < probe; ++i) mean += (double)std::max(p_len[i], 0) + (double)std::max(t_len[i], 0);
       mean = std::max(mean / (double)probe, 1.0);
-      const int64_t by_bytes = std::max<int64_t>(65536, (int64_t)(2.0e9 / mean));
-      chunk = std::min(by_bytes, std::max<int64_t>(131072, (n + 2) / 3));
-      first = std::min(chunk, std::max<int64_t>(32768, n / 16));
+      const int64_t by_bytes = std::max<int64_t>(65536, (int64_t)(1.0e9 / mean));
+      chunk = std::min(by_bytes, std::max<int64_t>(131072, (n + 11) / 12));
+      first = std::min(chunk, std::max<int64_t>(32768, n / 32));
     }
     starts.push_back(0);
-    int64_t cur = first;
-    for (int64_t off = std::min(first, n); off < n;) {
-      starts.push_back(off);
-      cur = std::min<int64_t>(chunk, 2 * cur);
-      off += cur;
-    }
+    for (int64_t off = std::min(first, n); off < n; off += chunk) starts.push_back(off);
     starts.push_back(n);
     if (n == 0) starts.assign({0, 0});
   }
