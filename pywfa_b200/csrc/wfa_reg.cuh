@@ -308,16 +308,60 @@ struct RegAligner {
     }
   }
 
-  /* age the M ring by one score: `Mn` becomes M[0] */
+  /* age the M ring by one score: `Mn` becomes M[0] (registers PLO..PHI; the others hold nulls throughout) */
+  template <int PLO, int PHI>
   WFA_DEV void push(const lv::vu (&Mn)[P], bool exists) {
 #pragma unroll
     for (int r = RM - 1; r > 0; --r) {
 #pragma unroll
-      for (int p = 0; p < P; ++p) M[r][p] = M[r - 1][p];
+      for (int p = PLO; p <= PHI; ++p) M[r][p] = M[r - 1][p];
     }
 #pragma unroll
-    for (int p = 0; p < P; ++p) M[0][p] = Mn[p];
+    for (int p = PLO; p <= PHI; ++p) M[0][p] = Mn[p];
     flags = (flags & ~F_MRING) | ((flags << 1) & F_MRING) | (exists ? 1u : 0u);
+  }
+
+  /* the middle register(s): columns 64 * NLO .. 64 * NHI + 63 hold the score-0 seeds of an end-to-end alignment */
+  static constexpr int NLO = (P - 1) / 2, NHI = P / 2;
+
+  /* ---- phases A + B of a score step on packed registers PLO..PHI (the others are all null) ---- */
+  template <int PLO, int PHI>
+  WFA_DEV void recurrence(lv::vu (&Mn)[P]) {
+    using namespace lv;
+    /* phase A: per source diagonal max(open, extend), rotated to the consuming lane */
+    vu rl[P], rr[P];
+#pragma unroll
+    for (int p = PLO; p <= PHI; ++p) {
+      rl[p] = from_lane(vimax2(M[DOE - 1][p], I[p]), lprev);
+      rr[p] = from_lane(vimax2(M[DOE - 1][p], D[p]), lnext);
+    }
+    /* phase B: the recurrence (compute_affine.c:44-86), 64 diagonals per instruction */
+#pragma unroll
+    for (int p = PLO; p <= PHI; ++p) {
+      const vu L = prmt(p > PLO ? rl[p > PLO ? p - 1 : PLO] : splat(REG_NULL2), rl[p], selL);
+      const vu Rr = prmt(rr[p], p < PHI ? rr[p < PHI ? p + 1 : p] : splat(REG_NULL2), selR);
+      const vu ins = vadd2(L, splat(REG_ONE2));
+      const vu del = Rr;
+      const vu mis = vadd2(M[DX - 1][p], splat(REG_ONE2));
+      vu m;
+      if (FULL) {
+        /* origin code of both cells of the register, from the sign bits of packed differences (all
+         * operands lie within +-16384 + drift, so no difference wraps): bit 0 "deletion beats mismatch"
+         * (mismatch wins ties), bit 1 "insertion beats both" (it loses ties), bit 2 / 3 "I[s][k+1] /
+         * D[s][k-1] is opened, not extended" (ext >= open extends) -- wavefront_backtrace.c:49-59 order */
+        const vu m1 = vimax2(mis, del);
+        m = vimax2(m1, ins);
+        const vu t1 = vsub2(mis, del), t2 = vsub2(m1, ins);
+        const vu t3 = vsub2(I[p], M[DOE - 1][p]), t4 = vsub2(D[p], M[DOE - 1][p]);
+        const vu n = ((t1 >> 15) & 0x00010001u) | ((t2 >> 14) & 0x00020002u) | ((t3 >> 13) & 0x00040004u) | ((t4 >> 12) & 0x00080008u);
+        hist_store<HS>(hist, s * (32 * P) + 32 * p, lane, as_vi((n | (n >> 12)) & 0xffu));
+      } else {
+        m = vimax3(mis, ins, del);
+      }
+      /* offsets beyond the matrix are nulled: M > ub  <=>  M + ~ub >= 0 */
+      Mn[p] = bitsel(signmask2(vadd2(m, ~ub2[p])), m, splat(REG_NULL2));
+      I[p] = ins; D[p] = del;
+    }
   }
 
   /* ---- one score step: score 0 seeds the wavefront, every later score computes it -------- */
@@ -325,6 +369,7 @@ struct RegAligner {
     using namespace lv;
     vu Mn[P];
     int dlo, dhi;                                     /* window range the new wavefront can occupy */
+    bool narrow = false;                              /* this step touched the middle register(s) only */
     if (seeding) {
       dlo = c_lo; dhi = c_hi;
 #pragma unroll
@@ -341,7 +386,7 @@ struct RegAligner {
         /* null step (allocate_output_null, compute.c:374-400) */
 #pragma unroll
         for (int p = 0; p < P; ++p) Mn[p] = splat(REG_NULL2);
-        push(Mn, false);
+        push<0, P - 1>(Mn, false);
         wprev = 0;
         if (s >= s_limit) { status = 3; return true; }
         return false;
@@ -356,39 +401,16 @@ struct RegAligner {
         s_event = next_event();
       }
 
-      /* phase A: per source diagonal max(open, extend), rotated to the consuming lane */
-      vu rl[P], rr[P];
+      /* phases A + B on the packed registers the wavefront can occupy: while it stays inside the middle
+       * register(s) (about half the scores of a typical pair on the 192- and 256-diagonal windows) the
+       * outer ones hold nothing but nulls in every ring slot and are neither computed nor rotated */
+      narrow = NLO > 0 && dlo >= 64 * NLO && dhi < 64 * (NHI + 1);
+      if (narrow) {
+        recurrence<NLO, NHI>(Mn);
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        rl[p] = from_lane(vimax2(M[DOE - 1][p], I[p]), lprev);
-        rr[p] = from_lane(vimax2(M[DOE - 1][p], D[p]), lnext);
-      }
-      /* phase B: the recurrence (compute_affine.c:44-86), 64 diagonals per instruction */
-#pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const vu L = prmt(p > 0 ? rl[p > 0 ? p - 1 : 0] : splat(REG_NULL2), rl[p], selL);
-        const vu Rr = prmt(rr[p], p < P - 1 ? rr[p < P - 1 ? p + 1 : p] : splat(REG_NULL2), selR);
-        const vu ins = vadd2(L, splat(REG_ONE2));
-        const vu del = Rr;
-        const vu mis = vadd2(M[DX - 1][p], splat(REG_ONE2));
-        vu m;
-        if (FULL) {
-          /* origin code of both cells of the register, from the sign bits of packed differences (all
-           * operands lie within +-16384 + drift, so no difference wraps): bit 0 "deletion beats mismatch"
-           * (mismatch wins ties), bit 1 "insertion beats both" (it loses ties), bit 2 / 3 "I[s][k+1] /
-           * D[s][k-1] is opened, not extended" (ext >= open extends) -- wavefront_backtrace.c:49-59 order */
-          const vu m1 = vimax2(mis, del);
-          m = vimax2(m1, ins);
-          const vu t1 = vsub2(mis, del), t2 = vsub2(m1, ins);
-          const vu t3 = vsub2(I[p], M[DOE - 1][p]), t4 = vsub2(D[p], M[DOE - 1][p]);
-          const vu n = ((t1 >> 15) & 0x00010001u) | ((t2 >> 14) & 0x00020002u) | ((t3 >> 13) & 0x00040004u) | ((t4 >> 12) & 0x00080008u);
-          hist_store<HS>(hist, s * (32 * P) + 32 * p, lane, as_vi((n | (n >> 12)) & 0xffu));
-        } else {
-          m = vimax3(mis, ins, del);
-        }
-        /* offsets beyond the matrix are nulled: M > ub  <=>  M + ~ub >= 0 */
-        Mn[p] = bitsel(signmask2(vadd2(m, ~ub2[p])), m, splat(REG_NULL2));
-        I[p] = ins; D[p] = del;
+        for (int p = 0; p < P; ++p) if (p < NLO || p > NHI) Mn[p] = splat(REG_NULL2);
+      } else {
+        recurrence<0, P - 1>(Mn);
       }
       const bool ex_o = (flags >> (DOE - 1)) & 1u;
       bool exIn = ex_o || (flags & F_I), exDn = ex_o || (flags & F_D);
@@ -417,7 +439,8 @@ struct RegAligner {
       wprev = cur_hi - cur_lo + 1;                    /* 0 when nothing is valid (cur_lo = cur_hi + 1) */
     }
     /* (far from the matrix edges the outermost diagonals are reached by one gap of `reach` bases and are valid) */
-    push(Mn, wprev > 0);
+    if (narrow) push<NLO, NHI>(Mn, wprev > 0);
+    else push<0, P - 1>(Mn, wprev > 0);
     /* step limit first, then termination (unialign.c:241-273 order); score 0 has no limit check */
     if (!seeding && s >= s_limit) {
       status = 3;
