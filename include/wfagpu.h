@@ -152,6 +152,24 @@ int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
                        int64_t* cig_off, const uint32_t** cig_runs);
 
 /*
+ * One pair: the literal replacement of a single wavefront_align(aligner, pattern,
+ * plen, text, tlen) call (W/wavefront/wavefront_align.c:212-241; bound at
+ * pywfa/WFA_wrap.pxd:1281, called at pywfa/align.pyx:439) followed by the reads
+ * of aligner->cigar / ->align_status (pywfa/align.pyx:443,463,731-833).  pattern /
+ * text are raw ASCII (any case, no terminator needed).  locs[4] as above;
+ * *cig_runs points at *n_runs run words (length << 4 | op) in library-owned
+ * memory, valid until the next call on this context.  Short gap-affine pairs
+ * without cut-offs run through one kernel launch on a mapped mailbox (no staging
+ * copies); anything else is a batch of one.  A loop over single pairs is the
+ * slowest way to use a GPU -- prefer wfagpu_align_batch -- but it is what
+ * pywfa's a(text, pattern) does, so it is kept as cheap as a launch allows.
+ */
+int wfagpu_align_pair(wfagpu_ctx* ctx, const wfagpu_config_t* cfg,
+                      const char* pattern, int32_t plen, const char* text, int32_t tlen,
+                      int32_t* score, int32_t* status, int32_t* locs,
+                      const uint32_t** cig_runs, int32_t* n_runs);
+
+/*
  * Staged form of the same path, for callers that keep batches resident in HBM
  * (bench.py's device-resident `value`, pipelined streaming).
  *   prepare : H2D of the raw bases, 2-bit packing and length bucketing on the device

@@ -89,6 +89,10 @@ def lib():
     L.wfagpu_batch_get_stats.restype = C.c_int
     L.wfagpu_last_launches.argtypes = [vp]
     L.wfagpu_last_launches.restype = C.c_int64
+    i32p = C.POINTER(C.c_int32)
+    L.wfagpu_align_pair.argtypes = [vp, cfgp, cp, C.c_int32, cp, C.c_int32, i32p, i32p, i32p,
+                                    C.POINTER(C.POINTER(C.c_uint32)), i32p]
+    L.wfagpu_align_pair.restype = C.c_int
     L.wfagpu_set_run_buffer.argtypes = [vp, vp, i64]
     L.wfagpu_set_run_buffer.restype = C.c_int
     L.wfagpu_host_alloc.argtypes = [C.c_size_t]
@@ -250,6 +254,17 @@ class Context:
             raise ValueError("run buffer must be a contiguous uint32 array")
         self._run_buf = buf
         self._check(lib().wfagpu_set_run_buffer(self._h, _ptr(buf), buf.size))
+
+    def align_pair(self, cfg: Config, pattern: bytes, text: bytes):
+        """``wfagpu_align_pair``: one pair, low latency.  Returns ``(score, status, locs, runs)`` with
+        ``runs`` a list of ``length << 4 | op`` words."""
+        score, status, n = C.c_int32(), C.c_int32(), C.c_int32()
+        locs = (C.c_int32 * 4)()
+        runs = C.POINTER(C.c_uint32)()
+        rc = lib().wfagpu_align_pair(self._h, C.addressof(cfg), pattern, len(pattern), text, len(text),
+                                     C.byref(score), C.byref(status), locs, C.byref(runs), C.byref(n))
+        self._check(rc)
+        return score.value, status.value, list(locs), runs[:n.value]
 
     def last_launches(self) -> int:
         return int(lib().wfagpu_last_launches(self._h))

@@ -503,14 +503,15 @@ class WavefrontAligner:
         self._text = text
         self.text_len = len(tb)
         self._validate(len(pb), len(tb))
-        seq = np.frombuffer(pb + tb + b"\0", np.uint8)
-        r = _run(_context(self._device),
-            self._cfg, seq, np.array([0], np.int64), np.array([len(pb)], np.int32),
-            np.array([len(pb)], np.int64), np.array([len(tb)], np.int32))
-        self._score = int(r["score"][0])
-        self._status = int(r["status"][0])
-        self._cigartuples = _runs_to_tuples(r["runs"])
-        self._locations = [int(v) for v in r["locs"][0]]
+        try:
+            self._score, self._status, self._locations, runs = _context(self._device).align_pair(self._cfg, pb, tb)
+        except _ffi.WfaGpuError as e:
+            if e.code == _ffi.EUNSUPPORTED:
+                raise NotImplementedError(str(e)) from None
+            if e.code == _ffi.EINVAL:
+                raise ValueError(str(e)) from None
+            raise
+        self._cigartuples = [(w & 15, w >> 4) for w in runs]
         return self._score
 
     @property

@@ -23,6 +23,7 @@
 #include "wfa_reg.cuh"
 #include "wfa_vec.cuh"
 #include "wfa_launch.h"
+#include "wfa_pack16.cuh"
 
 namespace wfagpu {
 
@@ -467,6 +468,76 @@ __global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const _
   if (lane == 0 && cells_acc) atomicAdd(K.cells_total, (unsigned long long)cells_acc);
 }
 
+/* ---- one pair, one warp, one launch: the low-latency path of wfagpu_align_pair ------------------ */
+/*
+ * Replaces ONE wavefront_align call (W/wavefront/wavefront_align.c:212-241) for callers that loop over
+ * pairs (pywfa's a(text, pattern)).  Everything a batch needs several kernels and copies for happens in
+ * this one launch: the bases are read straight out of the caller-visible mailbox in mapped host memory,
+ * packed and turned into windows in shared memory, aligned on the 256-diagonal register window with the
+ * origin arena, edit stack and run staging in shared memory, and the results (incl. the CIGAR runs) are
+ * written back into the mailbox.  rc = 1 asks the host to take the batch path (non-ACGT bytes, a pair
+ * the window cannot hold).
+ */
+template <bool FULL>
+__global__ void __launch_bounds__(32) wfa_pair_kernel(const __grid_constant__ KParams K, PairBox* box) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P = 4;
+  const int lane = threadIdx.x & 31;
+  const int plen = box->plen, tlen = box->tlen;
+  const int pwn = (plen + 15) >> 4, twn = (tlen + 15) >> 4;
+  uint32_t* const sm_pk = reinterpret_cast<uint32_t*>(smem_raw);                     /* packed words: PAIR_PK_WORDS */
+  uint32_t* const sm_win = sm_pk + PAIR_PK_WORDS;                                    /* windows: 2 * PAIR_MAX_LEN + 2 */
+  uint8_t* const ops = reinterpret_cast<uint8_t*>(sm_win + 2 * PAIR_MAX_LEN + 2);    /* edit stack: PAIR_OPS_BYTES */
+  uint8_t* const hist_p = ops + PAIR_OPS_BYTES;                                      /* origin arena / run staging */
+  uint32_t* const stage = reinterpret_cast<uint32_t*>(hist_p);
+  const uint8_t* const ascii = reinterpret_cast<const uint8_t*>(box) + PAIR_ASCII_OFF;
+  bool bad = false;
+  for (int w = lane; w < pwn + twn; w += 32) {
+    const bool is_t = w >= pwn;
+    const int j = is_t ? w - pwn : w;
+    const int len = is_t ? tlen : plen;
+    sm_pk[w] = pack16<true>(ascii + (is_t ? PAIR_TEXT_OFF : 0) + 16 * j, min(16, len - 16 * j), bad);
+  }
+  if (lane == 0) sm_pk[pwn + twn] = 0;
+  __syncwarp();
+  if (__any_sync(0xffffffffu, bad)) { if (lane == 0) box->rc = 1; return; }
+  uint32_t* sp = sm_win; uint32_t* st = sm_win + plen + 1;
+  build_windows(sm_pk, plen, sp);
+  build_windows(sm_pk + pwn, tlen, st);
+  __syncwarp();
+  RegParams R;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
+  R.hrows = PAIR_HIST_ROWS; R.opcap = PAIR_OPS_BYTES; R.runcap = plen + tlen + 2;
+  const RegWindow rw = reg_window(P, K.endsfree, K.match, K.pbf, K.tbf);
+  R.kbase = rw.kbase; R.c_lo = rw.c_lo; R.c_hi = rw.c_hi;
+  PairResult res;
+  const lv::histref hist = lv::make_histref(hist_p, true);
+  const int rc = align_pair_reg<P, 2, 4, FULL, FULL>(R, sm_pk, sm_pk + pwn, lv::make_seqref(sp), lv::make_seqref(st), plen, tlen,
+                                                     hist, ops, stage, lane == 0, res);
+  if (rc == PAIR_OVERFLOW) { if (lane == 0) box->rc = 1; return; }
+  int nr = 0, stt = res.status;
+  if (FULL) {
+    nr = __shfl_sync(0xffffffffu, res.nruns, 0);
+    if (nr < 0 || nr > R.runcap) { if (lane == 0) box->rc = 1; return; }
+    __syncwarp();
+    uint32_t* const out = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(box) + PAIR_RUNS_OFF);
+    for (int i = lane; i < nr; i += 32) out[i] = stage[i];
+  }
+  if (lane == 0) {
+    box->score = res.score; box->status = stt; box->nruns = nr;
+    for (int q = 0; q < 4; ++q) box->locs[q] = (FULL && nr > 0) ? res.locs[q] : 0;
+    box->cells = res.cells;
+    box->rc = 0;
+  }
+}
+
+cudaError_t launch_pair(const KParams& P, bool full, PairBox* box, cudaStream_t st) {
+  if (full) wfa_pair_kernel<true><<<1, 32, PAIR_SMEM_BYTES, st>>>(P, box);
+  else wfa_pair_kernel<false><<<1, 32, PAIR_SMEM_BYTES, st>>>(P, box);
+  return cudaGetLastError();
+}
+
 /* ---- the packed-halfword tier (wfa_vec.cuh): NW warps per pair, rings in shared memory ---- */
 /* shared memory of one group: [metadata int4 x mr*3][flags 256 B][2 step plans 512 B][packed sequences][offset rings] */
 template <bool TWO_P, bool FULL, int NW, int HEUR>
@@ -761,6 +832,13 @@ int reg_occupancy(int regs, bool full, int block, size_t smem) {
   return nb;
 }
 
+static cudaError_t init_pair(int smem_optin) {
+  (void)smem_optin;
+  cudaError_t e = cudaFuncSetAttribute(wfa_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(wfa_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES);
+  return e;
+}
+
 static cudaError_t init_reg(int smem_optin) {
   cudaError_t e = cudaSuccess;
   for (int regs = 2; regs <= 4; ++regs)
@@ -875,6 +953,8 @@ cudaError_t init_kernels(int smem_optin) {
   if (e != cudaSuccess) return e;
   const cudaError_t e2 = init_vec(smem_optin);
   if (e2 != cudaSuccess) return e2;
+  const cudaError_t e3 = init_pair(smem_optin);
+  if (e3 != cudaSuccess) return e3;
   return init_grid(smem_optin);
 }
 

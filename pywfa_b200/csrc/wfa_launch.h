@@ -66,6 +66,25 @@ size_t grid_scratch_bytes(int groups);
 int grid_occupancy(bool two_p, bool full, size_t smem);   /* resident CTAs per SM */
 cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int ncta, size_t smem, void* scratch, cudaStream_t st);
 
+/* ---- single pair (wfa_pair_kernel) ---- */
+constexpr int PAIR_MAX_LEN = 1000;                       /* longest sequence the one-launch path takes */
+constexpr int PAIR_TEXT_OFF = 1024;                      /* text bytes start here in the mailbox's ASCII region */
+constexpr int PAIR_ASCII_OFF = 64;                       /* mailbox layout: header | ASCII (2 x 1024) | runs */
+constexpr int PAIR_RUNS_OFF = PAIR_ASCII_OFF + 2 * 1024;
+constexpr int PAIR_BOX_BYTES = PAIR_RUNS_OFF + 4 * (2 * PAIR_MAX_LEN + 2);
+constexpr int PAIR_PK_WORDS = 2 * ((PAIR_MAX_LEN + 15) / 16) + 2;
+constexpr int PAIR_OPS_BYTES = 2 * PAIR_MAX_LEN + 16;
+constexpr int PAIR_HIST_ROWS = 32 * 4 + 4 + 1;           /* scores the 256-diagonal window can hold */
+constexpr int PAIR_HIST_BYTES = PAIR_HIST_ROWS * 32 * 4 > 4 * (2 * PAIR_MAX_LEN + 2) ? PAIR_HIST_ROWS * 32 * 4 : 4 * (2 * PAIR_MAX_LEN + 2);
+constexpr int PAIR_SMEM_BYTES = 4 * PAIR_PK_WORDS + 4 * (2 * PAIR_MAX_LEN + 2) + PAIR_OPS_BYTES + PAIR_HIST_BYTES + 32;
+struct PairBox {                                          /* header of the mailbox (mapped pinned host memory) */
+  int32_t plen, tlen;
+  int32_t score, status, locs[4], nruns;
+  int32_t rc;                                             /* 0: done; 1: take the batch path */
+  long long cells;
+};
+cudaError_t launch_pair(const KParams& P, bool full, PairBox* box, cudaStream_t st);
+
 /* runs_out == nullptr: count + scan (tile_sums needs cigar_order_tiles(n)+1 entries, total in the
  * last one); otherwise gather into cig_off[n+1] (values offset by cig_base) / runs_out. */
 cudaError_t launch_cigar_order(const int* nruns, const long long* runs_base, long long n,

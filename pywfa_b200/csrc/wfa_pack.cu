@@ -24,6 +24,7 @@
 
 #include "wfa_core.cuh"
 #include "wfa_launch.h"
+#include "wfa_pack16.cuh"
 
 namespace wfagpu {
 
@@ -148,45 +149,6 @@ __global__ void layout_apply_kernel(const int32_t* __restrict__ p_len, const int
     if (threadIdx.x == LAY_THREADS - 1) carry_s = excl + v;
     __syncthreads();
   }
-}
-
-/* 16 bases -> one word.  `s` may have any alignment: two aligned 16-byte loads (only chunks that
- * hold at least one of the wanted bytes are touched, so nothing outside the caller's bytes' own
- * 16-byte lines is ever read) and a funnel shift.  Returns the packed word; `bad` is raised when a
- * byte other than ACGT/acgt was seen. */
-__device__ __forceinline__ uint32_t pack16(const uint8_t* s, int nb, bool& bad) {
-  const uintptr_t a = reinterpret_cast<uintptr_t>(s);
-  const uint4* al = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-  const int sh = (int)(a & 15);
-  const uint4 lo = __ldg(al);
-  uint4 hi = make_uint4(0, 0, 0, 0);
-  if (sh + nb > 16) hi = __ldg(al + 1);
-  const int r = (sh & 3) * 8;
-  uint32_t w0, w1, w2, w3;
-  switch (sh >> 2) {
-    case 0: w0 = __funnelshift_r(lo.x, lo.y, r); w1 = __funnelshift_r(lo.y, lo.z, r); w2 = __funnelshift_r(lo.z, lo.w, r); w3 = __funnelshift_r(lo.w, hi.x, r); break;
-    case 1: w0 = __funnelshift_r(lo.y, lo.z, r); w1 = __funnelshift_r(lo.z, lo.w, r); w2 = __funnelshift_r(lo.w, hi.x, r); w3 = __funnelshift_r(hi.x, hi.y, r); break;
-    case 2: w0 = __funnelshift_r(lo.z, lo.w, r); w1 = __funnelshift_r(lo.w, hi.x, r); w2 = __funnelshift_r(hi.x, hi.y, r); w3 = __funnelshift_r(hi.y, hi.z, r); break;
-    default: w0 = __funnelshift_r(lo.w, hi.x, r); w1 = __funnelshift_r(hi.x, hi.y, r); w2 = __funnelshift_r(hi.y, hi.z, r); w3 = __funnelshift_r(hi.z, hi.w, r); break;
-  }
-  uint32_t w[4] = {w0, w1, w2, w3};
-  uint32_t out = 0, ok = 0xffffffffu;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    /* bytes of this word that exist: nb - 4q of them (clamped to 0..4) */
-    const int live = min(max(nb - 4 * q, 0), 4);
-    const uint32_t keep = live >= 4 ? 0xffffffffu : ((1u << (8 * live)) - 1u);
-    const uint32_t x = w[q] & keep;
-    const uint32_t u = x & 0xDFDFDFDFu;
-    const uint32_t good = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) | __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
-    ok &= good | ~keep;
-    uint32_t c = (x >> 1) & 0x03030303u;
-    c |= c >> 6;
-    c = (c | (c >> 12)) & 0xffu;
-    out |= c << (8 * q);
-  }
-  bad |= ok != 0xffffffffu;
-  return out;
 }
 
 /* One warp (BLOCK = false) or one CTA (long reads) per pair. */

@@ -136,7 +136,7 @@ WFA_DEV void build_windows(const uint32_t* words, int len, uint32_t* win) {
   }
 }
 
-template <int P, int DX, int DOE, bool FULL>
+template <int P, int DX, int DOE, bool FULL, bool HS_ = reg_hist_in_smem(P, FULL)>
 struct RegAligner {
   static constexpr int RM = DX > DOE ? DX : DOE;   /* M ring: M[r] = wavefront of score s-1-r when score s is computed */
   static constexpr int DE = 1;
@@ -159,7 +159,7 @@ struct RegAligner {
   uint32_t flags;
   bool endsfree;
   int pef, tef;
-  static constexpr bool HS = reg_hist_in_smem(P, FULL);   /* origin arena in shared memory */
+  static constexpr bool HS = HS_;                  /* origin arena in shared memory */
   lv::histref hist;
   int hrows;
   int plen, tlen, kbase;
@@ -472,11 +472,11 @@ struct RegAligner {
  * backtrace.  Returns PAIR_DONE (res filled by every lane except nruns / locs, which only the
  * leader knows and must be broadcast by the caller) or PAIR_OVERFLOW.
  */
-template <int P, int DX, int DOE, bool FULL>
+template <int P, int DX, int DOE, bool FULL, bool HS = reg_hist_in_smem(P, FULL)>
 WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_t* tw, lv::seqref pwin, lv::seqref twin,
                            int plen, int tlen, const lv::histref& hist, uint8_t* ops, uint32_t* runs_stage, bool is_leader,
                            PairResult& res) {
-  RegAligner<P, DX, DOE, FULL> A;
+  RegAligner<P, DX, DOE, FULL, HS> A;
   A.init(R, pwin, twin, plen, tlen, hist);
   int end_k = 0, end_off = 0;
   if (A.run(end_k, end_off) == PAIR_OVERFLOW) return PAIR_OVERFLOW;

@@ -150,11 +150,14 @@ struct wfagpu_ctx {
   std::mutex call_mu;                   /* one call at a time per context: aligners on several threads may share it */
   DebugKnobs knobs;
   StageRing ring;                       /* pageable input -> pinned pieces -> device */
+  DevBuf whole_seq;                     /* the caller's whole byte range, when its pairs are shuffled (every chunk spans it) */
+  cudaEvent_t whole_done = nullptr;
   PinBuf gather_seq, gather_off;        /* scattered input gathered back to back (and the offsets it has there) */
   cudaEvent_t gather_done = nullptr;
   bool gather_busy = false;
   PinBuf pin_pack[kShells];             /* PackCounters of the chunk staged in slot c % kShells */
   PinBuf pin_runs, pin_small;
+  unsigned char* pair_box = nullptr;    /* mailbox of the single-pair path: mapped pinned memory (wfa_launch.h: PairBox) */
   uint32_t* user_runs = nullptr;        /* caller-provided destination of the CIGAR runs (wfagpu_set_run_buffer) */
   size_t user_runs_cap = 0;             /* ... and its capacity in words */
   std::vector<wfagpu_batch*> spare;
@@ -511,7 +514,8 @@ extern "C" int wfagpu_create(wfagpu_ctx** out, int device, char* err, size_t err
       (e = cudaStreamCreateWithPriority(&ctx->pack_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaStreamCreateWithPriority(&ctx->d2h_stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&ctx->run_done, cudaEventDisableTiming)) != cudaSuccess ||
-      (e = cudaEventCreateWithFlags(&ctx->gather_done, cudaEventDisableTiming)) != cudaSuccess) {
+      (e = cudaEventCreateWithFlags(&ctx->gather_done, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&ctx->whole_done, cudaEventDisableTiming)) != cudaSuccess) {
     set_err(err, errlen, "CUDA init failed: %s", cudaGetErrorString(e));
     return bail(WFAGPU_ECUDA);
   }
@@ -542,6 +546,7 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& pb : ctx->ring.buf) pb.release();
+  if (ctx->pair_box) cudaFreeHost(ctx->pair_box);
   ctx->gather_seq.release(); ctx->gather_off.release();
   for (auto& pb : ctx->pin_pack) pb.release();
   ctx->pin_runs.release(); ctx->pin_small.release();
@@ -550,7 +555,8 @@ extern "C" void wfagpu_destroy(wfagpu_ctx* ctx) {
   ctx->hist_code.release(); ctx->hmeta.release(); ctx->runs_stage.release(); ctx->gring.release();
   ctx->rhist.release(); ctx->rops.release(); ctx->gscratch.release();
   for (cudaStream_t s : {ctx->stream, ctx->copy_stream, ctx->pack_stream, ctx->d2h_stream}) if (s) cudaStreamDestroy(s);
-  for (cudaEvent_t ev : {ctx->run_done, ctx->gather_done, ctx->ring.ev[0], ctx->ring.ev[1], ctx->ring.ev[2]})
+  ctx->whole_seq.release();
+  for (cudaEvent_t ev : {ctx->run_done, ctx->gather_done, ctx->whole_done, ctx->ring.ev[0], ctx->ring.ev[1], ctx->ring.ev[2]})
     if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < kShells; ++i) {
     if (ctx->uploaded[i]) cudaEventDestroy(ctx->uploaded[i]);
@@ -1251,6 +1257,26 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
     if (n == 0) starts.assign({0, 0});
   }
   const int64_t nchunks = (int64_t)starts.size() - 1;
+  if (nchunks > 1 && in.k_seq != MEM_LOCAL) {
+    /* Pairs in shuffled order: every chunk touches the caller's whole byte range although the range as
+     * a whole is dense.  Upload it once and pack every chunk in place from that copy, instead of
+     * gathering each chunk's pairs on the host. */
+    PairScan c0, all;
+    scan_pairs(p_off, p_len, t_off, t_len, starts[1], 16, &c0);
+    if (c0.first_negative < 0 && c0.hi - c0.lo > 2 * c0.seq_bytes + 65536) {
+      scan_pairs(p_off, p_len, t_off, t_len, n, 16, &all);
+      if (all.first_negative < 0 && all.hi - all.lo <= 2 * all.seq_bytes + 65536) {
+        const size_t span = (size_t)(all.hi - all.lo);
+        CK(ctx->whole_seq.ensure(span + 16));
+        rc = upload(ctx, ctx->whole_seq.p, seq + all.lo, span, in.k_seq, ctx->copy_stream);
+        if (rc != WFAGPU_OK) return rc;
+        CK(cudaEventRecord(ctx->whole_done, ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->pack_stream, ctx->whole_done, 0));
+        in.seq = ctx->whole_seq.as<uint8_t>() - all.lo;      /* device address of the caller's byte 0 */
+        in.k_seq = MEM_LOCAL;
+      }
+    }
+  }
   wfagpu_batch* shells[kShells];
   for (int i = 0; i < kShells; ++i) shells[i] = i < nchunks ? batch_acquire(ctx) : nullptr;
   std::mutex mu;
@@ -1452,6 +1478,62 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
 }
 
 extern "C" int64_t wfagpu_last_launches(const wfagpu_ctx* ctx) { return ctx ? ctx->last_launches : 0; }
+
+/*
+ * One pair, low latency.  Short gap-affine pairs without cut-offs whose penalties the register tier is
+ * instantiated for go through ONE kernel launch that reads the bases from a mapped mailbox and writes the
+ * results back into it (wfa_pair_kernel); everything else is a batch of one.
+ */
+extern "C" int wfagpu_align_pair(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const char* pattern, int32_t plen,
+                                 const char* text, int32_t tlen, int32_t* score, int32_t* status, int32_t* locs,
+                                 const uint32_t** cig_runs, int32_t* n_runs) {
+  if (!ctx || !cfg || plen < 0 || tlen < 0 || (plen && !pattern) || (tlen && !text) || !score || !status)
+    return fail(ctx, WFAGPU_EINVAL, "bad arguments");
+  char msg[400];
+  int rc = wfagpu_config_check(cfg, plen, tlen, msg, sizeof msg);
+  if (rc != WFAGPU_OK) return fail(ctx, rc, "%s", msg);
+  const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
+  KParams k;
+  memset(&k, 0, sizeof k);
+  fill_kparams(*cfg, k);
+  const bool fast = cfg->distance == WFAGPU_DISTANCE_AFFINE && cfg->heuristic == WFAGPU_HEURISTIC_NONE && cfg->wildcard == 0 &&
+                    plen <= PAIR_MAX_LEN && tlen <= PAIR_MAX_LEN && reg_tier_supported(k.dx, k.doe1, k.de1, 4);
+  if (fast) {
+    std::lock_guard<std::mutex> call(ctx->call_mu);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->pair_box) CK(cudaHostAlloc((void**)&ctx->pair_box, PAIR_BOX_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
+    PairBox* box = reinterpret_cast<PairBox*>(ctx->pair_box);
+    box->plen = plen; box->tlen = tlen; box->rc = -1;
+    memcpy(ctx->pair_box + PAIR_ASCII_OFF, pattern, (size_t)plen);
+    memcpy(ctx->pair_box + PAIR_ASCII_OFF + PAIR_TEXT_OFF, text, (size_t)tlen);
+    CK(launch_pair(k, full, box, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_launches = 1;
+    if (box->rc == 0) {
+      *score = box->score; *status = box->status;
+      if (locs) memcpy(locs, box->locs, 16);
+      if (n_runs) *n_runs = box->nruns;
+      if (cig_runs) *cig_runs = reinterpret_cast<const uint32_t*>(ctx->pair_box + PAIR_RUNS_OFF);
+      return WFAGPU_OK;
+    }
+    if (box->rc != 1) return fail(ctx, WFAGPU_ECUDA, "single-pair kernel left no result");
+    /* non-ACGT bytes or a wavefront wider than the window: the batch path takes the pair */
+  }
+  std::string seq;
+  seq.reserve((size_t)plen + tlen + 1);
+  seq.append(pattern ? pattern : "", (size_t)plen).append(text ? text : "", (size_t)tlen).push_back('\0');
+  const int64_t p_off = 0, t_off = plen;
+  int64_t cig_off[2] = {0, 0};
+  int32_t l4[4] = {0, 0, 0, 0};
+  const uint32_t* runs = nullptr;
+  rc = wfagpu_align_batch(ctx, cfg, reinterpret_cast<const uint8_t*>(seq.data()), &p_off, &plen, &t_off, &tlen, 1, score, status,
+                          l4, cig_off, &runs);
+  if (rc != WFAGPU_OK) return rc;
+  if (locs) memcpy(locs, l4, 16);
+  if (n_runs) *n_runs = (int32_t)(cig_off[1] - cig_off[0]);
+  if (cig_runs) *cig_runs = runs + cig_off[0];
+  return WFAGPU_OK;
+}
 
 extern "C" int wfagpu_set_run_buffer(wfagpu_ctx* ctx, uint32_t* buf, int64_t capacity_words) {
   if (!ctx || capacity_words < 0 || (!buf && capacity_words)) return WFAGPU_EINVAL;

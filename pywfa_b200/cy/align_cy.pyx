@@ -1,8 +1,8 @@
 # cython: language_level=3
 # align_cy.pyx -- the Cython host layer over the C ABI: the shape a pywfa maintainer's align.pyx takes
 # when `wavefront_align` (pywfa/align.pyx:421-443) calls libwfagpu instead of WFA2-lib.  One cdef class
-# with pywfa's constructor kwargs; the alignment is one nogil call of wfagpu_align_batch with n = 1 and
-# the result properties read the arrays that call filled (pywfa/align.pyx:731-833 read aligner->cigar).
+# with pywfa's constructor kwargs; the alignment is one nogil call of wfagpu_align_pair (same arguments as
+# wavefront_align) and the result properties read what that call filled (pywfa/align.pyx:731-833 read aligner->cigar).
 # The configuration checks, AlignmentResult and the CIGAR post-processing are shared with the ctypes
 # host layer (pywfa_b200/align.py), which mirrors pywfa/align.pyx:17-295,309-419.
 from libc.stdint cimport int32_t, int64_t, uint8_t, uint32_t
@@ -64,24 +64,22 @@ cdef class WavefrontAligner:
         self.pattern_len = len(p)
         self.text_len = len(t)
         self._host._validate(len(p), len(t))
-        cdef bytes seq = p + t + b"\0"
-        cdef int64_t p_off = 0, t_off = len(p)
-        cdef int32_t p_len = len(p), t_len = len(t)
-        cdef int64_t cig_off[2]
+        cdef const char* pp = p
+        cdef const char* tp = t
+        cdef int32_t p_len = len(p), t_len = len(t), n_runs = 0
         cdef const uint32_t* runs = NULL
-        cdef const uint8_t* sp = <const uint8_t*><const char*>seq
         cdef int rc
-        with nogil:
-            rc = gpu.wfagpu_align_batch(self._ctx, &self._cfg, sp, &p_off, &p_len, &t_off, &t_len, 1,
-                                        &self._score, &self._status, self._locs, cig_off, &runs)
+        with nogil:      # the one call that replaces wavefront_align(aligner, pattern, plen, text, tlen), align.pyx:439
+            rc = gpu.wfagpu_align_pair(self._ctx, &self._cfg, pp, p_len, tp, t_len,
+                                       &self._score, &self._status, self._locs, &runs, &n_runs)
         if rc == -5:
             raise NotImplementedError(gpu.wfagpu_last_error(self._ctx).decode())
         if rc == -1:
             raise ValueError(gpu.wfagpu_last_error(self._ctx).decode())
         if rc != 0:
             raise RuntimeError(gpu.wfagpu_last_error(self._ctx).decode())
-        cdef int64_t i
-        self._cigartuples = [(runs[i] & 15, runs[i] >> 4) for i in range(cig_off[0], cig_off[1])]
+        cdef int32_t i
+        self._cigartuples = [(runs[i] & 15, runs[i] >> 4) for i in range(n_runs)]
         return self._score
 
     @property

@@ -21,5 +21,8 @@ cdef extern from "wfagpu.h" nogil:
                            const int64_t* t_off, const int32_t* t_len, int64_t n,
                            int32_t* score, int32_t* status, int32_t* locs,
                            int64_t* cig_off, const uint32_t** cig_runs)
+    int wfagpu_align_pair(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, const char* pattern, int32_t plen,
+                          const char* text, int32_t tlen, int32_t* score, int32_t* status, int32_t* locs,
+                          const uint32_t** cig_runs, int32_t* n_runs)
     void* wfagpu_host_alloc(size_t nbytes)
     void wfagpu_host_free(void* p)

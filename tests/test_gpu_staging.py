@@ -201,3 +201,43 @@ def test_negative_length_and_free_end_errors(gpu_ctx, oracle):
     # the context stays usable after an error
     cfg = oracle.make_config(span="end-to-end")
     assert_same(gpu_ctx.align_batch(cfg, *batch), oracle.align_batch(cfg, *batch, kind=oracle.checker_kind()), what="after errors")
+
+
+def test_single_pair_entry_point(gpu_ctx, oracle):
+    """wfagpu_align_pair: the one-launch mailbox path (short gap-affine pairs without cut-offs) and its
+    fall-backs to a batch of one (non-ACGT bytes, other distances / cut-offs, long or very divergent pairs)
+    give what the checker gives for the same pairs."""
+    rng = np.random.default_rng(14)
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C"), ("ACGT" * 250, "ACGT" * 250)]
+    for _ in range(120):
+        lp = int(rng.integers(1, 400))
+        p = _rnd(rng, lp)
+        t = _mutate(rng, p, float(rng.choice([0.02, 0.1, 0.3]))) if rng.random() < 0.8 else _rnd(rng, int(rng.integers(1, 400)))
+        pairs.append((p, t))
+    pairs.append((_rnd(rng, 999), _rnd(rng, 1000)))                 # unrelated: wider than the 256-diagonal window
+    pairs.append((_rnd(rng, 1500), _mutate(rng, _rnd(rng, 1500), 0.1)))   # longer than the mailbox takes
+    pairs.append(("ACGTNACGTTTGA", "ACGTAACGTTTGA"))                # N: byte mode
+    pairs.append(("acgtacgtacgt", "ACGTACCTACGT"))                  # lower case packs alike
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(span="end-to-end"), dict(), dict(span="end-to-end", scope="score"),
+               dict(pattern_begin_free=0, pattern_end_free=0, text_begin_free=0, text_end_free=0, match=-1, span="end-to-end"),
+               dict(distance="affine2p"), dict(heuristic="adaptive", span="end-to-end"),
+               dict(span="end-to-end", max_steps=30)):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
+        full = kw.get("scope", "full") == "full"
+        for i, (p, t) in enumerate(pairs):
+            score, status, locs, runs = gpu_ctx.align_pair(cfg, p.encode(), t.encode())
+            assert (score, status) == (int(want["score"][i]), int(want["status"][i])), (kw, i)
+            if full:
+                assert runs == want["runs"][want["cig_off"][i]:want["cig_off"][i + 1]].tolist(), (kw, i)
+                assert locs == want["locs"][i].tolist(), (kw, i)
+            else:
+                assert runs == []
+    # the pywfa surface rides on it
+    import pywfa_b200
+    a = pywfa_b200.WavefrontAligner("TCTTTACTCGCGCGTTGGAGAAATACAATAGT")
+    for _ in range(3):
+        r = a("TCTATACTGCGCGTTTGGAGAAATAAAATAGT")
+        assert (r.score, r.status, r.cigarstring) == (-24, 0, "3M1X4M1D7M1I9M1X6M")
+    assert gpu_ctx.last_launches() >= 0
