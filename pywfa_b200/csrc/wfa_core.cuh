@@ -117,6 +117,7 @@ struct KParams {
   int* retry_list; int* retry_count;
   int* done_count; int* ovf_count;   /* pairs this tier tried so far / of those, beyond its capacity (tier_gives_up) */
   int skip_groups;               /* > 0: groups in flight; a tier that overflows most of its first pairs forwards the rest */
+  int work_limit;                /* this launch takes work items below this index only (host-side probing of a tier) */
   /* results (SoA) */
   int* score; int* status; int* locs; int* nruns; long long* runs_base;
   /* scope=full scratch */

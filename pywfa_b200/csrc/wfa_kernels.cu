@@ -125,7 +125,7 @@ __global__ void wfa_align_kernel(const __grid_constant__ KParams P) {
     gm.h_code = nullptr; gm.hmeta = nullptr; gm.runs_stage = nullptr; gm.ops = nullptr; gm.opcap = 0;
   }
 
-  const int n_work = *P.n_work;
+  const int n_work = min(*P.n_work, P.work_limit);
   long long cells_acc = 0;
   bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
   /* the host zeroed the scratch (barrier count); the reduction sets start at +inf */
   if (g.rank < 3 * (MAX_RED + 1)) (&g.gs->red[0][0])[g.rank] = INT_MAX;
   g.sync();
-  const int n_work = *P.n_work;
+  const int n_work = min(*P.n_work, P.work_limit);
   long long cells_acc = 0;
   bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const _
   /* the run staging re-uses the arena: the backward walk has left it when the replay emits runs */
   uint32_t* const stage = !FULL ? nullptr : HS ? reinterpret_cast<uint32_t*>(hist_p) : K.runs_stage + (long long)warp_id * K.runcap;
 
-  const int n_work = *K.n_work;
+  const int n_work = min(*K.n_work, K.work_limit);
   long long cells_acc = 0;
   for (;;) {
     int w = 0;
@@ -582,7 +582,7 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     return r;
   };
 
-  const int n_work = *P.n_work;
+  const int n_work = min(*P.n_work, P.work_limit);
   long long cells_acc = 0;
   bool gave_up = false;          /* this group's verdict of tier_gives_up */
   for (;;) {
@@ -652,6 +652,24 @@ __global__ void __launch_bounds__(NW == 1 ? 128 : NW * 32, NW == 1 ? 5 : NW == 8
     vec::gsync<NW>();
   }
   if (rank == 0 && cells_acc) atomicAdd(P.cells_total, (unsigned long long)cells_acc);
+}
+
+/* ---- tier probing: hand the untried rest of a work list to the next tier ------------------- */
+__global__ void forward_rest_kernel(const int* __restrict__ worklist, const int* __restrict__ n_work, int from,
+                                    int* __restrict__ retry_list, int* __restrict__ retry_count) {
+  const int n = *n_work;
+  const int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int pid = worklist ? worklist[i] : i;
+  retry_list[atomicAdd(retry_count, 1)] = pid;
+}
+
+cudaError_t launch_forward_rest(const int* worklist, const int* n_work, int from, long long n_bound, int* retry_list,
+                                int* retry_count, cudaStream_t st) {
+  const long long rest = n_bound - from;
+  if (rest <= 0) return cudaSuccess;
+  forward_rest_kernel<<<(int)((rest + 255) / 256), 256, 0, st>>>(worklist, n_work, from, retry_list, retry_count);
+  return cudaGetLastError();
 }
 
 /* ---- CIGAR ordering ------------------------------------------------------------------ */

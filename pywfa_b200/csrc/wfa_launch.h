@@ -66,6 +66,10 @@ size_t grid_scratch_bytes(int groups);
 int grid_occupancy(bool two_p, bool full, size_t smem);   /* resident CTAs per SM */
 cudaError_t launch_grid(const KParams& P, bool two_p, bool full, int groups, int ncta, size_t smem, void* scratch, cudaStream_t st);
 
+/* append work items [from, *n_work) of a tier's work list to its retry list untried (the tier was probed and given up on) */
+cudaError_t launch_forward_rest(const int* worklist, const int* n_work, int from, long long n_bound, int* retry_list,
+                                int* retry_count, cudaStream_t st);
+
 /* ---- single pair (wfa_pair_kernel) ---- */
 constexpr int PAIR_MAX_LEN = 1000;                       /* longest sequence the one-launch path takes */
 constexpr int PAIR_TEXT_OFF = 1024;                      /* text bytes start here in the mailbox's ASCII region */

@@ -1004,14 +1004,41 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         k.retry_count = &dc->retry[li];
         k.done_count = &dc->done[li]; k.ovf_count = &dc->ovf[li];
         if (first_li < 0) { first_li = li; chain_t0 = trace ? now_ms() : 0; }
-        if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
-        else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
-        else if (t.mode == 2) {
-          CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
-          CK(launch_grid(k, b->two_p, b->full, (int)groups, grid_ctas, t.smem, ctx->gscratch.p, st));
+        /* One CTA (or several) per pair and many more pairs than CTAs in flight: probe the tier with one
+         * wave of pairs first.  If three quarters of them exceed its capacity the rest of the queue goes to
+         * the next tier untried (a 10 kbp batch without cut-off otherwise spends a quarter of its time in a
+         * tier every pair overflows); else the same launch index continues with the whole queue. */
+        const bool probing = t.mode != 0 && ti + 1 < bk.tiers.size() && !ctx->knobs.no_tier_skip && nwork >= 3 * groups;
+        k.work_limit = probing ? (int)groups : INT_MAX;
+        auto launch_tier = [&]() -> int {
+          if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
+          else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
+          else if (t.mode == 2) {
+            CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
+            CK(launch_grid(k, b->two_p, b->full, (int)groups, grid_ctas, t.smem, ctx->gscratch.p, st));
+          }
+          else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
+          b->stats.kernel_launches++;
+          return WFAGPU_OK;
+        };
+        { const int r = launch_tier(); if (r != WFAGPU_OK) return r; }
+        if (probing) {
+          CK(cudaMemcpyAsync(hc, dc, sizeof *hc, cudaMemcpyDeviceToHost, st));
+          CK(cudaStreamSynchronize(st));
+          if (4ll * hc->retry[li] >= 3ll * groups) {
+            CK(launch_forward_rest(cur_list, k.n_work, (int)groups, nwork, k.retry_list, k.retry_count, st));
+            b->stats.kernel_launches++;
+            if (trace) fprintf(stderr, "[wfagpu]   bucket %d tier %zu probed with %lld pairs: %d overflowed, the rest is forwarded untried\n",
+                               q, ti, groups, hc->retry[li]);
+          } else {
+            /* go on with the whole queue from where the probe stopped (every group's last, failed fetch
+             * moved the work counter past the probe) */
+            hc->work[li] = (int)groups;
+            CK(cudaMemcpyAsync(&dc->work[li], &hc->work[li], sizeof(int), cudaMemcpyHostToDevice, st));
+            k.work_limit = INT_MAX;
+            const int r = launch_tier(); if (r != WFAGPU_OK) return r;
+          }
         }
-        else CK(launch_align(k, b->two_p, b->full, t.mode, t.off16, blocks, t.threads, t.smem, st));
-        b->stats.kernel_launches++;
         if (trace)
           fprintf(stderr, "[wfagpu]   bucket %d (<= %d bp) tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d)%s\n",
                   q, bk.max_len, ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
