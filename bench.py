@@ -426,6 +426,11 @@ def run_workload(env, name, n_pairs, steps, warmup, want_e2e=True, sample_clocks
         # the job's result arrays: ONE set for all ranks, in shared memory that every rank's copy engine
         # writes its slice of directly (host-side gather without a copy; N = 1: plain pinned arrays)
         runs_cap = int(int(res["cig_off"][-1]) * 1.1) + 4096 if full else 0
+        if env.world > 1 and full:
+            # every rank maps the same segment: the per-rank slice of the run array is the largest any rank needs
+            cap = torch.tensor([runs_cap], device="cuda", dtype=torch.int64)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+            runs_cap = int(cap.item())
         shared = SharedResults(env.world * n_pairs, full, env.rank, env.world, tag=f"bench-{name}", runs_per_rank=runs_cap)
         outs = shared.slices(env.rank * n_pairs, n_pairs)
         if full:

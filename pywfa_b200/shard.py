@@ -159,6 +159,9 @@ class SharedResults:
                 with open(self._path, "wb") as fh:
                     fh.truncate(total)
             dist.barrier()
+            if os.path.getsize(self._path) != total:
+                raise ValueError(f"SharedResults: rank {rank} computed a {total}-byte layout but rank 0 created "
+                                 f"{os.path.getsize(self._path)} bytes: n_total / full / runs_per_rank must agree on all ranks")
             fh = open(self._path, "r+b")
             self._map = mmap.mmap(fh.fileno(), total)
             fh.close()

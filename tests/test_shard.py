@@ -107,3 +107,75 @@ def test_multi_device_threads_on_gpu(oracle):
         got = align_multi_device(cfg, batch, devices)
         for k in ("score", "status", "locs", "cig_off", "runs"):
             assert np.array_equal(got[k], want[k]), k
+
+
+def _shm_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle_py
+    from pywfa_b200.shard import SharedResults
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n_rank = 300
+        ok = True
+        for kw, full in ((dict(span="end-to-end"), True), (dict(scope="score", span="end-to-end"), False)):
+            cfg = oracle_py.make_config(**kw)
+            # every rank owns a part of the job's batch (different divergence: different run counts per rank)
+            part = generate_pairs(n_rank, 150, 0.04 + 0.06 * rank, seed=50 + rank)
+            local = oracle_py.align_batch(cfg, *part, kind="port")
+            cap = torch.tensor([len(local["runs"]) + 16], dtype=torch.int64)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX)
+            shared = SharedResults(world * n_rank, full, rank, world, tag="test-shm", runs_per_rank=int(cap.item()), pin=False)
+            out = shared.slices(rank * n_rank, n_rank)
+            out["score"][:] = local["score"]; out["status"][:] = local["status"]
+            if full:
+                out["locs"][:] = local["locs"]; out["cig_off"][:] = local["cig_off"]
+                shared.run_slice()[:len(local["runs"])] = local["runs"]
+            dist.barrier()
+            if rank == 0:
+                for r in range(world):
+                    want = oracle_py.align_batch(cfg, *generate_pairs(n_rank, 150, 0.04 + 0.06 * r, seed=50 + r), kind="port")
+                    got = shared.slices(r * n_rank, n_rank, rank=r)
+                    ok = ok and np.array_equal(got["score"], want["score"]) and np.array_equal(got["status"], want["status"])
+                    if full:
+                        ok = ok and np.array_equal(got["cig_off"], want["cig_off"]) and np.array_equal(got["locs"], want["locs"])
+                        ok = ok and np.array_equal(shared.run_slice(r)[:len(want["runs"])], want["runs"])
+                shared.touch()
+            del out
+            shared.close()
+            # a rank that disagrees about the layout must fail loudly, not map a short file
+            bad = None
+            try:
+                SharedResults(world * n_rank, True, rank, world, tag="test-shm-bad", runs_per_rank=1000 + 100000 * rank, pin=False)
+            except ValueError as e:
+                bad = e
+            ok = ok and (bad is not None if rank else bad is None)
+            dist.barrier()
+            if rank == 0:
+                try:
+                    os.unlink(f"/dev/shm/test-shm-bad-{port}")
+                except OSError:
+                    pass
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shared_results_two_gloo_ranks(oracle):
+    """The zero-copy gather: both ranks write their shard's results into one shared-memory segment; rank 0
+    reads the whole job's arrays.  Per-rank run counts differ, the layout must still agree."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_shm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = [q.get(timeout=5) for _ in range(2)]
+    assert all(ok for _, ok in res) and {r for r, _ in res} == {0, 1}
