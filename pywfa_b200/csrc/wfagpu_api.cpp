@@ -1104,7 +1104,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
                           b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), nullptr, 0, st));
     CK(launch_cigar_order(b->nruns.as<int>(), b->runs_base.as<long long>(), b->n, b->tile_sums.as<long long>(),
                           b->runs_tmp.as<uint32_t>(), b->cig_off.as<long long>(), b->runs_out.as<uint32_t>(), b->cig_base, st));
-    b->stats.kernel_launches += 3;
+    b->stats.kernel_launches += 4;
   }
   b->ran = true;
   return WFAGPU_OK;
