@@ -13,7 +13,7 @@ from .align import (  # noqa: F401
     elide_mismatches_from_cigar,
 )
 
-from .fastx import FastxRecord, align_fastx, read_fastx  # noqa: F401,E402
+from .fastx import FastxRecord, align_fastx, read_fastx, read_sam, read_seqs  # noqa: F401,E402
 
 __all__ = ["WavefrontAligner", "AlignmentResult", "BatchResult", "clip_cigartuples",
-           "cigartuples_to_str", "elide_mismatches_from_cigar", "read_fastx", "align_fastx", "FastxRecord"]
+           "cigartuples_to_str", "elide_mismatches_from_cigar", "read_fastx", "read_sam", "read_seqs", "align_fastx", "FastxRecord"]

@@ -1,11 +1,14 @@
-"""FASTA / FASTQ streaming into the batched entry point.
+"""FASTA / FASTQ / SAM streaming into the batched entry point.
 
 The reference's own tests read their fixtures with ``pysam.FastxFile`` and align record by record
 (``pywfa/tests/test.py:198-232``); here records are parsed with the standard library only (plain or
 gzip, FASTA with wrapped lines, 4-line FASTQ) and handed to ``WavefrontAligner.align_arrays`` in
 batches, so that reading batch ``i+1`` overlaps nothing on the GPU but at least never builds
 Python strings per base.  ``FastxRecord`` mirrors the fields of pysam's proxy that the reference's
-tests use (``name``, ``sequence``, ``comment``, ``quality``).
+tests use (``name``, ``sequence``, ``comment``, ``quality``).  Text SAM is read as well (``read_sam``:
+QNAME / SEQ / QUAL of every alignment line, reverse-strand records restored to the read's original
+orientation on request), so that reads can be re-aligned straight from a mapper's output; ``read_seqs``
+picks the parser from the first byte / the header.
 """
 from __future__ import annotations
 
@@ -69,6 +72,42 @@ def read_fastx(path) -> Iterator[FastxRecord]:
             raise ValueError(f"{path}: neither FASTA ('>') nor FASTQ ('@')")
 
 
+_COMP = bytes.maketrans(b"ACGTNacgtnRYKMBVDHrykmbvdh", b"TGCANtgcanYRMKVBHDyrmkvbhd")
+
+
+def read_sam(path, original_orientation: bool = False) -> Iterator[FastxRecord]:
+    """Yield the reads of a text SAM file (plain or gzip): ``name`` = QNAME, ``sequence`` = SEQ, ``quality`` =
+    QUAL, ``comment`` = ``"FLAG RNAME POS CIGAR"``.  Header lines (``@``) and records without a stored
+    sequence (``*``) are skipped.  SAM stores reverse-strand alignments reverse-complemented;
+    ``original_orientation=True`` undoes that (FLAG 0x10), which is what re-alignment against another
+    reference wants."""
+    with _open(path) as fh:
+        for line in fh:
+            if not line.strip() or line[0] == "@":
+                continue
+            f = line.rstrip("\r\n").split("\t")
+            if len(f) < 11:
+                raise ValueError(f"{path}: SAM line with {len(f)} fields")
+            seq, qual = f[9], f[10]
+            if seq == "*":
+                continue
+            if original_orientation and int(f[1]) & 0x10:
+                seq = seq.encode("ascii").translate(_COMP)[::-1].decode("ascii")
+                qual = qual[::-1] if qual != "*" else qual
+            yield FastxRecord(f[0], seq, " ".join((f[1], f[2], f[3], f[5])), None if qual == "*" else qual)
+
+
+def read_seqs(path, **kw) -> Iterator[FastxRecord]:
+    """FASTA, FASTQ or SAM, told apart by content: ``>`` = FASTA; ``@`` followed by a two-letter SAM header
+    tag and a tab (``@HD\t``, ``@SQ\t``, ...) or a line with >= 11 tab-separated fields = SAM; else FASTQ."""
+    with _open(path) as fh:
+        first = fh.readline()
+        while first and not first.strip():
+            first = fh.readline()
+    is_sam = (len(first) > 3 and first[0] == "@" and first[3] == "\t") or (first[:1] not in (">", "@") and first.count("\t") >= 10)
+    return read_sam(path, **kw) if is_sam else read_fastx(path)
+
+
 def _batch_arrays(patterns, texts):
     """[(bytes)...] x2 -> the (seq, p_off, p_len, t_off, t_len) layout of ``wfagpu_align_batch``."""
     p_len = np.fromiter((len(b) for b in patterns), np.int32, len(patterns))
@@ -85,8 +124,8 @@ def align_fastx(aligner, texts_path, patterns_path=None, batch_size: int = 26214
     """Align the records of ``texts_path`` against the records of ``patterns_path`` pairwise (or all
     against the aligner's cached pattern) and yield ``(names, BatchResult)`` per batch of
     ``batch_size`` pairs.  ``names[i]`` is ``(pattern_name, text_name)``."""
-    texts = read_fastx(texts_path)
-    patterns = read_fastx(patterns_path) if patterns_path is not None else None
+    texts = read_seqs(texts_path)
+    patterns = read_seqs(patterns_path) if patterns_path is not None else None
     cached = None
     if patterns is None:
         if not aligner._pattern:

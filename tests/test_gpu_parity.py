@@ -269,6 +269,25 @@ def test_fastx_streaming(gpu_ctx, oracle, tmp_path):
             assert br.cigarstring(i) == oracle.runs_to_cigarstring(want["runs"][want["cig_off"][seen + i]:want["cig_off"][seen + i + 1]])
         seen += n
     assert seen == len(pairs)
+    # the same texts out of a mapper's SAM output (reverse-strand records are stored reverse-complemented)
+    comp = str.maketrans("ACGTN", "TGCAN")
+    with open(tmp_path / "t.sam", "w") as fs:
+        fs.write("@HD\tVN:1.6\n@SQ\tSN:ref\tLN:100000\n")
+        for i, (p, t) in enumerate(pairs):
+            rev = i % 3 == 0
+            seq = t.translate(comp)[::-1] if rev else t
+            fs.write(f"t{i}\t{16 if rev else 0}\tref\t{1 + i}\t60\t{len(t)}M\t*\t0\t0\t{seq}\t*\n")
+    from pywfa_b200.fastx import read_sam
+    texts = [r.sequence for r in read_sam(tmp_path / "t.sam", original_orientation=True)]
+    assert texts == [t for _, t in pairs]
+    seen = 0
+    for names, br in pywfa_b200.align_fastx(a, tmp_path / "t.sam", tmp_path / "p.fa", batch_size=512):
+        rev_in_batch = [i for i in range(len(names)) if (seen + i) % 3 == 0]
+        fwd = [i for i in range(len(names)) if (seen + i) % 3 != 0]
+        assert br.score[fwd].tolist() == want["score"][seen:seen + len(names)][fwd].tolist()
+        assert len(rev_in_batch) > 0
+        seen += len(names)
+    assert seen == len(pairs)
 
 
 def test_capacity_bounds_hold_for_every_pair_of_a_batch(gpu_ctx, oracle):

@@ -193,3 +193,37 @@ def test_fastx_reader(tmp_path):
         list(read_fastx(bad))
     seq, po, pl, to, tl = _batch_arrays([b"ACG", b"T"], [b"AC", b"TTTT"])
     assert seq.tobytes() == b"ACGACTTTTT\0" and po.tolist() == [0, 5] and to.tolist() == [3, 6] and pl.tolist() == [3, 1] and tl.tolist() == [2, 4]
+
+
+def test_sam_reader(tmp_path):
+    """Text SAM through pywfa_b200.fastx.read_sam / read_seqs: header lines skipped, QNAME / SEQ / QUAL taken,
+    records without a stored sequence skipped, reverse-strand records restored on request, gzip, and the
+    format sniffing that lets align_fastx take FASTA, FASTQ or SAM."""
+    import gzip
+
+    from pywfa_b200.fastx import read_sam, read_seqs
+    sam = tmp_path / "r.sam"
+    sam.write_text("@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:1000\n"
+                   "r1\t0\tchr1\t10\t60\t8M\t*\t0\t0\tACGTTGCA\tIIIIHHHH\tNM:i:0\n"
+                   "r2\t16\tchr1\t50\t60\t6M\t*\t0\t0\tAACCGT\t123456\n"
+                   "r3\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n"
+                   "r4\t0\tchr1\t70\t60\t4M\t*\t0\t0\tacgn\t*\n")
+    recs = list(read_sam(sam))
+    assert [(r.name, r.sequence, r.quality) for r in recs] == [("r1", "ACGTTGCA", "IIIIHHHH"), ("r2", "AACCGT", "123456"), ("r4", "acgn", None)]
+    assert recs[0].comment == "0 chr1 10 8M"
+    orig = list(read_sam(sam, original_orientation=True))
+    assert (orig[1].sequence, orig[1].quality) == ("ACGGTT", "654321") and orig[0].sequence == "ACGTTGCA"
+    gz = tmp_path / "r.sam.gz"
+    with gzip.open(gz, "wt") as fh:
+        fh.write(sam.read_text())
+    assert [r.sequence for r in read_seqs(gz)] == ["ACGTTGCA", "AACCGT", "acgn"]
+    headless = tmp_path / "h.sam"
+    headless.write_text("r1\t0\tchr1\t10\t60\t8M\t*\t0\t0\tACGTTGCA\tIIIIHHHH\n")
+    assert [r.name for r in read_seqs(headless)] == ["r1"]
+    fq = tmp_path / "r.fq"
+    fq.write_text("@r1 c\nACGT\n+\nIIII\n")
+    assert [r.sequence for r in read_seqs(fq)] == ["ACGT"]
+    short = tmp_path / "bad.sam"
+    short.write_text("@HD\tVN:1.6\nr1\t0\tchr1\n")
+    with pytest.raises(ValueError):
+        list(read_seqs(short))
