@@ -20,10 +20,16 @@ extern "C" {
 #endif
 
 /* ---- enums (values are ABI) -------------------------------------------- */
-/* distance_metric_t, W/wavefront/wavefront_penalties.h:41-47 (only the two
- * gap-affine metrics are on the accelerated path). */
+/* distance_metric_t, W/wavefront/wavefront_penalties.h:41-47.  The gap-affine
+ * metrics have the fast tiers; gap-linear, edit (levenshtein) and indel are
+ * M-only recurrences (W/wavefront/wavefront_compute_linear.c:44-75,
+ * wavefront_compute_edit.c:43-97) and run on the scalar tiers.  For LINEAR the
+ * indel penalty travels in gap_extension1, as in pywfa (align.pyx:352-355). */
 #define WFAGPU_DISTANCE_AFFINE    0
 #define WFAGPU_DISTANCE_AFFINE2P  1
+#define WFAGPU_DISTANCE_LINEAR    2
+#define WFAGPU_DISTANCE_EDIT      3
+#define WFAGPU_DISTANCE_INDEL     4
 /* alignment_scope_t, W/wavefront/wavefront_attributes.h:50-53 */
 #define WFAGPU_SCOPE_SCORE        0
 #define WFAGPU_SCOPE_FULL         1

@@ -39,7 +39,7 @@ class Config(C.Structure):
     _fields_ = [(f, C.c_int32) for f in _FIELDS]
 
 
-_DIST = {"affine": 0, "affine2p": 1}
+_DIST = {"affine": 0, "affine2p": 1, "linear": 2, "levenshtein": 3, "indel": 4}
 _SCOPE = {"score": 0, "full": 1}
 _SPAN = {"end-to-end": 0, "ends-free": 1}
 _HEUR = {None: 0, "adaptive": 1, "X-drop": 2}

@@ -28,7 +28,16 @@ typedef struct {
 /* kwargs -> wavefront_aligner_attr_t, exactly as pywfa/align.pyx:343-417 */
 void* ref_new(const wfagpu_config_t* cfg, int memory_mode) {
   wavefront_aligner_attr_t attr = wavefront_aligner_attr_default;
-  if (cfg->distance == WFAGPU_DISTANCE_AFFINE) {
+  if (cfg->distance == WFAGPU_DISTANCE_INDEL) {
+    attr.distance_metric = indel;                     /* align.pyx:347-348 */
+  } else if (cfg->distance == WFAGPU_DISTANCE_EDIT) {
+    attr.distance_metric = edit;                      /* align.pyx:349-350 */
+  } else if (cfg->distance == WFAGPU_DISTANCE_LINEAR) {
+    attr.distance_metric = gap_linear;                /* align.pyx:351-355 */
+    attr.linear_penalties.match = cfg->match;
+    attr.linear_penalties.mismatch = cfg->mismatch;
+    attr.linear_penalties.indel = cfg->gap_extension1;
+  } else if (cfg->distance == WFAGPU_DISTANCE_AFFINE) {
     attr.distance_metric = gap_affine;
     attr.affine_penalties.match = cfg->match;
     attr.affine_penalties.mismatch = cfg->mismatch;

@@ -54,6 +54,9 @@ typedef struct {
   /* normalised penalties, W/wavefront/wavefront_penalties.c:95-173 */
   int match, x, o1, e1, o2, e2;
   int affine2p;
+  int m_only;            /* gap-linear / edit / indel: M wavefronts only (compute_linear.c, compute_edit.c) */
+  int no_mis;            /* indel: no mismatch source */
+  int edit_like;         /* edit / indel: compute_edit.c's driver (no null steps, positive scores) */
   int max_scope;         /* W/wavefront/wavefront_components.c:81-124 */
   int plen, tlen;
   const char* p;
@@ -112,6 +115,24 @@ static inline int comp_null(const oracle_t* o, int s, int c) {
 static void set_penalties(oracle_t* o) {
   const wfagpu_config_t* c = &o->cfg;
   o->affine2p = (c->distance == WFAGPU_DISTANCE_AFFINE2P);
+  o->m_only = o->no_mis = o->edit_like = 0;
+  if (c->distance == WFAGPU_DISTANCE_LINEAR) {
+    /* wavefront_penalties_set_linear, penalties.c:62-93: the indel penalty sits in gap_opening1; here it
+     * is the "extension" of a zero-cost opening, so that s - o1 - e1 addresses the open source */
+    o->m_only = 1;
+    o->o1 = 0; o->o2 = 0; o->e2 = 1;
+    if (c->match < 0) { o->match = c->match; o->x = 2 * c->mismatch - 2 * c->match; o->e1 = 2 * c->gap_extension1 - c->match; }
+    else { o->match = 0; o->x = c->mismatch; o->e1 = c->gap_extension1; }
+    o->max_scope = MAXI(o->x, o->e1) + 1;                /* components.c:60-66 */
+    return;
+  }
+  if (c->distance == WFAGPU_DISTANCE_EDIT || c->distance == WFAGPU_DISTANCE_INDEL) {
+    /* wavefront_penalties_set_edit / _indel, penalties.c:38-61 */
+    o->m_only = 1; o->edit_like = 1; o->no_mis = (c->distance == WFAGPU_DISTANCE_INDEL);
+    o->match = 0; o->x = 1; o->o1 = 0; o->e1 = 1; o->o2 = 0; o->e2 = 1;
+    o->max_scope = 2;                                    /* components_dimensions_edit, components.c:44-58 */
+    return;
+  }
   if (c->match < 0) {
     o->match = c->match;
     o->x = 2 * c->mismatch - 2 * c->match;
@@ -133,6 +154,7 @@ static void set_penalties(oracle_t* o) {
 /* wavefront_compute_classic_score, compute.c:108-120 */
 static int classic_score(const oracle_t* o, int plen, int tlen, int wf_score) {
   const int swg_match = -o->match;
+  if (o->edit_like) return wf_score;                     /* distance_metric <= edit, compute.c:117 */
   if (swg_match == 0) return -wf_score;
   /* WF_SCORE_TO_SW_SCORE, penalties.h:73 (int32 wrap-around, C truncating division) */
   const int32_t sum = (int32_t)((uint32_t)plen + (uint32_t)tlen);
@@ -322,6 +344,29 @@ static inline int inbounds(const oracle_t* o, int k, int32_t off) {
   const uint32_t h = (uint32_t)off, v = (uint32_t)(off - k);
   return h <= (uint32_t)o->tlen && v <= (uint32_t)o->plen;
 }
+
+/* wavefront_compute_edit_exact_prune, compute_edit.c:198-275: on wavefronts of >= 1000 diagonals drop the ends
+ * whose best case |remaining v - remaining h| is worse than the best worst case max(remaining v, remaining h) */
+static void edit_exact_prune(const oracle_t* o, wfset_t* w) {
+  const int lo = w->lo[CM], hi = w->hi[CM];
+  if (hi - lo + 1 < 1000) return;
+  const int32_t* off = w->off[CM] - w->clo;
+  const int ak = o->tlen - o->plen;
+#define EBEST(k) ((k) >= ak ? (k) - ak : ak - (k))
+#define EWORST(k) MAXI(o->plen - (off[k] - (k)), o->tlen - off[k])
+  const int sample_k = lo + (hi - lo) / 2;
+  if (off[sample_k] < 0) return;
+  const int smax = EWORST(sample_k);
+  if (EBEST(lo) <= smax && EBEST(hi) <= smax) return;
+  int min_worst = INT_MAX;
+  for (int k = lo; k <= hi; ++k) if (off[k] >= 0) min_worst = MINI(min_worst, EWORST(k));
+  int nlo = lo, nhi = hi;
+  for (int k = lo; k <= hi; ++k) { if (EBEST(k) <= min_worst) break; ++nlo; }
+  for (int k = hi; k > nlo; --k) { if (EBEST(k) <= min_worst) break; --nhi; }
+#undef EBEST
+#undef EWORST
+  w->lo[CM] = nlo; w->hi[CM] = nhi;
+}
 /* wavefront_compute_trim_ends, compute.c:571-605 */
 static void trim(const oracle_t* o, wfset_t* w, int c) {
   const int32_t* off = w->off[c] - w->clo;
@@ -337,13 +382,23 @@ static void compute_step(oracle_t* o, int s) {
   const int so2 = s - o->o2 - o->e2, se2 = s - o->e2;
   wfset_t* w = wf_at(o, s);          /* may realloc o->wf: take it before any other pointer */
   /* fetch_input + null tests, compute.c:298-344, compute_affine.c:235-244, affine2p.c:340-353 */
-  const int n_mx = comp_null(o, sx, CM), n_mo1 = comp_null(o, so1, CM);
-  const int n_i1 = comp_null(o, se1, CI1), n_d1 = comp_null(o, se1, CD1);
+  const int n_mx = o->no_mis ? 1 : comp_null(o, sx, CM), n_mo1 = comp_null(o, so1, CM);
+  const int n_i1 = o->m_only ? 1 : comp_null(o, se1, CI1), n_d1 = o->m_only ? 1 : comp_null(o, se1, CD1);
   const int n_mo2 = two ? comp_null(o, so2, CM) : 1;
   const int n_i2 = two ? comp_null(o, se2, CI2) : 1, n_d2 = two ? comp_null(o, se2, CD2) : 1;
   const int ef_req = endsfree_required(o, s);
   const int efk = ef_req ? s / (-o->match) : 0;
   const int ef_t = ef_req && (o->tbf >= efk), ef_p = ef_req && (o->pbf >= efk);
+  if (o->edit_like && n_mo1) {
+    /* wavefront_compute_edit (compute_edit.c:329-374) has no null step: a null predecessor yields a null
+     * wavefront and num_null_steps = INT_MAX, i.e. "unreachable" at the next extend */
+    o->num_null_steps = INT_MAX;
+    w->exists = 1; w->clo = 0; w->chi = 0;
+    w->off[CM] = (int32_t*)malloc(sizeof(int32_t));
+    w->off[CM][0] = OFFSET_NULL;
+    if (o->bt_mode) w->code = (uint8_t*)calloc(1, 1);
+    return;
+  }
   if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
     o->num_null_steps++;
     /* allocate_output_null, compute.c:374-400; endsfree_allocate_null :208-254.
@@ -370,8 +425,11 @@ static void compute_step(oracle_t* o, int s) {
 #define HI_OF(isnull, sc, c) ((isnull) ? -1 : o->wf[sc].hi[c])
   int lo = LO_OF(n_mx, sx, CM), hi = HI_OF(n_mx, sx, CM);
   lo = MINI(lo, LO_OF(n_mo1, so1, CM) - 1); hi = MAXI(hi, HI_OF(n_mo1, so1, CM) + 1);
-  lo = MINI(lo, LO_OF(n_i1, se1, CI1) + 1); hi = MAXI(hi, HI_OF(n_i1, se1, CI1) + 1);
-  lo = MINI(lo, LO_OF(n_d1, se1, CD1) - 1); hi = MAXI(hi, HI_OF(n_d1, se1, CD1) - 1);
+  if (o->edit_like) { lo = o->wf[so1].lo[CM] - 1; hi = o->wf[so1].hi[CM] + 1; }   /* compute_edit.c:346-347 */
+  if (!o->m_only) {                                                              /* compute.c:52-58: gap-linear stops here */
+    lo = MINI(lo, LO_OF(n_i1, se1, CI1) + 1); hi = MAXI(hi, HI_OF(n_i1, se1, CI1) + 1);
+    lo = MINI(lo, LO_OF(n_d1, se1, CD1) - 1); hi = MAXI(hi, HI_OF(n_d1, se1, CD1) - 1);
+  }
   if (two) {
     lo = MINI(lo, LO_OF(n_mo2, so2, CM) - 1); hi = MAXI(hi, HI_OF(n_mo2, so2, CM) + 1);
     lo = MINI(lo, LO_OF(n_i2, se2, CI2) + 1); hi = MAXI(hi, HI_OF(n_i2, se2, CI2) + 1);
@@ -382,7 +440,7 @@ static void compute_step(oracle_t* o, int s) {
   if (ef_t) { chi = MAXI(chi, efk); clo = MINI(clo, efk); }
   if (ef_p) { clo = MINI(clo, -efk); chi = MAXI(chi, -efk); }
   const size_t width = (size_t)(chi - clo + 1);
-  const int has[NCOMP] = {1, !n_mo1 || !n_i1, !n_mo1 || !n_d1,
+  const int has[NCOMP] = {1, !o->m_only && (!n_mo1 || !n_i1), !o->m_only && (!n_mo1 || !n_d1),
                           two && (!n_mo2 || !n_i2), two && (!n_mo2 || !n_d2)};
   w->exists = 1; w->clo = clo; w->chi = chi;
   for (int c = 0; c < NCOMP; ++c) {
@@ -399,7 +457,7 @@ static void compute_step(oracle_t* o, int s) {
     const int32_t ins1 = MAXI(i1o, i1e) + 1;
     const int32_t d1o = rd(o, so1, CM, k + 1), d1e = rd(o, se1, CD1, k + 1);
     const int32_t del1 = MAXI(d1o, d1e);
-    const int32_t misms = rd(o, sx, CM, k) + 1;
+    const int32_t misms = o->no_mis ? OFFSET_NULL : rd(o, sx, CM, k) + 1;
     int32_t ins = ins1, del = del1;
     int32_t ins2 = OFFSET_NULL, del2 = OFFSET_NULL;
     int32_t i2o = OFFSET_NULL, i2e = OFFSET_NULL, d2o = OFFSET_NULL, d2e = OFFSET_NULL;
@@ -454,6 +512,11 @@ static void compute_step(oracle_t* o, int s) {
     }
   }
   for (int c = 0; c < NCOMP; ++c) if (has[c]) trim(o, w, c);
+  if (o->edit_like) {
+    /* compute_edit.c:367-373 */
+    if (w->lo[CM] > w->hi[CM]) o->num_null_steps = INT_MAX;
+    else if (!o->no_mis && o->cfg.span == WFAGPU_SPAN_END2END) edit_exact_prune(o, w);
+  }
 }
 
 /* ---- backtrace ------------------------------------------------------------------------ */
@@ -516,7 +579,7 @@ static void backtrace(oracle_t* o, cigar_buf_t* cg, int a_score, int a_k, int32_
                                     bt_cand(o, se2, CD2, k + 1, 0, BT_D2_EXT)) : OFFSET_NULL;
       switch (mt) {
         case CM: {
-          const int64_t ms = bt_cand(o, sx, CM, k, 1, BT_M);
+          const int64_t ms = o->no_mis ? OFFSET_NULL : bt_cand(o, sx, CM, k, 1, BT_M);   /* backtrace.c:261-263 */
           best = two ? MAXI(ms, MAXI(MAXI(i1, i2), MAXI(d1, d2))) : MAXI(ms, MAXI(i1, d1));
           break;
         }
@@ -579,6 +642,24 @@ static int maxtrim_affine(const oracle_t* o, cigar_buf_t* cg) {
       case 'D': score -= c->gap_extension1 + ((last == 'D') ? 0 : c->gap_opening1); break;
     }
     last = cg->ops[i];
+    if (max_score < score) { max_score = score; max_off = i; }
+  }
+  const int trimmed = (max_off != cg->end - 1);
+  if (max_score == 0) { cg->begin = cg->end = 0; cg->score = INT32_MIN; }
+  else { cg->end = max_off + 1; cg->score = max_score; }
+  return trimmed;
+}
+/* cigar_maxtrim_gap_linear, W/alignment/cigar.c:419-472 (user penalties; the indel penalty travels in gap_extension1) */
+static int maxtrim_linear(const oracle_t* o, cigar_buf_t* cg) {
+  const wfagpu_config_t* c = &o->cfg;
+  const int match_score = (c->match != 0) ? c->match : -1;
+  int max_score = 0, max_off = cg->begin, score = 0;
+  for (int i = cg->begin; i < cg->end; ++i) {
+    switch (cg->ops[i]) {
+      case 'M': score -= match_score; break;
+      case 'X': score -= c->mismatch; break;
+      default: score -= c->gap_extension1; break;
+    }
     if (max_score < score) { max_score = score; max_off = i; }
   }
   const int trimmed = (max_off != cg->end - 1);
@@ -685,8 +766,11 @@ int oracle_align(const wfagpu_config_t* cfg, int bt_mode,
     } else {
       if (o.end_off != OFFSET_NULL) backtrace(&o, &cg, score, o.end_k, o.end_off);
       if (unreachable) {
-        const int trimmed = o.affine2p ? maxtrim_affine2p(&o, &cg) : maxtrim_affine(&o, &cg);
-        (void)trimmed;
+        /* wavefront_aligner_maxtrim_cigar, aligner.c:663-675: does not apply to edit / indel */
+        if (o.edit_like) { /* the CIGAR and the score the backtrace left stay as they are */ }
+        else if (o.m_only) (void)maxtrim_linear(&o, &cg);
+        else if (o.affine2p) (void)maxtrim_affine2p(&o, &cg);
+        else (void)maxtrim_affine(&o, &cg);
         status = WFAGPU_STATUS_PARTIAL;
       } else {
         cg.score = classic_score(&o, o.end_off - o.end_k, o.end_off, score);

@@ -11,9 +11,12 @@ through ``libwfagpu.so``; there is no CPU fallback.
 
 Intentional deviations from the reference:
   * configurations the reference ``exit(1)``s on raise ``ValueError`` before any launch;
-  * distances other than ``affine`` / ``affine2p`` and ``memory_mode="biwfa"`` (different
-    tie-breaks) raise ``NotImplementedError``; non-ACGT bases and the wildcard are aligned in
-    the library's byte mode;
+  * ``memory_mode="biwfa"`` (different tie-breaks) raises ``NotImplementedError``; non-ACGT bases
+    and the wildcard are aligned in the library's byte mode;
+  * ``distance="linear" | "levenshtein" | "indel"`` are aligned by the scalar tiers only (no
+    register / packed-halfword kernels for them).  Changing ``distance`` after construction keeps
+    the constructor's penalties (the reference's setter re-reads per-metric copies that it only
+    initialised for the constructor's metric, ``align.pyx:610-620``);
   * ``span="end-to-end"`` ignores the ``*_begin_free`` / ``*_end_free`` values.  pywfa copies them
     into ``alignment_form`` regardless of the span, and WFA2-lib then still seeds wavefront 0 with
     ``lo = -pattern_begin_free, hi = text_begin_free`` (``wavefront_aligner.c:260-261``) while
@@ -40,8 +43,8 @@ __all__ = ["WavefrontAligner", "AlignmentResult", "BatchResult", "clip_cigartupl
 INT_MAX = 2 ** 31 - 1
 _CIGAR_LETTERS = "MIDNSHP=XB"          # SAM op codes, pywfa/align.pyx:11-14 / :290
 
-_DISTANCES = {"affine": 0, "affine2p": 1}
-_UNACCELERATED = ("indel", "levenshtein", "linear")
+_DISTANCES = {"affine": 0, "affine2p": 1, "linear": 2, "levenshtein": 3, "indel": 4}     # wfagpu.h WFAGPU_DISTANCE_*
+_DISTANCE_NAMES = {v: k for k, v in _DISTANCES.items()}
 _SCOPES = {"score": 0, "full": 1}
 _SPANS = {"end-to-end": 0, "ends-free": 1}
 _HEURISTICS = {None: 0, "adaptive": 1, "X-drop": 2}
@@ -290,15 +293,15 @@ class WavefrontAligner:
         self._cfg = _ffi.Config()
         self._device = device
         self.wildcard = wildcard
-        if distance in _UNACCELERATED:
-            raise NotImplementedError(f"{distance} distance is not on the B200 accelerated path "
-                                      "(affine, affine2p)")
         if distance not in _DISTANCES:
             raise NotImplementedError(f'{distance} distance not implemented')
         self._cfg.distance = _DISTANCES[distance]
-        self._cfg.match, self._cfg.mismatch = int(match), int(mismatch)
-        self._cfg.gap_opening1, self._cfg.gap_extension1 = int(gap_opening), int(gap_extension)
-        self._cfg.gap_opening2, self._cfg.gap_extension2 = int(gap_opening2), int(gap_extension2)
+        # the caller's penalties; gap-linear's single indel penalty is the constructor's
+        # gap_extension (align.pyx:351-355) and follows both gap setters afterwards (:675, :684)
+        self._pen = dict(match=int(match), mismatch=int(mismatch), gap_opening1=int(gap_opening),
+                         gap_extension1=int(gap_extension), gap_opening2=int(gap_opening2),
+                         gap_extension2=int(gap_extension2), indel=int(gap_extension))
+        self._sync_penalties()
         if scope not in _SCOPES:
             raise ValueError(f'{scope} scope not understood')
         self._cfg.scope = _SCOPES[scope]
@@ -346,11 +349,29 @@ class WavefrontAligner:
         if rc != _ffi.OK:
             raise ValueError(err.value.decode())
 
+    def _sync_penalties(self):
+        """caller's penalties -> the configuration the library reads (gap-linear: the indel
+        penalty travels in gap_extension1, include/wfagpu.h)"""
+        c, u = self._cfg, self._pen
+        c.match, c.mismatch = u["match"], u["mismatch"]
+        c.gap_opening1 = u["gap_opening1"]
+        c.gap_extension1 = u["indel"] if c.distance == 2 else u["gap_extension1"]
+        c.gap_opening2, c.gap_extension2 = u["gap_opening2"], u["gap_extension2"]
+
     def _normalised(self):
         """(match, mismatch, o1, e1, o2, e2) as WFA2-lib stores them after
         wavefront_penalties_set_* (Eizenga's transform when match < 0; -1 for the unused
-        piece-2 penalties of gap-affine), which is what the reference's getters return."""
+        penalties of the metric, W/wavefront/wavefront_penalties.c:38-173), which is what the
+        reference's getters return."""
         c = self._cfg
+        if c.distance == 4:
+            return [0, -1, 1, -1, -1, -1]
+        if c.distance == 3:
+            return [0, 1, 1, -1, -1, -1]
+        if c.distance == 2:
+            if c.match < 0:
+                return [c.match, 2 * c.mismatch - 2 * c.match, 2 * c.gap_extension1 - c.match, -1, -1, -1]
+            return [0, c.mismatch, c.gap_extension1, -1, -1, -1]
         if c.match < 0:
             vals = [c.match, 2 * c.mismatch - 2 * c.match, 2 * c.gap_opening1,
                     2 * c.gap_extension1 - c.match, 2 * c.gap_opening2, 2 * c.gap_extension2 - c.match]
@@ -429,28 +450,37 @@ class WavefrontAligner:
 
     @property
     def distance(self):
-        return "affine2p" if self._cfg.distance == 1 else "affine"
+        return _DISTANCE_NAMES[self._cfg.distance]
 
     @distance.setter
     def distance(self, distance):
-        if distance in _UNACCELERATED:
-            raise NotImplementedError(f"{distance} distance is not on the B200 accelerated path")
         if distance not in _DISTANCES:
             raise NotImplementedError(f'{distance} distance not implemented')
+        old = self._cfg.distance
         self._cfg.distance = _DISTANCES[distance]
-        self._validate()
+        self._sync_penalties()
+        try:
+            self._validate()
+        except Exception:
+            self._cfg.distance = old
+            self._sync_penalties()
+            raise
 
     def _penalty_prop(field, index):                          # noqa: N805
         def get(self):
             return self._normalised()[index]
 
         def set_(self, value):
-            old = getattr(self._cfg, field)
-            setattr(self._cfg, field, int(value))
+            old = dict(self._pen)
+            self._pen[field] = int(value)
+            if field in ("gap_opening1", "gap_extension1"):
+                self._pen["indel"] = int(value)
+            self._sync_penalties()
             try:
                 self._validate()
             except Exception:
-                setattr(self._cfg, field, old)
+                self._pen = old
+                self._sync_penalties()
                 raise
         return property(get, set_)
 

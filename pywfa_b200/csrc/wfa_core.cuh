@@ -89,6 +89,11 @@ struct KParams {
   /* normalised penalties (W/wavefront/wavefront_penalties.c:95-173) */
   int x, o1, e1, o2, e2, match;
   int max_scope;                 /* W/wavefront/wavefront_components.c:81-124 (original units) */
+  /* gap-linear / edit / indel (W/wavefront/wavefront_compute_linear.c, wavefront_compute_edit.c): M wavefronts
+   * only (the gap sources are the "open" sources of a zero-cost opening); indel has no mismatch source;
+   * edit / indel run compute_edit.c's driver (no null steps, range = previous range +-1, positive scores) */
+  int m_only, no_mis, edit_like;
+  int edit_prune;                /* edit, end-to-end: wavefront_compute_edit_exact_prune (compute_edit.c:219-275) */
   /* score unit g = gcd(x, o1+e1, e1[, o2+e2, e2]) and the penalties in that unit */
   int g, dx, doe1, de1, doe2, de2;
   int rm, r1, r2;                /* ring slots: M, I1/D1, I2/D2 (scaled look-back + 1) */
@@ -264,8 +269,9 @@ WFA_DEV bool in_bounds(int k, int off, int plen, int tlen) {
 
 /* wavefront_compute_classic_score, W/wavefront/wavefront_compute.c:108-120 with
  * WF_SCORE_TO_SW_SCORE (wavefront_penalties.h:73): int32 wrap-around, C truncating division */
-WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score) {
+WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score, int edit_like = 0) {
   const int swg_match = -match;
+  if (edit_like) return wf_score;               /* distance_metric <= edit, compute.c:117 */
   if (swg_match == 0) return -wf_score;
   const int32_t sum = (int32_t)((uint32_t)plen + (uint32_t)tlen);
   const int32_t prod = (int32_t)((uint32_t)swg_match * (uint32_t)sum);
@@ -583,11 +589,11 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     if (TWO_P) { if (++c2 == P.r2) c2 = 0; }
     {
       /* fetch_input, compute.c:298-344: one 16-byte metadata read per source component */
-      const int4 aMx = meta[((s - P.dx) & mmask) * NC + CM];
+      int4 aMo2 = make_int4(1, -1, 0, 0), aI2 = aMo2, aD2 = aMo2;
+      const int4 aMx = P.no_mis ? aMo2 : meta[((s - P.dx) & mmask) * NC + CM];
       const int4 aMo1 = meta[((s - P.doe1) & mmask) * NC + CM];
       const int4* const rowe1 = meta + ((s - P.de1) & mmask) * NC;
-      const int4 aI1 = rowe1[CI1], aD1 = rowe1[CD1];
-      int4 aMo2 = make_int4(1, -1, 0, 0), aI2 = aMo2, aD2 = aMo2;
+      const int4 aI1 = P.m_only ? aMo2 : rowe1[CI1], aD1 = P.m_only ? aMo2 : rowe1[CD1];
       if (TWO_P) {
         aMo2 = meta[((s - P.doe2) & mmask) * NC + CM];
         const int4* const rowe2 = meta + ((s - P.de2) & mmask) * NC;
@@ -598,8 +604,9 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
       const bool n_i2 = TWO_P ? aI2.x > aI2.y : true;
       const bool n_d2 = TWO_P ? aD2.x > aD2.y : true;
       int4* const mrow = meta + (s & mmask) * NC;
-      if (n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) {
-        /* null step: allocate_output_null, compute.c:374-400 */
+      if ((n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) || (P.edit_like && n_mo1)) {
+        /* null step: allocate_output_null, compute.c:374-400.  wavefront_compute_edit (compute_edit.c:329-374)
+         * has no null steps: a null predecessor sets num_null_steps = INT_MAX, "unreachable" at once (below) */
         cur_exists = false;
         for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
         term_k = KNONE;
@@ -620,8 +627,11 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         /* wavefront_compute_limits_input, compute.c:40-86 (null inputs carry lo=1, hi=-1) */
         int lo = sMx.lo, hi = sMx.hi;
         lo = imin(lo, sMo1.lo - 1); hi = imax(hi, sMo1.hi + 1);
-        lo = imin(lo, sI1.lo + 1); hi = imax(hi, sI1.hi + 1);
-        lo = imin(lo, sD1.lo - 1); hi = imax(hi, sD1.hi - 1);
+        if (P.edit_like) { lo = sMo1.lo - 1; hi = sMo1.hi + 1; }     /* compute_edit.c:346-347 */
+        if (!P.m_only) {                                             /* compute.c:52-58: gap-linear stops at the M sources */
+          lo = imin(lo, sI1.lo + 1); hi = imax(hi, sI1.hi + 1);
+          lo = imin(lo, sD1.lo - 1); hi = imax(hi, sD1.hi - 1);
+        }
         if (TWO_P) {
           lo = imin(lo, sMo2.lo - 1); hi = imax(hi, sMo2.hi + 1);
           lo = imin(lo, sI2.lo + 1); hi = imax(hi, sI2.hi + 1);
@@ -631,7 +641,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         if (width > wcap) return PAIR_OVERFLOW;
         if (FULL) { if (s >= P.scap || cell_off + width > P.hcap) return PAIR_OVERFLOW; }
         /* allocate_output, compute.c:401-486 */
-        const bool has_i1 = !n_mo1 || !n_i1, has_d1 = !n_mo1 || !n_d1;
+        const bool has_i1 = !P.m_only && (!n_mo1 || !n_i1), has_d1 = !P.m_only && (!n_mo1 || !n_d1);
         const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
         OffT* const oM = gm.ring[CM] + cm * wcap;
         OffT* const oI1 = gm.ring[CI1] + c1 * wcap;
@@ -701,6 +711,36 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           if (c < NC && has[c] && red[2 * c] != INT_MAX) { clo[c] = red[2 * c]; chi[c] = -red[2 * c + 1]; }
           else { clo[c] = 1; chi[c] = -1; }
         }
+        if (P.edit_prune && chi[CM] - clo[CM] + 1 >= 1000) {
+          /* exact pruning of the ends whose best case |k - ak| is worse than the best worst case
+           * max(remaining v, remaining h); the reference looks at the offsets BEFORE their extension,
+           * which are recomputed here from the sources (the slot now holds the extended ones) */
+          const int lo_t = clo[CM], hi_t = chi[CM];
+          auto pre = [&](int k) {
+            const int km = k & wmask, kl = (k - 1) & wmask, kr = (k + 1) & wmask;
+            const int v = imax(rd<G::kGrid>(sMo1, k + 1, kr), imax(rd<G::kGrid>(sMx, k, km), rd<G::kGrid>(sMo1, k - 1, kl)) + 1);
+            return in_bounds(k, v, plen, tlen) ? v : OFFNULL;
+          };
+          auto best = [&](int k) { return k >= ak ? k - ak : ak - k; };
+          const int sample_k = lo_t + (hi_t - lo_t) / 2;
+          const int so = pre(sample_k);
+          const int smax = imax(plen - (so - sample_k), tlen - so);
+          if (so >= 0 && !(best(lo_t) <= smax && best(hi_t) <= smax)) {
+            int mw = INT_MAX;
+            for (int k = lo_t + g.rank; k <= hi_t; k += g.size) {
+              const int f = pre(k);
+              if (f >= 0) mw = imin(mw, imax(plen - (f - k), tlen - f));
+            }
+            int r1[1] = {mw};
+            g.template allmin<1>(r1);
+            mw = r1[0];
+            /* best(k) is |k - ak|: the surviving range is [ak - mw, ak + mw] clipped, scanned as the reference does */
+            int nlo = lo_t, nhi = hi_t;
+            while (nlo <= hi_t && best(nlo) > mw) ++nlo;
+            while (nhi > nlo && best(nhi) > mw) --nhi;
+            clo[CM] = nlo; chi[CM] = nhi;
+          }
+        }
         cur_exists = true;
         for (int c = g.lrank; c < NC; c += g.lsize) {
           /* lane c publishes component c */
@@ -726,7 +766,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     {
       const int so = s * P.g;
       if (!cur_exists) {
-        const int su = s_exist + P.max_scope + 1;
+        const int su = P.edit_like ? so : s_exist + P.max_scope + 1;
         if (su <= so && su < P.max_steps) { status = 2; end_score = su; break; }
       }
       if (so >= P.max_steps) {
@@ -744,11 +784,11 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
   if (status == 3) {
     res.score = -P.max_steps; res.status = ST_MAX_STEPS;
   } else if (!FULL) {
-    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score); res.status = ST_COMPLETED; }
+    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score, P.edit_like); res.status = ST_COMPLETED; }
     else {
       /* end position was never assigned: end_v = NULL - DIAGONAL_NULL with int32 wrap */
       const int32_t end_v = (int32_t)((uint32_t)OFFNULL - (uint32_t)INT_MAX);
-      res.score = classic_score(P.match, end_v, OFFNULL, end_score); res.status = ST_PARTIAL;
+      res.score = classic_score(P.match, end_v, OFFNULL, end_score, P.edit_like); res.status = ST_PARTIAL;
     }
   } else {
     if (status == 1) {
@@ -758,7 +798,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         res.nruns = n;
         if (n >= 0) locations_from_runs(gm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }
-      res.score = classic_score(P.match, end_off - end_k, end_off, end_score);
+      res.score = classic_score(P.match, end_off - end_k, end_off, end_score, P.edit_like);
       res.status = ST_COMPLETED;
     } else {
       /* dropped: no end position -> empty CIGAR; maxtrim on an empty CIGAR clears the

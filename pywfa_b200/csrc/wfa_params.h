@@ -24,9 +24,20 @@ inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
     k.o1 = c.gap_opening1; k.e1 = c.gap_extension1;
     k.o2 = c.gap_opening2; k.e2 = c.gap_extension2;
   }
+  k.m_only = k.no_mis = k.edit_like = k.edit_prune = 0;
+  if (c.distance == WFAGPU_DISTANCE_LINEAR) {
+    /* wavefront_penalties_set_linear, penalties.c:62-93: one indel penalty (carried in gap_extension1 as pywfa does,
+     * align.pyx:351-355), here the extension of a zero-cost opening: s - o1 - e1 addresses the gap source */
+    k.m_only = 1; k.o1 = 0;
+  } else if (c.distance == WFAGPU_DISTANCE_EDIT || c.distance == WFAGPU_DISTANCE_INDEL) {
+    /* wavefront_penalties_set_edit / _indel, penalties.c:38-61 */
+    k.m_only = k.edit_like = 1; k.no_mis = c.distance == WFAGPU_DISTANCE_INDEL;
+    k.edit_prune = c.distance == WFAGPU_DISTANCE_EDIT && c.span == WFAGPU_SPAN_END2END;
+    k.match = 0; k.x = 1; k.o1 = 0; k.e1 = 1;
+  }
   int scope_indel = k.o1 + k.e1;
   if (two_p) scope_indel = std::max(scope_indel, k.o2 + k.e2);
-  k.max_scope = std::max(scope_indel, k.x) + 1;
+  k.max_scope = k.edit_like ? 2 : std::max(scope_indel, k.x) + 1;     /* components.c:44-66 / :81-124 */
   if (!two_p) { k.o2 = 0; k.e2 = 1; }
   /* every reachable score is a sum of x, o+e and e terms: step in units of their gcd */
   auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };

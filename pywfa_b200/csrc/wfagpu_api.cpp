@@ -226,7 +226,7 @@ long long score_bound(const KParams& k, long long maxp, long long maxt) {
    * (shorter = min of the maxima, rest = the longer maximum) and "delete everything, insert everything". */
   const long long one_gap = (long long)k.x * std::min(maxp, maxt) + k.o1 + (long long)k.e1 * std::max(maxp, maxt);
   const long long gaps = (maxp ? k.o1 + (long long)k.e1 * maxp : 0) + (maxt ? k.o1 + (long long)k.e1 * maxt : 0);
-  return std::min(one_gap, gaps);
+  return k.no_mis ? gaps : std::min(one_gap, gaps);      /* indel: no mismatches to pay with */
 }
 
 int pow2_floor(long long v) { int p = 1; while (2ll * p <= v) p <<= 1; return p; }
@@ -266,7 +266,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
   /* register-resident tiers first: gap-affine, no heuristic, instantiated penalty shape, short reads */
   const bool no_reg = dbg.no_reg;
   const int winw = B.maxp + B.maxt + 2;       /* sequence windows: one word per base */
-  if (!no_reg && !B.byte_mode && !B.two_p && k.heuristic == 0 && std::max(B.maxp, B.maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
+  if (!no_reg && !B.byte_mode && !B.two_p && !k.m_only && k.heuristic == 0 && std::max(B.maxp, B.maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
     const int maxlen = std::max(B.maxp, B.maxt);
     const int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;     /* window the typical pair of this length needs */
     for (int regs = first; regs <= 4; ++regs) {
@@ -289,7 +289,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
    * leave two / one CTA per SM */
   const bool no_vec = dbg.no_vec;
   bool vec_covers_smem = false;
-  const bool use_vec = !no_vec && !B.byte_mode && std::max(B.maxp, B.maxt) <= VEC_MAX_LEN;   /* byte mode: scalar tiers */
+  const bool use_vec = !no_vec && !B.byte_mode && !k.m_only && std::max(B.maxp, B.maxt) <= VEC_MAX_LEN;   /* byte mode, gap-linear / edit / indel: scalar tiers */
   if (use_vec) {
     const int nslots = k.rm + 2 * k.r1 + (B.two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
     const long long nblk_max = (wmax + 63) / 64 + 1;
@@ -417,26 +417,42 @@ extern "C" void wfagpu_config_default(wfagpu_config_t* cfg) {
 
 extern "C" int wfagpu_config_check(const wfagpu_config_t* c, int64_t plen, int64_t tlen, char* err, size_t errlen) {
   if (!c) { set_err(err, errlen, "null configuration"); return WFAGPU_EINVAL; }
-  if (c->distance != WFAGPU_DISTANCE_AFFINE && c->distance != WFAGPU_DISTANCE_AFFINE2P) {
-    set_err(err, errlen, "distance %d is not on the accelerated path (affine, affine2p)", c->distance);
-    return WFAGPU_EUNSUPPORTED;
+  if (c->distance < WFAGPU_DISTANCE_AFFINE || c->distance > WFAGPU_DISTANCE_INDEL) {
+    set_err(err, errlen, "bad distance %d", c->distance);
+    return WFAGPU_EINVAL;
   }
+  const bool edit_like = c->distance == WFAGPU_DISTANCE_EDIT || c->distance == WFAGPU_DISTANCE_INDEL;
   if (c->scope != WFAGPU_SCOPE_SCORE && c->scope != WFAGPU_SCOPE_FULL) { set_err(err, errlen, "bad scope %d", c->scope); return WFAGPU_EINVAL; }
   if (c->span != WFAGPU_SPAN_END2END && c->span != WFAGPU_SPAN_ENDSFREE) { set_err(err, errlen, "bad span %d", c->span); return WFAGPU_EINVAL; }
   if (c->heuristic < WFAGPU_HEURISTIC_NONE || c->heuristic > WFAGPU_HEURISTIC_XDROP) { set_err(err, errlen, "bad heuristic %d", c->heuristic); return WFAGPU_EINVAL; }
   /* wavefront_penalties_set_affine/_affine2p, W/wavefront/wavefront_penalties.c:95-173 */
   if (c->wildcard < 0 || c->wildcard > 255) { set_err(err, errlen, "wildcard must be 0 (none) or one byte"); return WFAGPU_EINVAL; }
-  if (c->match > 0) { set_err(err, errlen, "[WFA::Penalties] Match score must be negative or zero (M=%d)", c->match); return WFAGPU_EINVAL; }
-  if (c->mismatch <= 0 || c->gap_opening1 < 0 || c->gap_extension1 <= 0) {
-    set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O=%d,E=%d) must be (X>0,O>=0,E>0)", c->mismatch, c->gap_opening1, c->gap_extension1);
-    return WFAGPU_EINVAL;
+  if (edit_like) {
+    /* wavefront_penalties_set_edit / _indel (penalties.c:38-61) ignore every penalty field;
+     * the drop heuristics are refused with these metrics (wavefront_align_presets__checks, W/wavefront/wavefront_align.c:82-89) */
+    if (c->heuristic == WFAGPU_HEURISTIC_XDROP) {
+      set_err(err, errlen, "[WFA] Heuristics drops are not compatible with 'edit'/'indel' distance metrics");
+      return WFAGPU_EINVAL;
+    }
+  } else {
+    if (c->match > 0) { set_err(err, errlen, "[WFA::Penalties] Match score must be negative or zero (M=%d)", c->match); return WFAGPU_EINVAL; }
+    if (c->distance == WFAGPU_DISTANCE_LINEAR) {
+      /* wavefront_penalties_set_linear, penalties.c:62-93; the indel penalty travels in gap_extension1 (align.pyx:355) */
+      if (c->mismatch <= 0 || c->gap_extension1 <= 0) {
+        set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,D=%d,I=%d) must be (X>0,D>0,I>0)", c->mismatch, c->gap_extension1, c->gap_extension1);
+        return WFAGPU_EINVAL;
+      }
+    } else if (c->mismatch <= 0 || c->gap_opening1 < 0 || c->gap_extension1 <= 0) {
+      set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O=%d,E=%d) must be (X>0,O>=0,E>0)", c->mismatch, c->gap_opening1, c->gap_extension1);
+      return WFAGPU_EINVAL;
+    }
   }
   if (c->distance == WFAGPU_DISTANCE_AFFINE2P && (c->gap_opening2 < 0 || c->gap_extension2 <= 0)) {
     set_err(err, errlen, "[WFA::Penalties] Penalties (X=%d,O1=%d,E1=%d,O2=%d,E2=%d) must be (X>0,O1>=0,E1>0,O1>=0,E1>0)",
             c->mismatch, c->gap_opening1, c->gap_extension1, c->gap_opening2, c->gap_extension2);
     return WFAGPU_EINVAL;
   }
-  if (c->match < 0 && c->span == WFAGPU_SPAN_ENDSFREE && (c->pattern_begin_free > 0 || c->text_begin_free > 0)) {
+  if (!edit_like && c->match < 0 && c->span == WFAGPU_SPAN_ENDSFREE && (c->pattern_begin_free > 0 || c->text_begin_free > 0)) {
     set_err(err, errlen, "match < 0 with begin-free ends is outside the accelerated path");
     return WFAGPU_EUNSUPPORTED;
   }

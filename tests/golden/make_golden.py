@@ -10,7 +10,9 @@ It imports the reference's own Python module (oracle/_ref/pywfa, cythonized from
   * postprocess.json   : clip_cigartuples / elide_mismatches_from_cigar / cigartuples_to_str
     outputs of the reference for a set of inputs;
   * synthetic.json     : seeded synthetic batches per configuration (inputs are regenerated from
-    the seed by pywfa_b200.synth.generate_pairs) with the reference's score/status/CIGAR/cells.
+    the seed by pywfa_b200.synth.generate_pairs) with the reference's score/status/CIGAR/cells;
+  * metrics.json       : the same three kinds for distance = linear / levenshtein / indel
+    (`--metrics` regenerates this file only).
 The GPU box has no /root/reference: tests only read the committed JSON.
 """
 import json
@@ -179,9 +181,80 @@ def synthetic_cases():
     return out
 
 
+METRIC_SYNTH = [
+    ("linear-e2e", dict(distance="linear", span="end-to-end"), 128, 150, 0.08, 0),
+    ("linear-endsfree", dict(distance="linear", pattern_begin_free=5, pattern_end_free=8, text_begin_free=6, text_end_free=9), 96, 150, 0.1, 6),
+    ("linear-match-2", dict(distance="linear", span="end-to-end", match=-2, mismatch=4, gap_extension=3), 96, 150, 0.1, 0),
+    ("linear-score", dict(distance="linear", span="end-to-end", scope="score", mismatch=2, gap_extension=5), 128, 250, 0.1, 0),
+    ("linear-xdrop", dict(distance="linear", span="end-to-end", heuristic="X-drop", xdrop=30, steps_between_cutoffs=2), 64, 400, 0.15, 0),
+    ("linear-1kbp", dict(distance="linear", span="end-to-end", mismatch=6, gap_extension=4), 12, 1000, 0.1, 0),
+    ("edit-e2e", dict(distance="levenshtein", span="end-to-end"), 128, 150, 0.08, 0),
+    ("edit-endsfree", dict(distance="levenshtein", text_begin_free=20, text_end_free=20), 96, 150, 0.1, 20),
+    ("edit-score", dict(distance="levenshtein", span="end-to-end", scope="score"), 128, 250, 0.1, 0),
+    ("edit-adaptive", dict(distance="levenshtein", span="end-to-end", heuristic="adaptive", min_wavefront_length=5,
+                           max_distance_threshold=10, steps_between_cutoffs=2), 64, 400, 0.15, 0),
+    ("edit-max-steps", dict(distance="levenshtein", span="end-to-end", max_steps=12), 64, 150, 0.1, 0),
+    ("edit-2kbp", dict(distance="levenshtein", span="end-to-end"), 8, 2000, 0.15, 0),
+    ("indel-e2e", dict(distance="indel", span="end-to-end"), 128, 150, 0.08, 0),
+    ("indel-endsfree", dict(distance="indel", pattern_end_free=10, text_end_free=10), 96, 150, 0.1, 0),
+    ("indel-score", dict(distance="indel", span="end-to-end", scope="score"), 128, 250, 0.1, 0),
+    ("indel-1kbp", dict(distance="indel", span="end-to-end"), 12, 1000, 0.1, 0),
+]
+
+
+def metric_cases():
+    """gap-linear / edit / indel: the reference's own Python object on its README / test pairs, seeded batches
+    through the reference library, and the pairs on which levenshtein's exact pruning fires (sequences of very
+    different lengths: wavefronts of >= 1000 diagonals, compute_edit.c:219-275)."""
+    kat = []
+    P, T = "TCTTTACTCGCGCGTTGGAGAAATACAATAGT", "TCTATACTGCGCGTTTGGAGAAATAAAATAGT"
+    P2, T2 = "AATTAATTTAAGTCTAGGCTACTTTCGGTACTTTGTTCTT", "AATTTAAGTCTAGGCTACTTTCGGTACTTTCTT"
+    for d in ("linear", "levenshtein", "indel"):
+        kat.append(run_case(f"{d}_readme", dict(distance=d), P, T, source="pywfa/tests/test.py:16-46 with another metric"))
+        kat.append(run_case(f"{d}_e2e", dict(distance=d, span="end-to-end"), P2, T2, source="pywfa/tests/test.py:94-102 with another metric"))
+        kat.append(run_case(f"{d}_score", dict(distance=d, scope="score"), P, T, source="pywfa/tests/test.py:54-63 with another metric"))
+        kat.append(run_case(f"{d}_endsfree", dict(distance=d, pattern_begin_free=4, pattern_end_free=4, text_begin_free=4, text_end_free=4),
+                            "GGGGAAAAACCGGGGG", "CCCCCAAAAACCTTTTT", source="pywfa/tests/test.py:115-178 with another metric"))
+        kat.append(run_case(f"{d}_vs_empty", dict(distance=d, span="end-to-end"), "ACGT", "", source="derived"))
+    kat.append(run_case("linear_match_minus1", dict(distance="linear", span="end-to-end", match=-1, mismatch=3, gap_extension=2), P, T,
+                        source="derived (penalties.c:78-82)"))
+    syn = []
+    for i, (name, kw, n, length, div, flank) in enumerate(METRIC_SYNTH):
+        seed = 5000 + i
+        batch = generate_pairs(n, length, div, seed, text_flank=flank)
+        cfg = oracle_py.make_config(**kw)
+        r = oracle_py.align_batch(cfg, *batch, kind="reference")
+        cig = [oracle_py.runs_to_cigarstring(r["runs"][r["cig_off"][j]:r["cig_off"][j + 1]]) for j in range(n)]
+        syn.append(dict(name=name, config=kw, n=n, length=length, div=div, flank=flank, seed=seed,
+                        input_checksum=int(np.frombuffer(batch[0].tobytes(), np.uint8).astype(np.uint64).sum()),
+                        score=r["score"].tolist(), status=r["status"].tolist(), cigars=cig,
+                        locations=r["locs"].tolist(), cells=r["cells"].tolist()))
+    # exact pruning: unrelated and repeat-derived pairs of very different lengths (inputs from the seed)
+    import hashlib
+    rng = np.random.default_rng(5)
+    rs = lambda m: "".join("ACGT"[i] for i in rng.integers(0, 4, m))      # noqa: E731
+    pairs = []
+    for pl, tl in ((300, 3000), (3000, 300), (1500, 2500), (100, 2500)):
+        p = rs(pl)
+        pairs += [(p, rs(tl)), (p, (p * (tl // pl + 1))[:tl])]
+    from pywfa_b200.synth import pairs_from_strings
+    batch = pairs_from_strings(pairs)
+    prune = []
+    for kw in (dict(distance="levenshtein", span="end-to-end"), dict(distance="levenshtein", span="end-to-end", scope="score")):
+        r = oracle_py.align_batch(oracle_py.make_config(**kw), *batch, kind="reference")
+        prune.append(dict(config=kw, seed=5, score=r["score"].tolist(), status=r["status"].tolist(), cells=r["cells"].tolist(),
+                          cigar_sha256=hashlib.sha256(r["runs"].tobytes()).hexdigest(), n_runs=int(len(r["runs"]))))
+    return dict(kat=kat, synthetic=syn, prune=prune)
+
+
 if __name__ == "__main__":
+    if "--metrics" in sys.argv:
+        json.dump(metric_cases(), open(os.path.join(HERE, "metrics.json"), "w"))
+        print("metrics.json", os.path.getsize(os.path.join(HERE, "metrics.json")), "bytes")
+        sys.exit(0)
     json.dump(kat_cases(), open(os.path.join(HERE, "reference_kat.json"), "w"), indent=1)
     json.dump(postprocess_cases(), open(os.path.join(HERE, "postprocess.json"), "w"))
     json.dump(synthetic_cases(), open(os.path.join(HERE, "synthetic.json"), "w"))
-    for f in ("reference_kat.json", "postprocess.json", "synthetic.json"):
+    json.dump(metric_cases(), open(os.path.join(HERE, "metrics.json"), "w"))
+    for f in ("reference_kat.json", "postprocess.json", "synthetic.json", "metrics.json"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

@@ -32,7 +32,8 @@ def test_cython_layer_builds_and_has_no_cpu_path(cy):
 @pytest.mark.gpu
 def test_reference_known_answers_through_the_cython_layer(cy):
     kat = json.load(open(os.path.join(HERE, "golden", "reference_kat.json")))
-    assert len(kat) >= 40
+    kat += json.load(open(os.path.join(HERE, "golden", "metrics.json")))["kat"]      # linear / levenshtein / indel
+    assert len(kat) >= 56
     for case in kat:
         a = cy.WavefrontAligner(**case["ctor"])
         res = a(case["text"], case["pattern"], **case["call"])

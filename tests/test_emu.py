@@ -13,6 +13,7 @@ from pywfa_b200.synth import generate_pairs, pairs_from_strings
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SYN = json.load(open(os.path.join(HERE, "golden", "synthetic.json")))
+SYN = SYN + json.load(open(os.path.join(HERE, "golden", "metrics.json")))["synthetic"]
 
 _i64p = np.ctypeslib.ndpointer(np.int64, flags="C")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C")
@@ -111,6 +112,62 @@ def test_device_source_matches_oracle_ragged(emu, oracle):
         cfg = oracle.make_config(**kw)
         want = oracle.align_batch(cfg, *batch, kind="port")
         got = emu(cfg, batch)
+        for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
+            assert np.array_equal(got[k], want[k]), (kw, k)
+
+
+M_ONLY_CASES = [
+    dict(distance=d, **kw)
+    for d in ("linear", "levenshtein", "indel")
+    for kw in (dict(span="end-to-end"), dict(), dict(span="end-to-end", scope="score"),
+               dict(pattern_begin_free=3, pattern_end_free=5, text_begin_free=4, text_end_free=6),
+               dict(span="end-to-end", heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=10,
+                    steps_between_cutoffs=2),
+               dict(span="end-to-end", max_steps=25))
+] + [
+    dict(distance="linear", span="end-to-end", match=-2, mismatch=4, gap_extension=3),
+    dict(distance="linear", match=-2, mismatch=4, gap_extension=3, pattern_end_free=10, text_end_free=10),
+    dict(distance="linear", span="end-to-end", mismatch=2, gap_extension=5),
+    dict(distance="linear", span="end-to-end", mismatch=6, gap_extension=4, max_steps=31),
+    dict(distance="linear", span="end-to-end", heuristic="X-drop", xdrop=30, steps_between_cutoffs=2),
+]
+
+
+@pytest.mark.parametrize("kw", M_ONLY_CASES, ids=[str(i) for i in range(len(M_ONLY_CASES))])
+def test_gap_linear_edit_indel_match_oracle(emu, oracle, kw):
+    """the M-only metrics (compute_linear.c / compute_edit.c) run on the scalar tier's source"""
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C")]
+    rng = np.random.default_rng(29)
+    for _ in range(150):
+        lp, lt = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        pairs.append(("".join("ACGT"[i] for i in rng.integers(0, 4, lp)),
+                      "".join("ACGT"[i] for i in rng.integers(0, 4, lt))))
+    if kw.get("span") != "end-to-end":
+        pairs = [pt for pt in pairs if min(len(pt[0]), len(pt[1])) >= 10]
+    cfg = oracle.make_config(**kw)
+    for batch in (pairs_from_strings(pairs), generate_pairs(200, 200, 0.1, seed=3)):
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        for off16 in (0, 1):
+            got = emu(cfg, batch, wcap=1024, off16=off16)
+            assert not got["ovf"].any()
+            for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
+                assert np.array_equal(got[k], want[k]), (kw, off16, k)
+
+
+def test_edit_exact_prune_matches_oracle(emu, oracle):
+    """levenshtein end-to-end prunes wavefronts of >= 1000 diagonals (compute_edit.c:219-275)"""
+    rng = np.random.default_rng(5)
+    rs = lambda n: "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+    pairs = []
+    for pl, tl in ((300, 3000), (3000, 300), (1500, 2500), (100, 2500)):
+        p = rs(pl)
+        pairs += [(p, rs(tl)), (p, (p * (tl // pl + 1))[:tl])]
+    batch = pairs_from_strings(pairs)
+    for kw in (dict(distance="levenshtein", span="end-to-end"), dict(distance="levenshtein", span="end-to-end", scope="score")):
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = emu(cfg, batch)
+        assert not got["ovf"].any()
         for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
             assert np.array_equal(got[k], want[k]), (kw, k)
 

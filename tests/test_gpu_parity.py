@@ -49,6 +49,24 @@ CASES = [
     # beyond the packed-halfword tier's length limit with a narrow band: the scalar shared-memory tiers
     ("scalar-tiers-20kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 24, 20000, 0.10, 0),
     ("scalar-tiers-20kbp-xdrop-2p", dict(distance="affine2p", heuristic="X-drop", xdrop=400, scope="score"), 24, 20000, 0.05, 0),
+    # gap-linear / edit / indel (compute_linear.c, compute_edit.c): M wavefronts only, scalar tiers
+    ("linear-150bp-e2e", dict(distance="linear", span="end-to-end"), 5000, 150, 0.08, 0),
+    ("linear-250bp-score", dict(distance="linear", span="end-to-end", scope="score", mismatch=2, gap_extension=5), 5000, 250, 0.10, 0),
+    ("linear-endsfree-four", dict(distance="linear", pattern_begin_free=5, pattern_end_free=8, text_begin_free=6, text_end_free=9), 3000, 150, 0.1, 6),
+    ("linear-match-2", dict(distance="linear", span="end-to-end", match=-2, mismatch=4, gap_extension=3), 3000, 150, 0.1, 0),
+    ("linear-xdrop", dict(distance="linear", span="end-to-end", heuristic="X-drop", xdrop=30, steps_between_cutoffs=2), 2000, 400, 0.15, 0),
+    ("linear-10kbp", dict(distance="linear", span="end-to-end", mismatch=6, gap_extension=4), 16, 10000, 0.1, 0),
+    ("edit-150bp-e2e", dict(distance="levenshtein", span="end-to-end"), 5000, 150, 0.08, 0),
+    ("edit-250bp-score", dict(distance="levenshtein", span="end-to-end", scope="score"), 5000, 250, 0.10, 0),
+    ("edit-endsfree-flanks", dict(distance="levenshtein", text_begin_free=20, text_end_free=20), 3000, 150, 0.1, 20),
+    ("edit-adaptive", dict(distance="levenshtein", span="end-to-end", heuristic="adaptive", min_wavefront_length=5,
+                           max_distance_threshold=10, steps_between_cutoffs=2), 2000, 400, 0.15, 0),
+    ("edit-max-steps", dict(distance="levenshtein", span="end-to-end", max_steps=12), 2000, 150, 0.1, 0),
+    ("edit-10kbp", dict(distance="levenshtein", span="end-to-end"), 16, 10000, 0.15, 0),
+    ("indel-150bp-e2e", dict(distance="indel", span="end-to-end"), 5000, 150, 0.08, 0),
+    ("indel-endsfree", dict(distance="indel", pattern_end_free=10, text_end_free=10), 3000, 150, 0.1, 0),
+    ("indel-250bp-score", dict(distance="indel", span="end-to-end", scope="score"), 5000, 250, 0.10, 0),
+    ("indel-3kbp", dict(distance="indel", span="end-to-end"), 24, 3000, 0.1, 0),
 ]
 
 
@@ -81,6 +99,40 @@ def test_parity_ragged_and_empty(gpu_ctx, oracle):
         want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
         got = gpu_ctx.align_batch(cfg, *batch)
         assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"ragged {kw}")
+
+
+def test_m_only_metrics_ragged_bytes_and_prune(gpu_ctx, oracle):
+    """gap-linear / edit / indel on ragged and empty pairs, on pairs with non-ACGT bytes (byte mode), and
+    levenshtein's exact pruning of >= 1000-diagonal wavefronts (compute_edit.c:219-275) on pairs of very
+    different lengths -- against the checker and the committed reference outputs (metrics.json)."""
+    import hashlib
+    import json
+    import os
+    from test_emu import _pairs_with_n
+    from test_oracle import prune_pairs
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C")] + _ragged_pairs(31, 400, 0, 330)
+    ragged = pairs_from_strings(pairs)
+    with_n = pairs_from_strings(_pairs_with_n(13, 300, 20, 260))
+    for d in ("linear", "levenshtein", "indel"):
+        for kw in (dict(span="end-to-end"), dict(span="end-to-end", scope="score"), dict(span="end-to-end", max_steps=40)):
+            cfg = oracle.make_config(distance=d, **kw)
+            for what, batch in (("ragged", ragged), ("non-ACGT", with_n)):
+                want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
+                got = gpu_ctx.align_batch(cfg, *batch)
+                assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"{d} {what} {kw}")
+        cfg = oracle.make_config(distance=d, wildcard="N", pattern_end_free=6, text_end_free=6)
+        want = oracle.align_batch(cfg, *with_n, kind=oracle.checker_kind())
+        assert_same(gpu_ctx.align_batch(cfg, *with_n), want, what=f"{d} wildcard")
+    met = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.json")))
+    for case in met["prune"]:
+        bt = gpu_ctx.prepare(oracle.make_config(**case["config"]), *prune_pairs(case["seed"]))
+        bt.run(); got = bt.fetch()
+        cells = bt.stats()["cells"]
+        bt.free()
+        assert got["score"].tolist() == case["score"] and got["status"].tolist() == case["status"]
+        if case["config"].get("scope", "full") == "full":
+            assert hashlib.sha256(np.ascontiguousarray(got["runs"]).tobytes()).hexdigest() == case["cigar_sha256"]
+            assert cells == sum(case["cells"]), "the pruned wavefront ranges differ from the reference's"
 
 
 def _ragged_pairs(seed, n, lo_len, hi_len):
@@ -371,7 +423,8 @@ def test_python_api_single_and_batch(gpu_ctx):
     import os
 
     import pywfa_b200
-    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_kat.json")))
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    kat = json.load(open(os.path.join(gold, "reference_kat.json"))) + json.load(open(os.path.join(gold, "metrics.json")))["kat"]
     for case in kat:
         a = pywfa_b200.WavefrontAligner(**case["ctor"])
         res = a(case["text"], case["pattern"], **case["call"])

@@ -45,7 +45,7 @@ def test_config_default_and_layout(lib):
 @pytest.mark.parametrize("field,value,code", [
     ("match", 1, _ffi.EINVAL), ("mismatch", 0, _ffi.EINVAL), ("gap_opening1", -1, _ffi.EINVAL),
     ("gap_extension1", 0, _ffi.EINVAL), ("scope", 7, _ffi.EINVAL), ("span", 3, _ffi.EINVAL),
-    ("heuristic", 9, _ffi.EINVAL), ("distance", 4, _ffi.EUNSUPPORTED),
+    ("heuristic", 9, _ffi.EINVAL), ("distance", 5, _ffi.EINVAL), ("distance", -1, _ffi.EINVAL),
 ])
 def test_config_check_rejects_what_the_reference_exits_on(lib, field, value, code):
     cfg = _ffi.Config()
@@ -106,8 +106,26 @@ def test_constructor_defaults_and_errors():
             b.gap_opening2_penalty, b.gap_extension2_penalty) == (-1, 10, 12, 5, 48, 3)   # Eizenga transform
     with pytest.raises(NotImplementedError):
         pywfa_b200.WavefrontAligner(distance="hamming")
-    with pytest.raises(NotImplementedError):
-        pywfa_b200.WavefrontAligner(distance="levenshtein")     # reference supports it; not on this path
+    # the M-only metrics: getters return what wavefront_penalties_set_* leaves (penalties.c:38-93)
+    lv = pywfa_b200.WavefrontAligner(distance="levenshtein")
+    assert (lv.distance, lv.match_score, lv.mismatch_penalty, lv.gap_opening_penalty, lv.gap_extension_penalty,
+            lv.gap_opening2_penalty, lv.gap_extension2_penalty) == ("levenshtein", 0, 1, 1, -1, -1, -1)
+    ind = pywfa_b200.WavefrontAligner(distance="indel", mismatch=0)          # penalties are ignored
+    assert (ind.distance, ind.mismatch_penalty, ind.gap_opening_penalty) == ("indel", -1, 1)
+    lin = pywfa_b200.WavefrontAligner(distance="linear", mismatch=3, gap_opening=0, gap_extension=5)
+    assert (lin.distance, lin.mismatch_penalty, lin.gap_opening_penalty, lin.gap_extension_penalty) == ("linear", 3, 5, -1)
+    lin = pywfa_b200.WavefrontAligner(distance="linear", match=-1, mismatch=3, gap_extension=5)
+    assert (lin.match_score, lin.mismatch_penalty, lin.gap_opening_penalty) == (-1, 8, 11)      # Eizenga transform
+    lin.gap_opening_penalty = 2                                               # align.pyx:675: the indel penalty
+    assert lin.gap_opening_penalty == 5
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(distance="linear", gap_extension=0)
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(distance="indel", heuristic="X-drop")     # the reference exit(1)s at the first alignment
+    sw = pywfa_b200.WavefrontAligner(distance="levenshtein", mismatch=0)
+    with pytest.raises(ValueError):
+        sw.distance = "affine"                                                # mismatch=0 is not a gap-affine penalty
+    assert sw.distance == "levenshtein"
     with pytest.raises(ValueError):
         pywfa_b200.WavefrontAligner(scope="partial")
     with pytest.raises(ValueError):

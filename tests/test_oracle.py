@@ -12,6 +12,9 @@ from pywfa_b200.synth import generate_pairs, pairs_from_strings
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 KAT = json.load(open(os.path.join(GOLD, "reference_kat.json")))
 SYN = json.load(open(os.path.join(GOLD, "synthetic.json")))
+MET = json.load(open(os.path.join(GOLD, "metrics.json")))          # distance = linear / levenshtein / indel
+KAT = KAT + MET["kat"]
+SYN = SYN + MET["synthetic"]
 
 _CTOR_MAP = dict(gap_opening="gap_opening", gap_extension="gap_extension")
 
@@ -61,6 +64,28 @@ def test_oracle_matches_reference_synthetic(oracle, case, bt_mode):
         assert r["cells"].tolist() == case["cells"]
 
 
+def prune_pairs(seed):
+    """the pairs of metrics.json's "prune" section (tests/golden/make_golden.py:metric_cases)"""
+    rng = np.random.default_rng(seed)
+    rs = lambda m: "".join("ACGT"[i] for i in rng.integers(0, 4, m))      # noqa: E731
+    pairs = []
+    for pl, tl in ((300, 3000), (3000, 300), (1500, 2500), (100, 2500)):
+        p = rs(pl)
+        pairs += [(p, rs(tl)), (p, (p * (tl // pl + 1))[:tl])]
+    return pairs_from_strings(pairs)
+
+
+@pytest.mark.parametrize("case", MET["prune"], ids=[c["config"].get("scope", "full") for c in MET["prune"]])
+def test_oracle_matches_reference_edit_exact_prune(oracle, case):
+    """levenshtein end-to-end drops provably useless ends of wavefronts of >= 1000 diagonals"""
+    import hashlib
+    r = oracle.align_batch(oracle.make_config(**case["config"]), *prune_pairs(case["seed"]), kind="port")
+    assert r["score"].tolist() == case["score"] and r["status"].tolist() == case["status"]
+    assert hashlib.sha256(r["runs"].tobytes()).hexdigest() == case["cigar_sha256"] and len(r["runs"]) == case["n_runs"]
+    if case["config"].get("scope", "full") == "full":
+        assert r["cells"].tolist() == case["cells"]
+
+
 LIVE = [
     ("affine-e2e", dict(span="end-to-end"), 600, 150, 0.08, 0),
     ("affine-score", dict(span="end-to-end", scope="score"), 300, 250, 0.10, 0),
@@ -68,6 +93,10 @@ LIVE = [
     ("adaptive", dict(heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=10), 200, 300, 0.2, 0),
     ("xdrop", dict(heuristic="X-drop", xdrop=60, steps_between_cutoffs=2), 200, 300, 0.1, 0),
     ("match-2", dict(span="end-to-end", match=-2, distance="affine2p"), 200, 150, 0.1, 0),
+    ("linear", dict(distance="linear", pattern_end_free=12, text_end_free=7, mismatch=3, gap_extension=2), 200, 200, 0.12, 0),
+    ("linear-match-1-xdrop", dict(distance="linear", span="end-to-end", match=-1, heuristic="X-drop", xdrop=40), 200, 200, 0.12, 0),
+    ("levenshtein-adaptive", dict(distance="levenshtein", heuristic="adaptive", min_wavefront_length=5, max_distance_threshold=8), 200, 300, 0.2, 0),
+    ("indel-max-steps", dict(distance="indel", span="end-to-end", max_steps=30), 200, 200, 0.1, 0),
 ]
 
 
