@@ -23,7 +23,11 @@ Intentional deviations from the reference:
     initialising only offset 0 -- the other seeds are uninitialised memory, so the reference's
     result for that combination is undefined; here the seed is the single cell ``k = 0``;
   * ``match < 0`` together with ends-free *begin* gaps (score-dependent seeding,
-    ``wavefront_compute.c:124-254``) raises ``NotImplementedError``.
+    ``wavefront_compute.c:124-254``) raises ``NotImplementedError``: the reference itself does not
+    survive that combination on ordinary reads (r02, the unmodified library on 200 bp pairs at
+    10 % divergence: ``match=-1, text_begin_free=20, text_end_free=20, distance="affine2p"`` ends
+    in ``[WFA::Backtrace] I?/D?-Beginning backtrace error`` and ``exit(1)``), so there is no
+    behaviour to be bit-exact with.
 
 Thread safety: all aligners of one device share one library context; calls from several threads
 are serialised inside the library (pywfa's aligners are independent objects, one per thread works

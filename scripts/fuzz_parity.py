@@ -26,8 +26,11 @@ ctx = _ffi.Context(0)
 t0 = time.time()
 for r in range(rounds):
     kw = {}
-    if rng.random() < 0.5:
+    d = rng.random()
+    if d < 0.4:
         kw["distance"] = "affine2p"
+    elif d < 0.65:
+        kw["distance"] = str(rng.choice(["linear", "levenshtein", "indel"]))
     if rng.random() < 0.5:
         kw["span"] = "end-to-end"
     if rng.random() < 0.3:
@@ -42,7 +45,7 @@ for r in range(rounds):
     if h < 0.25:
         kw.update(heuristic="adaptive", min_wavefront_length=int(rng.integers(2, 30)), max_distance_threshold=int(rng.integers(5, 80)),
                   steps_between_cutoffs=int(rng.integers(1, 5)))
-    elif h < 0.45:
+    elif h < 0.45 and kw.get("distance") not in ("levenshtein", "indel"):     # the drops are refused with edit / indel
         kw.update(heuristic="X-drop", xdrop=int(rng.integers(5, 300)), steps_between_cutoffs=int(rng.integers(1, 5)))
     if rng.random() < 0.15:
         kw["max_steps"] = int(rng.integers(5, 400))
