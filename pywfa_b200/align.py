@@ -11,8 +11,12 @@ through ``libwfagpu.so``; there is no CPU fallback.
 
 Intentional deviations from the reference:
   * configurations the reference ``exit(1)``s on raise ``ValueError`` before any launch;
-  * ``memory_mode="biwfa"`` (different tie-breaks) raises ``NotImplementedError``; non-ACGT bases
-    and the wildcard are aligned in the library's byte mode;
+  * ``memory_mode="biwfa"`` is accepted for ``scope="score"`` without cut-offs and step limits
+    (BiWFA is exact: the reference returns the same score and status as its other memory modes
+    there, pinned by ``tests/golden/metrics.json``) and runs on the same kernels; with
+    ``scope="full"`` BiWFA picks other co-optimal CIGARs (7 % of 200 bp pairs at 10 % divergence),
+    with cut-offs / ``max_steps`` it stops elsewhere -- those raise ``NotImplementedError``;
+    non-ACGT bases and the wildcard are aligned in the library's byte mode;
   * ``distance="linear" | "levenshtein" | "indel"`` are aligned by the scalar tiers only (no
     register / packed-halfword kernels for them).  Changing ``distance`` after construction keeps
     the constructor's penalties (the reference's setter re-reads per-metric copies that it only
@@ -311,10 +315,7 @@ class WavefrontAligner:
         self._cfg.scope = _SCOPES[scope]
         if memory_mode not in _MEMORY_MODES:
             raise ValueError("memory_mode must be one of 'high', 'medium', 'low', 'biwfa'")
-        if memory_mode == "biwfa":
-            raise NotImplementedError("memory_mode='biwfa' breaks ties differently from the other "
-                                      "modes and is not on the accelerated path")
-        self._memory_mode = memory_mode
+        self._memory_mode = memory_mode        # "biwfa": see _validate
         self._cfg.pattern_begin_free, self._cfg.pattern_end_free = int(pattern_begin_free), int(pattern_end_free)
         self._cfg.text_begin_free, self._cfg.text_end_free = int(text_begin_free), int(text_end_free)
         if span not in _SPANS:
@@ -346,6 +347,15 @@ class WavefrontAligner:
     # ---- configuration -------------------------------------------------------------------
     def _validate(self, plen=-1, tlen=-1):
         import ctypes as C
+        if getattr(self, "_memory_mode", "high") == "biwfa":
+            c = self._cfg
+            if c.span == 1 and (c.pattern_begin_free > 0 or c.pattern_end_free > 0 or c.text_begin_free > 0
+                                or c.text_end_free > 0):
+                # wavefront_align_presets__checks, W/wavefront/wavefront_align.c:66-76 (exit(1) there)
+                raise ValueError("[WFA] BiWFA ends-free has not been tested properly yet")
+            if c.scope != 0 or c.heuristic != 0 or c.max_steps > 0:
+                raise NotImplementedError("memory_mode='biwfa' is on the accelerated path for scope='score' without "
+                                          "heuristic and max_steps only (elsewhere BiWFA breaks ties / stops differently)")
         err = C.create_string_buffer(512)
         rc = _ffi.lib().wfagpu_config_check(C.addressof(self._cfg), plen, tlen, err, len(err))
         if rc == _ffi.EUNSUPPORTED:

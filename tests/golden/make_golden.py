@@ -218,6 +218,13 @@ def metric_cases():
         kat.append(run_case(f"{d}_vs_empty", dict(distance=d, span="end-to-end"), "ACGT", "", source="derived"))
     kat.append(run_case("linear_match_minus1", dict(distance="linear", span="end-to-end", match=-1, mismatch=3, gap_extension=2), P, T,
                         source="derived (penalties.c:78-82)"))
+    # memory_mode="biwfa", scope="score": BiWFA is exact, same score / status as the other memory modes
+    for nm, kw in (("affine", {}), ("affine2p", dict(distance="affine2p")), ("match_minus1", dict(match=-1)),
+                   ("levenshtein", dict(distance="levenshtein")), ("linear", dict(distance="linear"))):
+        kat.append(run_case(f"biwfa_score_{nm}", dict(memory_mode="biwfa", scope="score", span="end-to-end", **kw), P, T,
+                            source="pywfa/align.pyx:386-387 (wavefront_memory_ultralow), score only"))
+        kat.append(run_case(f"biwfa_score_{nm}_2", dict(memory_mode="biwfa", scope="score", span="end-to-end", **kw), P2, T2,
+                            source="pywfa/align.pyx:386-387 (wavefront_memory_ultralow), score only"))
     syn = []
     for i, (name, kw, n, length, div, flank) in enumerate(METRIC_SYNTH):
         seed = 5000 + i

@@ -126,6 +126,14 @@ def test_constructor_defaults_and_errors():
     with pytest.raises(ValueError):
         sw.distance = "affine"                                                # mismatch=0 is not a gap-affine penalty
     assert sw.distance == "levenshtein"
+    # BiWFA: exact, so score-only results equal the other memory modes'; its CIGAR tie-breaks / stops are not reproduced
+    assert pywfa_b200.WavefrontAligner(memory_mode="biwfa", scope="score", span="end-to-end").memory_mode == "biwfa"
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(memory_mode="biwfa", span="end-to-end")
+    with pytest.raises(NotImplementedError):
+        pywfa_b200.WavefrontAligner(memory_mode="biwfa", scope="score", span="end-to-end", heuristic="adaptive")
+    with pytest.raises(ValueError):
+        pywfa_b200.WavefrontAligner(memory_mode="biwfa", scope="score", text_end_free=3)    # the reference exit(1)s
     with pytest.raises(ValueError):
         pywfa_b200.WavefrontAligner(scope="partial")
     with pytest.raises(ValueError):

@@ -21,7 +21,7 @@ _CTOR_MAP = dict(gap_opening="gap_opening", gap_extension="gap_extension")
 
 def config_from_ctor(oracle, ctor):
     """pywfa constructor kwargs -> wfagpu_config_t (pattern is not a config field)."""
-    kw = {k: v for k, v in ctor.items() if k != "pattern"}
+    kw = {k: v for k, v in ctor.items() if k not in ("pattern", "memory_mode")}
     h = kw.get("heuristic")
     cfg = oracle.make_config(**kw)
     # only the chosen heuristic's parameters reach the aligner (wavefront_aligner.c:188-224)
