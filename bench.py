@@ -52,11 +52,15 @@ WORKLOADS = {
     "cfg5": (16, 100_000, 0.20, 0, dict(distance="affine2p", span="end-to-end", scope="full")),
     # length buckets: 150 bp + 250 bp + 1 kbp pairs shuffled into one batch (see --workload mixed)
     "mixed": (0, 0, 0.0, 0, dict(span="end-to-end", scope="score")),
+    # the M-only metrics: score-only runs on the gap-affine tiers, CIGARs on the scalar tiers
+    "edit-score": (4_000_000, 150, 0.05, 0, dict(distance="levenshtein", span="end-to-end", scope="score")),
+    "edit-full": (400_000, 150, 0.05, 0, dict(distance="levenshtein", span="end-to-end", scope="full")),
+    "linear-score": (4_000_000, 250, 0.10, 0, dict(distance="linear", span="end-to-end", scope="score")),
 }
 MIXED_PARTS = [(600_000, 150, 0.05), (300_000, 250, 0.10), (20_000, 1000, 0.05)]
 # pywfa pairs/s per host core (survey measurements), used to size the bounded CPU samples
 REF_PER_CORE = {"cfg1": 90_000, "cfg2": 25_000, "cfg3": 280, "cfg4-adaptive": 120, "cfg4-xdrop": 20_000, "cfg4-none": 1.5,
-                "cfg5": 0.005, "mixed": 40_000}
+                "cfg5": 0.005, "mixed": 40_000, "edit-score": 250_000, "edit-full": 150_000, "linear-score": 60_000}
 WORKLOAD_DESC = {
     "cfg1": "1M synthetic 150 bp pairs, 5% divergence, affine (x=4,o=6,e=2), end-to-end, scope=full",
     "cfg2": "10M synthetic 250 bp pairs, 10% divergence, affine (x=4,o=6,e=2), end-to-end, scope=score",
@@ -66,6 +70,9 @@ WORKLOAD_DESC = {
     "cfg4-none": "2k (of 100k) synthetic 10 kbp pairs, 15% divergence, affine, no heuristic, scope=full",
     "cfg5": "16 (of 10k) synthetic 100 kbp pairs, 20% divergence, affine2p, end-to-end, scope=full, several CTAs per pair, history in HBM",
     "mixed": "600k x 150 bp 5% + 300k x 250 bp 10% + 20k x 1 kbp 5% pairs shuffled into one batch, affine, end-to-end, scope=score (length buckets)",
+    "edit-score": "4M synthetic 150 bp pairs, 5% divergence, levenshtein, end-to-end, scope=score",
+    "edit-full": "400k synthetic 150 bp pairs, 5% divergence, levenshtein, end-to-end, scope=full",
+    "linear-score": "4M synthetic 250 bp pairs, 10% divergence, gap-linear (x=4, indel=2), end-to-end, scope=score",
 }
 
 

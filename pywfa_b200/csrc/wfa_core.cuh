@@ -93,6 +93,7 @@ struct KParams {
    * only (the gap sources are the "open" sources of a zero-cost opening); indel has no mismatch source;
    * edit / indel run compute_edit.c's driver (no null steps, range = previous range +-1, positive scores) */
   int m_only, no_mis, edit_like;
+  int pos_score;                 /* edit / indel report the distance itself (compute.c:117) */
   int edit_prune;                /* edit, end-to-end: wavefront_compute_edit_exact_prune (compute_edit.c:219-275) */
   /* score unit g = gcd(x, o1+e1, e1[, o2+e2, e2]) and the penalties in that unit */
   int g, dx, doe1, de1, doe2, de2;
@@ -269,9 +270,9 @@ WFA_DEV bool in_bounds(int k, int off, int plen, int tlen) {
 
 /* wavefront_compute_classic_score, W/wavefront/wavefront_compute.c:108-120 with
  * WF_SCORE_TO_SW_SCORE (wavefront_penalties.h:73): int32 wrap-around, C truncating division */
-WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score, int edit_like = 0) {
+WFA_DEV int classic_score(int match, int plen, int tlen, int wf_score, int pos_score = 0) {
   const int swg_match = -match;
-  if (edit_like) return wf_score;               /* distance_metric <= edit, compute.c:117 */
+  if (pos_score) return wf_score;               /* distance_metric <= edit, compute.c:117 */
   if (swg_match == 0) return -wf_score;
   const int32_t sum = (int32_t)((uint32_t)plen + (uint32_t)tlen);
   const int32_t prod = (int32_t)((uint32_t)swg_match * (uint32_t)sum);
@@ -784,11 +785,11 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
   if (status == 3) {
     res.score = -P.max_steps; res.status = ST_MAX_STEPS;
   } else if (!FULL) {
-    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score, P.edit_like); res.status = ST_COMPLETED; }
+    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score, P.pos_score); res.status = ST_COMPLETED; }
     else {
       /* end position was never assigned: end_v = NULL - DIAGONAL_NULL with int32 wrap */
       const int32_t end_v = (int32_t)((uint32_t)OFFNULL - (uint32_t)INT_MAX);
-      res.score = classic_score(P.match, end_v, OFFNULL, end_score, P.edit_like); res.status = ST_PARTIAL;
+      res.score = classic_score(P.match, end_v, OFFNULL, end_score, P.pos_score); res.status = ST_PARTIAL;
     }
   } else {
     if (status == 1) {
@@ -798,7 +799,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         res.nruns = n;
         if (n >= 0) locations_from_runs(gm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }
-      res.score = classic_score(P.match, end_off - end_k, end_off, end_score, P.edit_like);
+      res.score = classic_score(P.match, end_off - end_k, end_off, end_score, P.pos_score);
       res.status = ST_COMPLETED;
     } else {
       /* dropped: no end position -> empty CIGAR; maxtrim on an empty CIGAR clears the

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const _
   uint32_t* const sm_pk = reinterpret_cast<uint32_t*>(wbase + L.pk_off());
 
   RegParams R;
-  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps; R.pos_score = K.pos_score;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = K.rhrows; R.opcap = K.ropcap; R.runcap = K.runcap;
   R.kbase = K.reg_kbase; R.c_lo = K.reg_clo; R.c_hi = K.reg_chi;
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(32) wfa_pair_kernel(const __grid_constant__ KP
   build_windows(sm_pk + pwn, tlen, st);
   __syncwarp();
   RegParams R;
-  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps; R.pos_score = K.pos_score;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = PAIR_HIST_ROWS; R.opcap = PAIR_OPS_BYTES; R.runcap = plen + tlen + 2;
   const RegWindow rw = reg_window(P, K.endsfree, K.match, K.pbf, K.tbf);
@@ -829,31 +829,47 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
 }
 
 /* register tier: instantiated for the penalty shapes (x, o+e, e)/gcd = (2, 4, 1) -- pywfa's
- * default 4/6/2 -- and windows of 128 / 192 / 256 diagonals */
+ * default 4/6/2 -- with windows of 128 / 192 / 256 diagonals, and score-only for the zero-opening
+ * shapes (1, 1, 1) and (2, 1, 1): edit, indel and pywfa's default gap-linear 4/2 (metric_as_affine) */
+#define WFA_REG_DISPATCH_P(STMT, PP)                            \
+  do {                                                          \
+    if (shape == 0) {                                           \
+      if (full) { STMT(PP, 2, 4, true); } else { STMT(PP, 2, 4, false); } \
+    } else if (shape == 1) { STMT(PP, 1, 1, false); }           \
+    else { STMT(PP, 2, 1, false); }                             \
+  } while (0)
 #define WFA_REG_DISPATCH(STMT)                                  \
   do {                                                          \
-    if (regs == 2) {                                            \
-      if (full) { STMT(2, 2, 4, true); } else { STMT(2, 2, 4, false); } \
-    } else if (regs == 3) {                                     \
-      if (full) { STMT(3, 2, 4, true); } else { STMT(3, 2, 4, false); } \
-    } else {                                                    \
-      if (full) { STMT(4, 2, 4, true); } else { STMT(4, 2, 4, false); } \
-    }                                                           \
+    if (regs == 2) WFA_REG_DISPATCH_P(STMT, 2);                 \
+    else if (regs == 3) WFA_REG_DISPATCH_P(STMT, 3);            \
+    else WFA_REG_DISPATCH_P(STMT, 4);                           \
   } while (0)
 
-bool reg_tier_supported(int dx, int doe, int de, int regs) {
-  return dx == 2 && doe == 4 && de == 1 && (regs >= 2 && regs <= 4);
+static int reg_shape(int dx, int doe, int de, bool full) {
+  if (de != 1) return -1;
+  if (dx == 2 && doe == 4) return 0;
+  if (!full && dx == 1 && doe == 1) return 1;
+  if (!full && dx == 2 && doe == 1) return 2;
+  return -1;
+}
+
+bool reg_tier_supported(int dx, int doe, int de, int regs, bool full) {
+  return reg_shape(dx, doe, de, full) >= 0 && (regs >= 2 && regs <= 4);
 }
 
 cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st) {
+  const int shape = reg_shape(P.dx, P.doe1, P.de1, full);
+  if (shape < 0) return cudaErrorInvalidValue;
 #define WFA_REG_LAUNCH(PP, DX, DOE, FULL) wfa_reg_kernel<PP, DX, DOE, FULL><<<grid, block, smem, st>>>(P)
   WFA_REG_DISPATCH(WFA_REG_LAUNCH);
 #undef WFA_REG_LAUNCH
   return cudaGetLastError();
 }
 
-int reg_occupancy(int regs, bool full, int block, size_t smem) {
+int reg_occupancy(const KParams& P, int regs, bool full, int block, size_t smem) {
   int nb = 0;
+  const int shape = reg_shape(P.dx, P.doe1, P.de1, full);
+  if (shape < 0) return 0;
 #define WFA_REG_OCC(PP, DX, DOE, FULL) \
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, wfa_reg_kernel<PP, DX, DOE, FULL>, block, smem) != cudaSuccess) nb = 0
   WFA_REG_DISPATCH(WFA_REG_OCC);
@@ -871,7 +887,9 @@ static cudaError_t init_pair(int smem_optin) {
 static cudaError_t init_reg(int smem_optin) {
   cudaError_t e = cudaSuccess;
   for (int regs = 2; regs <= 4; ++regs)
-    for (int full = 0; full < 2; ++full) {
+    for (int v = 0; v < 4; ++v) {
+      const int shape = v < 2 ? 0 : v - 1;
+      const bool full = v == 1;
 #define WFA_REG_INIT(PP, DX, DOE, FULL) \
   e = cudaFuncSetAttribute(wfa_reg_kernel<PP, DX, DOE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)
       WFA_REG_DISPATCH(WFA_REG_INIT);

@@ -52,9 +52,9 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
 size_t block_reduce_smem_bytes();
 
 /* register-resident tier (wfa_reg.cuh): regs = packed registers per wavefront (window 64*regs) */
-bool reg_tier_supported(int dx, int doe, int de, int regs);
+bool reg_tier_supported(int dx, int doe, int de, int regs, bool full);
 cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st);
-int reg_occupancy(int regs, bool full, int block, size_t smem);
+int reg_occupancy(const KParams& P, int regs, bool full, int block, size_t smem);
 
 /* packed-halfword tier (wfa_vec.cuh): nw = warps per pair (1, 8 or 16) */
 cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st);

@@ -24,14 +24,14 @@ inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
     k.o1 = c.gap_opening1; k.e1 = c.gap_extension1;
     k.o2 = c.gap_opening2; k.e2 = c.gap_extension2;
   }
-  k.m_only = k.no_mis = k.edit_like = k.edit_prune = 0;
+  k.m_only = k.no_mis = k.edit_like = k.edit_prune = k.pos_score = 0;
   if (c.distance == WFAGPU_DISTANCE_LINEAR) {
     /* wavefront_penalties_set_linear, penalties.c:62-93: one indel penalty (carried in gap_extension1 as pywfa does,
      * align.pyx:351-355), here the extension of a zero-cost opening: s - o1 - e1 addresses the gap source */
     k.m_only = 1; k.o1 = 0;
   } else if (c.distance == WFAGPU_DISTANCE_EDIT || c.distance == WFAGPU_DISTANCE_INDEL) {
     /* wavefront_penalties_set_edit / _indel, penalties.c:38-61 */
-    k.m_only = k.edit_like = 1; k.no_mis = c.distance == WFAGPU_DISTANCE_INDEL;
+    k.m_only = k.edit_like = k.pos_score = 1; k.no_mis = c.distance == WFAGPU_DISTANCE_INDEL;
     k.edit_prune = c.distance == WFAGPU_DISTANCE_EDIT && c.span == WFAGPU_SPAN_END2END;
     k.match = 0; k.x = 1; k.o1 = 0; k.e1 = 1;
   }
@@ -58,6 +58,23 @@ inline void fill_kparams(const wfagpu_config_t& c, KParams& k) {
   k.min_wf_len = c.min_wavefront_length; k.max_dist_thr = c.max_distance_threshold;
   k.steps_between = c.steps_between_cutoffs; k.xdrop = c.xdrop;
   k.max_steps = c.max_steps <= 0 ? INT_MAX : c.max_steps;
+}
+
+/* Score-only alignments of the M-only metrics without a cut-off are gap-affine alignments with a zero-cost
+ * opening: gap-linear (x, e) = affine (x, 0, e); edit = affine (1, 0, 1); indel = affine (2, 0, 1), a mismatch
+ * costing what an insertion plus a deletion cost.  Score and status are the optimum's either way (WFA is exact;
+ * the two recurrences differ in wavefront ranges and CIGAR tie-breaks only), so these run on the fast gap-affine
+ * tiers.  Returns whether `k` (filled by fill_kparams) was rewritten. */
+inline bool metric_as_affine(const wfagpu_config_t& c, KParams& k) {
+  if (!k.m_only || c.scope != WFAGPU_SCOPE_SCORE || c.heuristic != WFAGPU_HEURISTIC_NONE) return false;
+  wfagpu_config_t a = c;
+  a.distance = WFAGPU_DISTANCE_AFFINE;
+  a.gap_opening1 = 0;
+  if (k.edit_like) { a.match = 0; a.mismatch = k.no_mis ? 2 : 1; a.gap_extension1 = 1; }
+  const int pos = k.pos_score, scope = k.max_scope;
+  fill_kparams(a, k);
+  k.pos_score = pos; k.max_scope = scope;
+  return true;
 }
 
 }  // namespace wfagpu

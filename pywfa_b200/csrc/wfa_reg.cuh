@@ -60,7 +60,7 @@ constexpr int REG_UB_MIN = -8192;              /* floor of ub[k] for diagonals l
 constexpr uint32_t REG_ONE2 = 0x00010001u;
 
 struct RegParams {
-  int match, g, max_steps;
+  int match, g, max_steps, pos_score;
   int endsfree, pbf, pef, tbf, tef;
   int kbase, c_lo, c_hi;   /* reg_window() of the launch */
   int hrows;          /* scope=full: rows of the origin arena (scores 0..hrows-1) */
@@ -487,9 +487,9 @@ WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_
   if (A.status == 3) {
     res.score = -R.max_steps; res.status = ST_MAX_STEPS;
   } else if (!FULL) {
-    res.score = classic_score(R.match, plen, tlen, end_score); res.status = ST_COMPLETED;
+    res.score = classic_score(R.match, plen, tlen, end_score, R.pos_score); res.status = ST_COMPLETED;
   } else {
-    res.score = classic_score(R.match, end_off - end_k, end_off, end_score);
+    res.score = classic_score(R.match, end_off - end_k, end_off, end_score, R.pos_score);
     res.status = ST_COMPLETED;
     if (is_leader) {
       FwdEmitter em; em.init(runs_stage, R.runcap);

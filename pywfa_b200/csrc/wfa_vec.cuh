@@ -924,10 +924,10 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
   if (status == 3) {
     res.score = -P.max_steps; res.status = ST_MAX_STEPS;
   } else if (!FULL) {
-    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score); res.status = ST_COMPLETED; }
+    if (status == 1) { res.score = classic_score(P.match, plen, tlen, end_score, P.pos_score); res.status = ST_COMPLETED; }
     else {
       const int32_t end_v = (int32_t)((uint32_t)OFFNULL - (uint32_t)INT_MAX);
-      res.score = classic_score(P.match, end_v, OFFNULL, end_score); res.status = ST_PARTIAL;
+      res.score = classic_score(P.match, end_v, OFFNULL, end_score, P.pos_score); res.status = ST_PARTIAL;
     }
   } else {
     if (status == 1) {
@@ -937,7 +937,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
         res.nruns = n;
         if (n >= 0) locations_from_runs(vm.runs_stage, imin(n, P.runcap), plen, tlen, res.locs);
       }
-      res.score = classic_score(P.match, end_off - end_k, end_off, end_score);
+      res.score = classic_score(P.match, end_off - end_k, end_off, end_score, P.pos_score);
       res.status = ST_COMPLETED;
     } else {
       res.score = INT32_MIN; res.status = ST_PARTIAL;

@@ -93,7 +93,7 @@ struct StageRing {
 
 /* test / tuning switches, read from the environment once per call (WFAGPU_* variables) */
 struct DebugKnobs {
-  bool trace = false, no_reg = false, no_vec = false, no_tier_skip = false, no_buckets = false, host_stage = false;
+  bool trace = false, no_reg = false, no_vec = false, no_tier_skip = false, no_buckets = false, host_stage = false, no_metric_map = false;
   int vec_nw = 0, block_threads = 0;
   long long chunk = 0;
 };
@@ -271,7 +271,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
     const int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;     /* window the typical pair of this length needs */
     for (int regs = first; regs <= 4; ++regs) {
       if (regs == 3 && first == 2) continue;                         /* 128 -> 256 directly: few pairs get that far */
-      if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs)) continue;
+      if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs, B.full)) continue;
       Tier t;
       t.regs = regs; t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = 64 * regs;
       t.scap = 32 * regs + k.doe1 + 1;          /* origin rows: scores the window can hold */
@@ -387,7 +387,7 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
     }
   }
   for (auto& t : B.tiers) {
-    int bps = t.regs ? reg_occupancy(t.regs, B.full, t.threads, t.smem)
+    int bps = t.regs ? reg_occupancy(k, t.regs, B.full, t.threads, t.smem)
               : t.mode == 2 ? grid_occupancy(B.two_p, B.full, t.smem)
               : t.vec_nw ? vec_occupancy(B.two_p, B.full, t.vec_nw, k.heuristic, t.threads, t.smem)
                          : align_occupancy(B.two_p, B.full, t.mode, t.off16, t.threads, t.smem);
@@ -637,6 +637,7 @@ void read_knobs(wfagpu_ctx* ctx) {
   k.no_vec = flag("WFAGPU_NO_VEC_TIER");
   k.no_tier_skip = flag("WFAGPU_NO_TIER_SKIP");
   k.no_buckets = flag("WFAGPU_NO_BUCKETS");
+  k.no_metric_map = flag("WFAGPU_NO_METRIC_MAP");
   k.vec_nw = (int)num("WFAGPU_VEC_NW");
   k.block_threads = (int)num("WFAGPU_BLOCK_THREADS");
   k.chunk = num("WFAGPU_CHUNK");
@@ -891,6 +892,7 @@ int batch_finish_stage(wfagpu_ctx* ctx, wfagpu_batch* b, const PackCounters* cou
   }
   KParams& k = b->kp;
   fill_kparams(b->cfg, k);
+  if (!ctx->knobs.no_metric_map) metric_as_affine(b->cfg, k);      /* score-only linear / edit / indel: the gap-affine tiers */
   k.byte_mode = b->byte_mode ? 1 : 0;
   k.wildcard = b->cfg.wildcard & 0xff;
   k.pairs = b->pairs.as<PairMeta>();
@@ -1540,7 +1542,7 @@ extern "C" int wfagpu_align_pair(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, co
   memset(&k, 0, sizeof k);
   fill_kparams(*cfg, k);
   const bool fast = cfg->distance == WFAGPU_DISTANCE_AFFINE && cfg->heuristic == WFAGPU_HEURISTIC_NONE && cfg->wildcard == 0 &&
-                    plen <= PAIR_MAX_LEN && tlen <= PAIR_MAX_LEN && reg_tier_supported(k.dx, k.doe1, k.de1, 4);
+                    plen <= PAIR_MAX_LEN && tlen <= PAIR_MAX_LEN && k.dx == 2 && k.doe1 == 4 && k.de1 == 1;   /* the shape wfa_pair_kernel is compiled for */
   if (fast) {
     std::lock_guard<std::mutex> call(ctx->call_mu);
     CK(cudaSetDevice(ctx->device));

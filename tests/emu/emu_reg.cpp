@@ -38,11 +38,14 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
   KParams K;
   memset(&K, 0, sizeof K);
   fill_kparams(*cfg, K);
-  if (cfg->distance != WFAGPU_DISTANCE_AFFINE || cfg->heuristic != WFAGPU_HEURISTIC_NONE) return -4;
-  if (!(K.dx == 2 && K.doe1 == 4 && K.de1 == 1)) return -4;
+  const bool mapped = metric_as_affine(*cfg, K);       /* score-only linear / edit / indel as zero-opening gap-affine */
+  if ((cfg->distance != WFAGPU_DISTANCE_AFFINE && !mapped) || cfg->heuristic != WFAGPU_HEURISTIC_NONE) return -4;
+  /* the penalty shapes the product instantiates (wfa_kernels.cu: reg_shape) */
+  const int shape = K.de1 != 1 ? -1 : (K.dx == 2 && K.doe1 == 4) ? 0 : (K.dx == 1 && K.doe1 == 1) ? 1 : (K.dx == 2 && K.doe1 == 1) ? 2 : -1;
+  if (shape < 0) return -4;
   const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
   RegParams R;
-  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps;
+  R.match = K.match; R.g = K.g; R.max_steps = K.max_steps; R.pos_score = K.pos_score;
   R.endsfree = K.endsfree; R.pbf = K.pbf; R.pef = K.pef; R.tbf = K.tbf; R.tef = K.tef;
   R.hrows = hrows;
   const RegWindow rw = reg_window(regs, K.endsfree, K.match, K.pbf, K.tbf);
@@ -61,11 +64,15 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
     memset(&res, 0, sizeof res);
     int rc;
     if (plen > REG_MAX_LEN || tlen > REG_MAX_LEN) rc = PAIR_OVERFLOW;
-    else if (regs == 1) rc = run_pair<1, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
-    else if (regs == 2) rc = run_pair<2, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
-    else if (regs == 3) rc = run_pair<3, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
-    else if (regs == 4) rc = run_pair<4, 2, 4>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res);
+#define RUN(PP, DX, DOE) rc = run_pair<PP, DX, DOE>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res)
+#define RUN_SHAPE(PP) do { if (shape == 0) RUN(PP, 2, 4); else if (shape == 1) RUN(PP, 1, 1); else RUN(PP, 2, 1); } while (0)
+    else if (regs == 1) RUN_SHAPE(1);
+    else if (regs == 2) RUN_SHAPE(2);
+    else if (regs == 3) RUN_SHAPE(3);
+    else if (regs == 4) RUN_SHAPE(4);
     else return -3;
+#undef RUN_SHAPE
+#undef RUN
     cig_off[i] = used;
     overflow[i] = (rc == PAIR_OVERFLOW);
     if (rc == PAIR_OVERFLOW) { score[i] = 0; status[i] = 0; cells[i] = 0; memset(locs + 4 * i, 0, 16); continue; }

@@ -154,6 +154,35 @@ def test_gap_linear_edit_indel_match_oracle(emu, oracle, kw):
                 assert np.array_equal(got[k], want[k]), (kw, off16, k)
 
 
+@pytest.mark.parametrize("metric,affine,sign", [
+    (dict(distance="linear", mismatch=2, gap_extension=5), dict(mismatch=2, gap_opening=0, gap_extension=5), 1),
+    (dict(distance="linear", match=-2, mismatch=4, gap_extension=3), dict(match=-2, mismatch=4, gap_opening=0, gap_extension=3), 1),
+    (dict(distance="levenshtein"), dict(mismatch=1, gap_opening=0, gap_extension=1), -1),
+    (dict(distance="indel"), dict(mismatch=2, gap_opening=0, gap_extension=1), -1),
+], ids=["linear-2-5", "linear-match-2", "levenshtein", "indel"])
+@pytest.mark.parametrize("form", [dict(span="end-to-end"), dict(pattern_end_free=7, text_end_free=12),
+                                  dict(pattern_begin_free=3, pattern_end_free=5, text_begin_free=4, text_end_free=6),
+                                  dict(span="end-to-end", max_steps=33)], ids=["e2e", "end-free", "four-free", "max-steps"])
+def test_score_only_metrics_equal_zero_opening_affine(emu, oracle, metric, affine, sign, form):
+    """what metric_as_affine (wfa_params.h) relies on: without a cut-off the M-only recurrences and gap-affine with a
+    zero-cost opening reach the same optimum -- same score (edit / indel: sign flipped) and status"""
+    if metric.get("match", 0) < 0 and (form.get("pattern_begin_free") or form.get("text_begin_free")):
+        pytest.skip("match < 0 with begin-free ends is rejected")
+    rng = np.random.default_rng(43)
+    pairs = []
+    for _ in range(300):
+        lp, lt = int(rng.integers(12, 160)), int(rng.integers(12, 160))
+        pairs.append(("".join("ACGT"[i] for i in rng.integers(0, 4, lp)), "".join("ACGT"[i] for i in rng.integers(0, 4, lt))))
+    for batch in (pairs_from_strings(pairs), generate_pairs(300, 180, 0.12, seed=7, text_flank=8)):
+        want = oracle.align_batch(oracle.make_config(scope="score", **metric, **form), *batch, kind="port")
+        got = emu(oracle.make_config(scope="score", **affine, **form), batch, wcap=1024)
+        assert not got["ovf"].any()
+        done = want["status"] == 0
+        assert np.array_equal(got["status"], want["status"])
+        assert np.array_equal(sign * got["score"][done], want["score"][done])
+        assert np.array_equal(got["score"][~done], want["score"][~done])        # -max_steps either way
+
+
 def test_edit_exact_prune_matches_oracle(emu, oracle):
     """levenshtein end-to-end prunes wavefronts of >= 1000 diagonals (compute_edit.c:219-275)"""
     rng = np.random.default_rng(5)

@@ -90,6 +90,52 @@ def test_register_tier_matches_oracle(emu_reg, oracle, name, kw, n, length, div,
     assert novf <= max_ovf * n, f"{novf} of {n} pairs overflowed the window"
 
 
+ZERO_OPEN = [
+    # the zero-opening shapes the product instantiates score-only: (x, o + e, e) / gcd = (1, 1, 1) and (2, 1, 1)
+    ("edit-like-1-0-1", dict(span="end-to-end", mismatch=1, gap_opening=0, gap_extension=1), 800, 150, 0.08, 0, 2),
+    ("indel-like-2-0-1", dict(span="end-to-end", mismatch=2, gap_opening=0, gap_extension=1), 800, 150, 0.08, 0, 2),
+    ("linear-like-4-0-2", dict(mismatch=4, gap_opening=0, gap_extension=2, text_begin_free=6, text_end_free=9), 800, 150, 0.08, 6, 3),
+    ("edit-like-250bp", dict(span="end-to-end", mismatch=1, gap_opening=0, gap_extension=1), 500, 250, 0.10, 0, 3),
+]
+
+
+@pytest.mark.parametrize("name,kw,n,length,div,flank,regs", ZERO_OPEN, ids=[c[0] for c in ZERO_OPEN])
+@pytest.mark.parametrize("scope", ["score", "full"])
+def test_register_tier_zero_opening_shapes(emu_reg, oracle, name, kw, n, length, div, flank, regs, scope):
+    batch = generate_pairs(n, length, div, seed=zlib.crc32(name.encode()) % 9973, text_flank=flank)
+    cfg = oracle.make_config(scope=scope, **kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu_reg(cfg, batch, regs)
+    assert compare(got, want, scope == "full") <= 0.05 * n
+
+
+@pytest.mark.parametrize("kw", [dict(distance="levenshtein", span="end-to-end"), dict(distance="indel", span="end-to-end"),
+                                dict(distance="linear", span="end-to-end"), dict(distance="levenshtein"),
+                                dict(distance="indel", pattern_end_free=10, text_end_free=10),
+                                dict(distance="linear", pattern_begin_free=5, pattern_end_free=8, text_begin_free=6, text_end_free=9),
+                                dict(distance="levenshtein", span="end-to-end", max_steps=9),
+                                dict(distance="linear", span="end-to-end", max_steps=21)],
+                         ids=lambda kw: "-".join(f"{k}={v}" for k, v in kw.items()))
+def test_score_only_metrics_as_zero_opening_affine(emu_reg, oracle, kw):
+    """metric_as_affine (wfa_params.h): score-only edit / indel / gap-linear alignments without a cut-off run as
+    gap-affine alignments with a zero-cost opening; score and status must equal the M-only recurrence's."""
+    rng = np.random.default_rng(41)
+    pairs = [("", ""), ("ACGT", ""), ("", "ACGT"), ("A", "A"), ("A", "C")]
+    for _ in range(400):
+        lp, lt = int(rng.integers(0, 90)), int(rng.integers(0, 90))
+        pairs.append(("".join("ACGT"[i] for i in rng.integers(0, 4, lp)), "".join("ACGT"[i] for i in rng.integers(0, 4, lt))))
+    if kw.get("span") != "end-to-end":
+        pairs = [pt for pt in pairs if min(len(pt[0]), len(pt[1])) >= 10]
+    cfg = oracle.make_config(scope="score", **kw)
+    for batch in (pairs_from_strings(pairs), generate_pairs(600, 200, 0.1, seed=3, text_flank=6)):
+        want = oracle.align_batch(cfg, *batch, kind="port")
+        got = emu_reg(cfg, batch, 4)
+        done = got["ovf"] == 0
+        assert done.sum() > 0.7 * len(done)
+        for key in ("score", "status"):
+            assert np.array_equal(got[key][done], want[key][done]), (kw, key)
+
+
 def test_register_tier_ragged_and_empty(emu_reg, oracle):
     rng = np.random.default_rng(5)
     acgt = "ACGT"

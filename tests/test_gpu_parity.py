@@ -135,6 +135,30 @@ def test_m_only_metrics_ragged_bytes_and_prune(gpu_ctx, oracle):
             assert cells == sum(case["cells"]), "the pruned wavefront ranges differ from the reference's"
 
 
+def test_score_only_metrics_on_the_affine_tiers_and_on_the_scalar_tiers(gpu_ctx, oracle, monkeypatch):
+    """score-only gap-linear / edit / indel without a cut-off run as zero-opening gap-affine alignments on the
+    register / packed-halfword tiers (metric_as_affine); WFAGPU_NO_METRIC_MAP keeps them on the M-only scalar
+    path.  Both must equal the checker; the fast path must not retry more pairs than its windows explain."""
+    cases = [
+        (dict(distance="levenshtein", span="end-to-end"), generate_pairs(20000, 150, 0.05, seed=3)),
+        (dict(distance="indel", span="end-to-end"), generate_pairs(10000, 250, 0.10, seed=4)),
+        (dict(distance="linear", span="end-to-end"), generate_pairs(10000, 250, 0.10, seed=5)),                 # (2, 1, 1): register tier
+        (dict(distance="linear", span="end-to-end", mismatch=2, gap_extension=5), generate_pairs(4000, 250, 0.10, seed=6)),   # packed-halfword tier
+        (dict(distance="linear", match=-1, mismatch=3, gap_extension=2, pattern_end_free=10, text_end_free=10), generate_pairs(4000, 200, 0.1, seed=7)),
+        (dict(distance="levenshtein", text_begin_free=20, text_end_free=20), generate_pairs(4000, 150, 0.1, seed=8, text_flank=20)),
+        (dict(distance="levenshtein", span="end-to-end", max_steps=14), generate_pairs(4000, 150, 0.1, seed=9)),
+        (dict(distance="levenshtein", span="end-to-end"), generate_pairs(200, 2000, 0.1, seed=10)),
+        (dict(distance="indel", span="end-to-end"), pairs_from_strings(_ragged_pairs(37, 600, 0, 330))),
+    ]
+    for kw, batch in cases:
+        cfg = oracle.make_config(scope="score", **kw)
+        want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
+        assert_same(gpu_ctx.align_batch(cfg, *batch), want, scope_full=False, what=f"mapped {kw}")
+        monkeypatch.setenv("WFAGPU_NO_METRIC_MAP", "1")
+        assert_same(gpu_ctx.align_batch(cfg, *batch), want, scope_full=False, what=f"scalar {kw}")
+        monkeypatch.delenv("WFAGPU_NO_METRIC_MAP")
+
+
 def _ragged_pairs(seed, n, lo_len, hi_len):
     """Pairs of unequal lengths: a pattern, and a text that embeds a mutated copy of part of it
     between random flanks (or is unrelated), so that wavefronts run along the matrix borders."""
