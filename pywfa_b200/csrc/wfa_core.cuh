@@ -492,8 +492,15 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     g.lsync();
   }
 
+#if defined(WFA_GRID_TIMING) && defined(__CUDA_ARCH__)   /* debugging build: where the cycles of a step go (one thread per CTA) */
+  long long tg_prev = clock64(), tg_acc[6] = {0, 0, 0, 0, 0, 0};
+#define WFA_TG(i) { if (G::kGrid) { const long long t_ = clock64(); tg_acc[i] += t_ - tg_prev; tg_prev = t_; } }
+#else
+#define WFA_TG(i)
+#endif
   for (;;) {
     /* ---- after-extend step of score s (extend.c:90-125 / :263-297) ---- */
+    WFA_TG(5)
     if (cur_exists) {
       if (term_k != KNONE) {
         end_k = term_k;
@@ -590,11 +597,13 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     if (TWO_P) { if (++c2 == P.r2) c2 = 0; }
     {
       /* fetch_input, compute.c:298-344: one 16-byte metadata read per source component */
+      /* gap-linear / edit / indel are never two-piece: the flags are dead code in those instantiations */
+      const bool m_only = !TWO_P && P.m_only != 0, no_mis = !TWO_P && P.no_mis != 0, edit_like = !TWO_P && P.edit_like != 0;
       int4 aMo2 = make_int4(1, -1, 0, 0), aI2 = aMo2, aD2 = aMo2;
-      const int4 aMx = P.no_mis ? aMo2 : meta[((s - P.dx) & mmask) * NC + CM];
+      const int4 aMx = no_mis ? aMo2 : meta[((s - P.dx) & mmask) * NC + CM];
       const int4 aMo1 = meta[((s - P.doe1) & mmask) * NC + CM];
       const int4* const rowe1 = meta + ((s - P.de1) & mmask) * NC;
-      const int4 aI1 = P.m_only ? aMo2 : rowe1[CI1], aD1 = P.m_only ? aMo2 : rowe1[CD1];
+      const int4 aI1 = m_only ? aMo2 : rowe1[CI1], aD1 = m_only ? aMo2 : rowe1[CD1];
       if (TWO_P) {
         aMo2 = meta[((s - P.doe2) & mmask) * NC + CM];
         const int4* const rowe2 = meta + ((s - P.de2) & mmask) * NC;
@@ -605,7 +614,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
       const bool n_i2 = TWO_P ? aI2.x > aI2.y : true;
       const bool n_d2 = TWO_P ? aD2.x > aD2.y : true;
       int4* const mrow = meta + (s & mmask) * NC;
-      if ((n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) || (P.edit_like && n_mo1)) {
+      if ((n_mx && n_mo1 && n_i1 && n_d1 && n_mo2 && n_i2 && n_d2) || (edit_like && n_mo1)) {
         /* null step: allocate_output_null, compute.c:374-400.  wavefront_compute_edit (compute_edit.c:329-374)
          * has no null steps: a null predecessor sets num_null_steps = INT_MAX, "unreachable" at once (below) */
         cur_exists = false;
@@ -628,8 +637,8 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         /* wavefront_compute_limits_input, compute.c:40-86 (null inputs carry lo=1, hi=-1) */
         int lo = sMx.lo, hi = sMx.hi;
         lo = imin(lo, sMo1.lo - 1); hi = imax(hi, sMo1.hi + 1);
-        if (P.edit_like) { lo = sMo1.lo - 1; hi = sMo1.hi + 1; }     /* compute_edit.c:346-347 */
-        if (!P.m_only) {                                             /* compute.c:52-58: gap-linear stops at the M sources */
+        if (edit_like) { lo = sMo1.lo - 1; hi = sMo1.hi + 1; }       /* compute_edit.c:346-347 */
+        if (!m_only) {                                             /* compute.c:52-58: gap-linear stops at the M sources */
           lo = imin(lo, sI1.lo + 1); hi = imax(hi, sI1.hi + 1);
           lo = imin(lo, sD1.lo - 1); hi = imax(hi, sD1.hi - 1);
         }
@@ -642,7 +651,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         if (width > wcap) return PAIR_OVERFLOW;
         if (FULL) { if (s >= P.scap || cell_off + width > P.hcap) return PAIR_OVERFLOW; }
         /* allocate_output, compute.c:401-486 */
-        const bool has_i1 = !P.m_only && (!n_mo1 || !n_i1), has_d1 = !P.m_only && (!n_mo1 || !n_d1);
+        const bool has_i1 = !m_only && (!n_mo1 || !n_i1), has_d1 = !m_only && (!n_mo1 || !n_d1);
         const bool has_i2 = TWO_P && (!n_mo2 || !n_i2), has_d2 = TWO_P && (!n_mo2 || !n_d2);
         OffT* const oM = gm.ring[CM] + cm * wcap;
         OffT* const oI1 = gm.ring[CI1] + c1 * wcap;
@@ -652,6 +661,11 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
         /* reductions: [2c] = first in-bounds k, [2c+1] = -(last in-bounds k), [10] = term */
         int red[2 * 5 + 1];
         for (int i = 0; i < 2 * 5 + 1; ++i) red[i] = INT_MAX;
+        WFA_TG(1)
+        /* (r02 experiment, not kept: four diagonals per thread and pass -- all source loads first, then the first
+         * sequence fetches -- for the several-CTAs-per-pair group, whose rings sit behind L2.  16 x 100 kbp got 7 %
+         * slower: ncu shows issue slots 51 % busy, DRAM 14 %, L2 20 %, i.e. the step is bound by its ~400
+         * warp-instructions per cell under the 64-register cap and by the per-score barrier, not by latency.) */
         for (int k = lo + g.rank; k <= hi; k += g.size) {
           const int km = k & wmask, kl = (k - 1) & wmask, kr = (k + 1) & wmask;
           const int i1o = rd<G::kGrid>(sMo1, k - 1, kl), i1e = rd<G::kGrid>(sI1, k - 1, kl);
@@ -698,6 +712,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           }
           oM[km] = off_store<OffT>(mx);
         }
+        WFA_TG(2)
         if (TWO_P) g.template allmin<11>(red);
         else {
           int r7[7] = {red[0], red[1], red[2], red[3], red[4], red[5], red[10]};
@@ -705,6 +720,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           red[0] = r7[0]; red[1] = r7[1]; red[2] = r7[2]; red[3] = r7[3]; red[4] = r7[4]; red[5] = r7[5];
           red[10] = r7[6];
         }
+        WFA_TG(3)
         term_k = red[10];
         /* trim_ends, compute.c:571-605: [first in-bounds, last in-bounds], else null */
         const bool has[5] = {true, has_i1, has_d1, has_i2, has_d2};
@@ -712,14 +728,18 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           if (c < NC && has[c] && red[2 * c] != INT_MAX) { clo[c] = red[2 * c]; chi[c] = -red[2 * c + 1]; }
           else { clo[c] = 1; chi[c] = -1; }
         }
-        if (P.edit_prune && chi[CM] - clo[CM] + 1 >= 1000) {
+        if (!TWO_P && P.edit_prune && chi[CM] - clo[CM] + 1 >= 1000) {
           /* exact pruning of the ends whose best case |k - ak| is worse than the best worst case
            * max(remaining v, remaining h); the reference looks at the offsets BEFORE their extension,
-           * which are recomputed here from the sources (the slot now holds the extended ones) */
+           * which are recomputed here from the source (edit: M[s-1] for all three moves; its descriptor is
+           * fetched again so that nothing stays live across the loop above) */
           const int lo_t = clo[CM], hi_t = chi[CM];
+          const int4 aQ = meta[((s - 1) & mmask) * NC + CM];
+          Src<OffT> sQ;
+          sQ.slot = gm.ring[CM] + aQ.z * wcap; sQ.lo = aQ.x; sQ.hi = aQ.y;
           auto pre = [&](int k) {
             const int km = k & wmask, kl = (k - 1) & wmask, kr = (k + 1) & wmask;
-            const int v = imax(rd<G::kGrid>(sMo1, k + 1, kr), imax(rd<G::kGrid>(sMx, k, km), rd<G::kGrid>(sMo1, k - 1, kl)) + 1);
+            const int v = imax(rd<G::kGrid>(sQ, k + 1, kr), imax(rd<G::kGrid>(sQ, k, km), rd<G::kGrid>(sQ, k - 1, kl)) + 1);
             return in_bounds(k, v, plen, tlen) ? v : OFFNULL;
           };
           auto best = [&](int k) { return k >= ak ? k - ak : ak - k; };
@@ -759,6 +779,10 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
           cell_off += width;
         }
         g.lsync();          /* ring stores were made visible by the barrier inside allmin */
+        WFA_TG(4)
+#if defined(WFA_GRID_TIMING) && defined(__CUDA_ARCH__)
+        ++tg_acc[0];
+#endif
       }
     }
     /* unreachable (extend.c:99-106: M[s] missing and num_null_steps > max_score_scope) and the
@@ -767,7 +791,7 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     {
       const int so = s * P.g;
       if (!cur_exists) {
-        const int su = P.edit_like ? so : s_exist + P.max_scope + 1;
+        const int su = (!TWO_P && P.edit_like) ? so : s_exist + P.max_scope + 1;
         if (su <= so && su < P.max_steps) { status = 2; end_score = su; break; }
       }
       if (so >= P.max_steps) {
@@ -778,6 +802,9 @@ WFA_DEV int align_pair(G& g, const KParams& P, const GroupMem<OffT>& gm, int ple
     }
   }
 
+#if defined(WFA_GRID_TIMING) && defined(__CUDA_ARCH__)
+  if (G::kGrid && g.lrank == 0 && P.dbg) for (int i = 0; i < 6; ++i) atomicAdd(P.dbg + i, (unsigned long long)tg_acc[i]);
+#endif
   /* ---- wavefront_unialign_terminate, unialign.c:147-237 ---- */
   res.cells = cells;
   res.nruns = 0;

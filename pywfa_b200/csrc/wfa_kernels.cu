@@ -217,13 +217,26 @@ struct GridGroup {
   int ncta, phase;
   __device__ __forceinline__ void lsync() { __syncthreads(); }
   __device__ __forceinline__ void sync() {
+    /* the pattern of cooperative groups' grid sync: the CTA barrier before makes the CTA's ring stores
+     * happen-before thread 0's release fence and arrival; the acquire fence after the poll and the CTA barrier
+     * hand what thread 0 saw to the CTA.  fence.acq_rel (MEMBAR.ALL.GPU) instead of __threadfence()'s
+     * sequentially-consistent MEMBAR.SC.GPU.  (A red.release / ld.acquire pair in inline PTX made ptxas spill
+     * 96 bytes per thread in this 64-register kernel.) */
     __syncthreads();
     if (lrank == 0) {
+#ifdef WFA_GRID_SC_FENCE
       __threadfence();
+#else
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
       atomicAdd(&gs->count, 1u);
       target += (unsigned int)ncta;
       while ((int)(*reinterpret_cast<volatile unsigned int*>(&gs->count) - target) < 0) { }
+#ifdef WFA_GRID_SC_FENCE
       __threadfence();
+#else
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
     }
     __syncthreads();
   }

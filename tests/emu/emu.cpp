@@ -26,6 +26,11 @@ struct EmuGroup {
   template <int N> void allmin(int (&)[N]) {}
 };
 
+/* the several-CTAs-per-pair group's code path (G::kGrid), one thread */
+struct EmuGridGroup : EmuGroup {
+  static constexpr bool kGrid = true;
+};
+
 struct EmuBuffers {      /* allocated once per batch */
   std::vector<unsigned char> ring;
   std::vector<int4> meta;
@@ -33,7 +38,7 @@ struct EmuBuffers {      /* allocated once per batch */
   std::vector<HistRow> hmeta;
 };
 
-template <class OffT, bool TWO_P, bool FULL>
+template <class OffT, bool TWO_P, bool FULL, class Group = EmuGroup>
 static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t* tw, int plen, int tlen,
                    std::vector<uint32_t>& stage, PairResult& res) {
   std::vector<uint8_t> ops((size_t)plen + tlen + 8);
@@ -50,8 +55,8 @@ static int run_one(KParams& P, EmuBuffers& B, const uint32_t* pw, const uint32_t
   gm.h_code = B.h_code.data(); gm.hmeta = B.hmeta.data();
   gm.runs_stage = stage.data();
   gm.ops = ops.data(); gm.opcap = (int)ops.size();
-  EmuGroup g;
-  return align_pair<EmuGroup, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
+  Group g;
+  return align_pair<Group, OffT, TWO_P, FULL>(g, P, gm, plen, tlen, res);
 }
 
 /* off16 != 0 selects the int16 offset rings of the short-read tiers */
@@ -96,12 +101,14 @@ extern "C" int emu_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, c
     PairResult res;
     memset(&res, 0, sizeof res);
     int rc;
-#define EMU_RUN(T)                                                                                          \
-    (two_p ? (full ? run_one<T, true, true>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)   \
-                   : run_one<T, true, false>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)) \
-           : (full ? run_one<T, false, true>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)  \
-                   : run_one<T, false, false>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)))
-    if (off16) rc = EMU_RUN(int16_t); else rc = EMU_RUN(int32_t);
+#define EMU_RUN(T, G)                                                                                          \
+    (two_p ? (full ? run_one<T, true, true, G>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)   \
+                   : run_one<T, true, false, G>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)) \
+           : (full ? run_one<T, false, true, G>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)  \
+                   : run_one<T, false, false, G>(P, B, pw.data(), tw.data(), plen, tlen, stage, res)))
+    if (off16 == 2) rc = EMU_RUN(int32_t, EmuGridGroup);          /* off16 == 2: the grid group's code path */
+    else if (off16) rc = EMU_RUN(int16_t, EmuGroup);
+    else rc = EMU_RUN(int32_t, EmuGroup);
 #undef EMU_RUN
     cig_off[i] = used;
     overflow[i] = (rc == PAIR_OVERFLOW);

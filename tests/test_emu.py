@@ -64,6 +64,20 @@ def test_device_source_matches_golden(emu, oracle, case):
         assert r["cells"].tolist() == case["cells"]
 
 
+@pytest.mark.parametrize("case", SYN, ids=[c["name"] for c in SYN])
+def test_device_source_grid_group_path_matches_golden(emu, oracle, case):
+    """the code path of the several-CTAs-per-pair group (G::kGrid: ring loads that bypass L1, int32 rings)"""
+    batch = generate_pairs(case["n"], case["length"], case["div"], case["seed"], text_flank=case["flank"])
+    cfg = oracle.make_config(**case["config"])
+    r = emu(cfg, batch, off16=2)
+    assert not r["ovf"].any()
+    assert r["score"].tolist() == case["score"] and r["status"].tolist() == case["status"]
+    cig = [oracle.runs_to_cigarstring(r["runs"][r["cig_off"][j]:r["cig_off"][j + 1]]) for j in range(case["n"])]
+    assert cig == case["cigars"] and r["locs"].tolist() == case["locations"]
+    if case["config"].get("scope", "full") == "full":
+        assert r["cells"].tolist() == case["cells"]
+
+
 @pytest.mark.parametrize("case", [c for c in SYN if c["length"] <= 2000], ids=[c["name"] for c in SYN if c["length"] <= 2000])
 def test_device_source_int16_rings_match_golden(emu, oracle, case):
     """the short-read tiers keep offsets as int16 (nulls = any negative value)"""
@@ -111,9 +125,10 @@ def test_device_source_matches_oracle_ragged(emu, oracle):
                dict(heuristic="X-drop", xdrop=30), dict(span="end-to-end", scope="score", max_steps=50)):
         cfg = oracle.make_config(**kw)
         want = oracle.align_batch(cfg, *batch, kind="port")
-        got = emu(cfg, batch)
-        for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
-            assert np.array_equal(got[k], want[k]), (kw, k)
+        for mode in (0, 2):
+            got = emu(cfg, batch, off16=mode)
+            for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
+                assert np.array_equal(got[k], want[k]), (kw, mode, k)
 
 
 M_ONLY_CASES = [
@@ -147,7 +162,7 @@ def test_gap_linear_edit_indel_match_oracle(emu, oracle, kw):
     cfg = oracle.make_config(**kw)
     for batch in (pairs_from_strings(pairs), generate_pairs(200, 200, 0.1, seed=3)):
         want = oracle.align_batch(cfg, *batch, kind="port")
-        for off16 in (0, 1):
+        for off16 in (0, 1, 2):
             got = emu(cfg, batch, wcap=1024, off16=off16)
             assert not got["ovf"].any()
             for k in ("score", "status", "cig_off", "runs", "locs", "cells"):
