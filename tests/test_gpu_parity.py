@@ -346,7 +346,7 @@ def test_fastx_streaming(gpu_ctx, oracle, tmp_path):
         seen += n
     assert seen == len(pairs)
     # the same texts out of a mapper's SAM output (reverse-strand records are stored reverse-complemented)
-    comp = str.maketrans("ACGTN", "TGCAN")
+    comp = str.maketrans("ACGTNacgtnRYKMryk", "TGCANtgcanYRMKyrm")       # IUPAC complement, as read_sam's
     with open(tmp_path / "t.sam", "w") as fs:
         fs.write("@HD\tVN:1.6\n@SQ\tSN:ref\tLN:100000\n")
         for i, (p, t) in enumerate(pairs):
