@@ -43,6 +43,10 @@ cudaError_t launch_layout(const int32_t* p_len, const int32_t* t_len, long long 
 cudaError_t launch_pack(const PackArgs& A, bool byte_mode, int max_len, int sms, cudaStream_t st);
 /* bytes of the flagged pairs -> words2 */
 cudaError_t launch_pack_side(const PackArgs& A, int sms, cudaStream_t st);
+/* dst[0 .. nwords) = 0, then dst[at + i] = vals.v[i] (i < MAX_BUCKETS): the per-batch counters, set by a kernel
+ * because a host-to-device copy on the compute stream queues behind the uploads of the chunks ahead */
+struct SmallInts { int v[MAX_BUCKETS]; };
+cudaError_t launch_init_words(uint32_t* dst, int nwords, int at, const SmallInts& vals, cudaStream_t st);
 
 /* mode 0: warp-per-pair (smem ring), 1: block-per-pair (smem ring), 2: block-per-pair (HBM ring) */
 cudaError_t launch_align(const KParams& P, bool two_p, bool full, int mode, bool off16, int grid, int block,

@@ -248,6 +248,17 @@ cudaError_t launch_pack(const PackArgs& A, bool byte_mode, int max_len, int sms,
   return cudaGetLastError();
 }
 
+__global__ void init_words_kernel(uint32_t* dst, int nwords, int at, SmallInts vals) {
+  for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+    const int j = i - at;
+    dst[i] = (j >= 0 && j < MAX_BUCKETS) ? (uint32_t)vals.v[j] : 0u;
+  }
+}
+cudaError_t launch_init_words(uint32_t* dst, int nwords, int at, const SmallInts& vals, cudaStream_t st) {
+  init_words_kernel<<<1, 256, 0, st>>>(dst, nwords, at, vals);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pack_side(const PackArgs& A, int sms, cudaStream_t st) {
   if (A.n <= 0) return cudaSuccess;
   const long long blocks = std::min<long long>((A.n + 7) / 8, (long long)sms * 8);
