@@ -1283,7 +1283,7 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
   for (auto& pb : ctx->pin_pack) CK(pb.ensure(sizeof(PackCounters)));
   if (cig_runs) { CK(ctx->pin_runs.ensure(4)); *cig_runs = ctx->user_runs ? ctx->user_runs : ctx->pin_runs.as<uint32_t>(); }
   const double t_start = now_ms();
-  /* chunking: the first chunk is small (its upload is the only one nothing overlaps), the others are a
+  /* chunking: the first chunks are small (the first upload is the only one nothing overlaps), the others are a
    * twelfth of the batch: when the kernels bind, a chunk costs a fixed ~0.3 ms (launches, one host round
    * trip, the tail of its persistent kernels); when the upload binds (several GPUs sharing the host's
    * memory bandwidth), what is not overlapped is the kernel time of the LAST chunk, so chunks must not be
@@ -1300,10 +1300,15 @@ extern "C" int wfagpu_align_batch(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, c
       mean = std::max(mean / (double)probe, 1.0);
       const int64_t by_bytes = std::max<int64_t>(65536, (int64_t)(1.0e9 / mean));
       chunk = std::min(by_bytes, std::max<int64_t>(131072, (n + 11) / 12));
-      first = std::min(chunk, std::max<int64_t>(32768, n / 32));
+      first = std::min<int64_t>(chunk, 32768);
     }
+    /* ramp: 32 k pairs, then doubling up to the chunk size -- a chunk's kernels hide the upload of the next,
+     * which the copy engine moves about twice as fast as the short-read kernels consume it */
     starts.push_back(0);
-    for (int64_t off = std::min(first, n); off < n; off += chunk) starts.push_back(off);
+    for (int64_t off = std::min(first, n), sz = first; off < n; off += sz) {
+      starts.push_back(off);
+      sz = std::min(chunk, 2 * sz);
+    }
     starts.push_back(n);
     if (n == 0) starts.assign({0, 0});
   }
