@@ -841,15 +841,20 @@ int align_occupancy(bool two_p, bool full, int mode, bool off16, int block, size
   WFA_DISPATCH(occupancy_one, block, smem);
 }
 
-/* register tier: instantiated for the penalty shapes (x, o+e, e)/gcd = (2, 4, 1) -- pywfa's
- * default 4/6/2 -- with windows of 128 / 192 / 256 diagonals, and score-only for the zero-opening
- * shapes (1, 1, 1) and (2, 1, 1): edit, indel and pywfa's default gap-linear 4/2 (metric_as_affine) */
+/* register tier: instantiated for the penalty shapes (x, o+e, e)/gcd = (2, 4, 1) -- pywfa's default 4/6/2 --,
+ * (4, 7, 1) -- 4/6/1, bwa-like --, (1, 2, 1) -- 1/1/1, 2/2/2 -- and (1, 3, 1) -- 2/4/2, 1/2/1 -- with windows of
+ * 128 / 192 / 256 diagonals, and score-only for the zero-opening shapes (1, 1, 1) and (2, 1, 1): edit, indel and
+ * pywfa's default gap-linear 4/2 (metric_as_affine).  Other sets run on the packed-halfword tier (3-12x slower
+ * on 150 bp, profiles/r02_results.md). */
+#define WFA_REG_BOTH(STMT, PP, DX, DOE) do { if (full) { STMT(PP, DX, DOE, true); } else { STMT(PP, DX, DOE, false); } } while (0)
 #define WFA_REG_DISPATCH_P(STMT, PP)                            \
   do {                                                          \
-    if (shape == 0) {                                           \
-      if (full) { STMT(PP, 2, 4, true); } else { STMT(PP, 2, 4, false); } \
-    } else if (shape == 1) { STMT(PP, 1, 1, false); }           \
-    else { STMT(PP, 2, 1, false); }                             \
+    if (shape == 0) WFA_REG_BOTH(STMT, PP, 2, 4);               \
+    else if (shape == 1) { STMT(PP, 1, 1, false); }             \
+    else if (shape == 2) { STMT(PP, 2, 1, false); }             \
+    else if (shape == 3) WFA_REG_BOTH(STMT, PP, 4, 7);          \
+    else if (shape == 4) WFA_REG_BOTH(STMT, PP, 1, 2);          \
+    else WFA_REG_BOTH(STMT, PP, 1, 3);                          \
   } while (0)
 #define WFA_REG_DISPATCH(STMT)                                  \
   do {                                                          \
@@ -863,6 +868,9 @@ static int reg_shape(int dx, int doe, int de, bool full) {
   if (dx == 2 && doe == 4) return 0;
   if (!full && dx == 1 && doe == 1) return 1;
   if (!full && dx == 2 && doe == 1) return 2;
+  if (dx == 4 && doe == 7) return 3;
+  if (dx == 1 && doe == 2) return 4;
+  if (dx == 1 && doe == 3) return 5;
   return -1;
 }
 
@@ -900,9 +908,12 @@ static cudaError_t init_pair(int smem_optin) {
 static cudaError_t init_reg(int smem_optin) {
   cudaError_t e = cudaSuccess;
   for (int regs = 2; regs <= 4; ++regs)
-    for (int v = 0; v < 4; ++v) {
-      const int shape = v < 2 ? 0 : v - 1;
-      const bool full = v == 1;
+    for (int v = 0; v < 10; ++v) {
+      /* (shape, scope) pairs that exist: shape 0 / 3 / 4 / 5 with both scopes, 1 / 2 score-only */
+      static const int shapes[10] = {0, 0, 1, 2, 3, 3, 4, 4, 5, 5};
+      static const bool fulls[10] = {false, true, false, false, false, true, false, true, false, true};
+      const int shape = shapes[v];
+      const bool full = fulls[v];
 #define WFA_REG_INIT(PP, DX, DOE, FULL) \
   e = cudaFuncSetAttribute(wfa_reg_kernel<PP, DX, DOE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin)
       WFA_REG_DISPATCH(WFA_REG_INIT);

@@ -270,7 +270,10 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
   const int winw = B.maxp + B.maxt + 2;       /* sequence windows: one word per base */
   if (!no_reg && !B.byte_mode && !B.two_p && !k.m_only && k.heuristic == 0 && std::max(B.maxp, B.maxt) <= REG_MAX_LEN && 4 * winw <= 8192) {
     const int maxlen = std::max(B.maxp, B.maxt);
-    const int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;     /* window the typical pair of this length needs */
+    /* window the typical pair of this length needs: tuned for the default shape (x/gcd = 2); a wavefront
+     * spreads one diagonal per score unit either side, and a mismatch costs x/gcd units, so other shapes scale */
+    int first = maxlen <= 192 ? 2 : maxlen <= 320 ? 3 : 4;
+    if (k.dx != 2) first = std::max(2, std::min(4, (int)((0.32 * maxlen * k.dx + 63.0) / 64.0)));
     for (int regs = first; regs <= 4; ++regs) {
       if (regs == 3 && first == 2) continue;                         /* 128 -> 256 directly: few pairs get that far */
       if (!reg_tier_supported(k.dx, k.doe1, k.de1, regs, B.full)) continue;

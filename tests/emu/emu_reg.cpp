@@ -41,7 +41,8 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
   const bool mapped = metric_as_affine(*cfg, K);       /* score-only linear / edit / indel as zero-opening gap-affine */
   if ((cfg->distance != WFAGPU_DISTANCE_AFFINE && !mapped) || cfg->heuristic != WFAGPU_HEURISTIC_NONE) return -4;
   /* the penalty shapes the product instantiates (wfa_kernels.cu: reg_shape) */
-  const int shape = K.de1 != 1 ? -1 : (K.dx == 2 && K.doe1 == 4) ? 0 : (K.dx == 1 && K.doe1 == 1) ? 1 : (K.dx == 2 && K.doe1 == 1) ? 2 : -1;
+  const int shape = K.de1 != 1 ? -1 : (K.dx == 2 && K.doe1 == 4) ? 0 : (K.dx == 1 && K.doe1 == 1) ? 1 : (K.dx == 2 && K.doe1 == 1) ? 2
+                    : (K.dx == 4 && K.doe1 == 7) ? 3 : (K.dx == 1 && K.doe1 == 2) ? 4 : (K.dx == 1 && K.doe1 == 3) ? 5 : -1;
   if (shape < 0) return -4;
   const bool full = cfg->scope == WFAGPU_SCOPE_FULL;
   RegParams R;
@@ -65,7 +66,8 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
     int rc;
     if (plen > REG_MAX_LEN || tlen > REG_MAX_LEN) rc = PAIR_OVERFLOW;
 #define RUN(PP, DX, DOE) rc = run_pair<PP, DX, DOE>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res)
-#define RUN_SHAPE(PP) do { if (shape == 0) RUN(PP, 2, 4); else if (shape == 1) RUN(PP, 1, 1); else RUN(PP, 2, 1); } while (0)
+#define RUN_SHAPE(PP) do { if (shape == 0) RUN(PP, 2, 4); else if (shape == 1) RUN(PP, 1, 1); else if (shape == 2) RUN(PP, 2, 1); \
+                           else if (shape == 3) RUN(PP, 4, 7); else if (shape == 4) RUN(PP, 1, 2); else RUN(PP, 1, 3); } while (0)
     else if (regs == 1) RUN_SHAPE(1);
     else if (regs == 2) RUN_SHAPE(2);
     else if (regs == 3) RUN_SHAPE(3);

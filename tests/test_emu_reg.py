@@ -109,6 +109,29 @@ def test_register_tier_zero_opening_shapes(emu_reg, oracle, name, kw, n, length,
     assert compare(got, want, scope == "full") <= 0.05 * n
 
 
+MORE_SHAPES = [
+    # (x, o + e, e) / gcd = (4, 7, 1), (1, 2, 1), (1, 3, 1): bwa-like 4/6/1, 1/1/1 (2/2/2), 2/4/2 (1/2/1)
+    ("bwa-like-4-6-1", dict(span="end-to-end", gap_extension=1), 800, 150, 0.08, 0, 3, 0.05),
+    ("bwa-like-4-6-1-128-overflows", dict(span="end-to-end", gap_extension=1), 400, 150, 0.08, 0, 2, 0.6),
+    ("bwa-like-4-6-1-250bp", dict(span="end-to-end", gap_extension=1), 500, 250, 0.08, 0, 4, 0.25),
+    ("bwa-like-endsfree", dict(gap_extension=1, pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7), 600, 200, 0.10, 4, 4, 0.3),
+    ("1-1-1", dict(span="end-to-end", mismatch=1, gap_opening=1, gap_extension=1), 800, 150, 0.08, 0, 2, 0.05),
+    ("2-2-2", dict(mismatch=2, gap_opening=2, gap_extension=2), 600, 250, 0.10, 0, 4, 0.05),
+    ("2-4-2", dict(span="end-to-end", mismatch=2, gap_opening=4, gap_extension=2), 800, 150, 0.08, 0, 2, 0.05),
+    ("1-2-1-max-steps", dict(span="end-to-end", mismatch=1, gap_opening=2, gap_extension=1, max_steps=17), 600, 150, 0.1, 0, 3, 0.05),
+]
+
+
+@pytest.mark.parametrize("name,kw,n,length,div,flank,regs,max_ovf", MORE_SHAPES, ids=[c[0] for c in MORE_SHAPES])
+@pytest.mark.parametrize("scope", ["score", "full"])
+def test_register_tier_more_penalty_shapes(emu_reg, oracle, name, kw, n, length, div, flank, regs, max_ovf, scope):
+    batch = generate_pairs(n, length, div, seed=zlib.crc32(name.encode()) % 9973, text_flank=flank)
+    cfg = oracle.make_config(scope=scope, **kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu_reg(cfg, batch, regs)
+    assert compare(got, want, scope == "full") <= max_ovf * n
+
+
 @pytest.mark.parametrize("kw", [dict(distance="levenshtein", span="end-to-end"), dict(distance="indel", span="end-to-end"),
                                 dict(distance="linear", span="end-to-end"), dict(distance="levenshtein"),
                                 dict(distance="indel", pattern_end_free=10, text_end_free=10),

@@ -49,6 +49,14 @@ CASES = [
     # beyond the packed-halfword tier's length limit with a narrow band: the scalar shared-memory tiers
     ("scalar-tiers-20kbp-adaptive", dict(span="end-to-end", heuristic="adaptive"), 24, 20000, 0.10, 0),
     ("scalar-tiers-20kbp-xdrop-2p", dict(distance="affine2p", heuristic="X-drop", xdrop=400, scope="score"), 24, 20000, 0.05, 0),
+    # the other penalty shapes the register tier is compiled for: (4,7,1), (1,2,1), (1,3,1)
+    ("reg-shape-bwa-like-4-6-1", dict(span="end-to-end", gap_extension=1), 20000, 150, 0.05, 0),
+    ("reg-shape-bwa-like-4-6-1-score-250bp", dict(span="end-to-end", gap_extension=1, scope="score"), 10000, 250, 0.08, 0),
+    ("reg-shape-bwa-like-endsfree", dict(gap_extension=1, pattern_begin_free=10, pattern_end_free=20, text_begin_free=5, text_end_free=7), 5000, 200, 0.10, 4),
+    ("reg-shape-1-1-1", dict(span="end-to-end", mismatch=1, gap_opening=1, gap_extension=1), 20000, 150, 0.05, 0),
+    ("reg-shape-2-2-2-score", dict(mismatch=2, gap_opening=2, gap_extension=2, scope="score"), 10000, 250, 0.10, 0),
+    ("reg-shape-2-4-2", dict(span="end-to-end", mismatch=2, gap_opening=4, gap_extension=2), 20000, 150, 0.05, 0),
+    ("reg-shape-1-2-1-max-steps", dict(span="end-to-end", mismatch=1, gap_opening=2, gap_extension=1, max_steps=17), 5000, 150, 0.1, 0),
     # gap-linear / edit / indel (compute_linear.c, compute_edit.c): M wavefronts only, scalar tiers
     ("linear-150bp-e2e", dict(distance="linear", span="end-to-end"), 5000, 150, 0.08, 0),
     ("linear-250bp-score", dict(distance="linear", span="end-to-end", scope="score", mismatch=2, gap_extension=5), 5000, 250, 0.10, 0),
