@@ -1060,8 +1060,10 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
           } else {
             /* go on with the whole queue from where the probe stopped (every group's last, failed fetch
              * moved the work counter past the probe) */
-            hc->work[li] = (int)groups;
-            CK(cudaMemcpyAsync(&dc->work[li], &hc->work[li], sizeof(int), cudaMemcpyHostToDevice, st));
+            SmallInts w;
+            memset(&w, 0, sizeof w);
+            w.v[0] = (int)groups;
+            CK(launch_init_words(reinterpret_cast<uint32_t*>(&dc->work[li]), 1, 0, w, st));       /* (no copy on this stream: see above) */
             k.work_limit = INT_MAX;
             const int r = launch_tier(); if (r != WFAGPU_OK) return r;
           }
