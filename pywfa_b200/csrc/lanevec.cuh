@@ -97,6 +97,8 @@ __device__ __forceinline__ vu load_win_at(lanead a, vi idx, vb p, uint32_t dflt)
 }
 /* min(a + b, c): VIADDMNMX */
 __device__ __forceinline__ vi vaddmin(vi a, vi b, vi c) { return __viaddmin_s32(a, b, c); }
+/* orders the warp's shared-memory accesses: what other lanes stored before is visible to the lane that reads after */
+__device__ __forceinline__ void fence_warp() { __syncwarp(); }
 /* pin a loop-invariant value in its register: the compiler may neither re-derive it nor fold it away */
 __device__ __forceinline__ void keep(uint32_t& x) { asm volatile("" : "+r"(x)); }
 __device__ __forceinline__ void keep(int& x) { asm volatile("" : "+r"(x)); }

@@ -491,6 +491,9 @@ WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_
   } else {
     res.score = classic_score(R.match, end_off - end_k, end_off, end_score, R.pos_score);
     res.status = ST_COMPLETED;
+    /* the leader reads origin codes every lane stored, and later overwrites the arena with the runs
+     * (compute-sanitizer racecheck flagged the missing barrier as an intra-warp hazard) */
+    lv::fence_warp();
     if (is_leader) {
       FwdEmitter em; em.init(runs_stage, R.runcap);
       const int n = backtrace_origin<A.HS>(hist, 32 * P, A.kbase, DX, DOE, 1, A.s, end_k, plen, tlen, pw, tw, ops, R.opcap, em);

@@ -130,6 +130,7 @@ inline vu load_win_at(const lanead& a, const vi& idx, const vb& p, uint32_t dflt
 }
 inline vi vaddmin(const vi& a, const vi& b, const vi& c) { vi r; LV_FOR { const int t = a.v[l] + b.v[l]; r.v[l] = t < c.v[l] ? t : c.v[l]; } return r; }
 inline vb operator==(const vu& a, uint32_t b) { vb r{0}; LV_FOR if (a.v[l] == b) r.m |= 1u << l; return r; }
+inline void fence_warp() {}          /* one host thread models the whole warp: nothing to order */
 template <class T> inline void keep(T&) {}
 inline void scatter_u32(uint32_t* base, const vi& idx, const vu& val, const vb& p) { LV_FOR if (p.m >> l & 1) base[idx.v[l]] = val.v[l]; }
 inline vu gather_u32(const uint32_t* base, const vi& idx, const vb& p) { vu r; LV_FOR r.v[l] = (p.m >> l & 1) ? base[idx.v[l]] : 0u; return r; }
