@@ -81,9 +81,9 @@ typedef struct wfagpu_config {
   int32_t steps_between_cutoffs;
   int32_t xdrop;
   int32_t match;                   /* <= 0; user penalties, NOT normalised   */
-  int32_t mismatch;
-  int32_t gap_opening1;
-  int32_t gap_extension1;
+  int32_t mismatch;                /* (EDIT / INDEL ignore all six penalties) */
+  int32_t gap_opening1;            /* unused by LINEAR                        */
+  int32_t gap_extension1;          /* LINEAR: the indel penalty               */
   int32_t gap_opening2;
   int32_t gap_extension2;
   int32_t max_steps;               /* <= 0 means unlimited (align.pyx:415)   */
@@ -98,9 +98,10 @@ typedef struct wfagpu_batch wfagpu_batch;   /* a packed, device-resident batch *
 /* Fill *cfg with pywfa's constructor defaults (pywfa/align.pyx:309-334). */
 void wfagpu_config_default(wfagpu_config_t* cfg);
 
-/* Validate what wavefront_penalties_set_affine/affine2p (W/wavefront/
- * wavefront_penalties.c:95-173) and wavefront_align_presets__checks
- * (W/wavefront/wavefront_align.c:48-103) exit(1) on.  plen/tlen < 0 skips the
+/* Validate what wavefront_penalties_set_linear/affine/affine2p (W/wavefront/
+ * wavefront_penalties.c:62-173) and wavefront_align_presets__checks
+ * (W/wavefront/wavefront_align.c:48-103, incl. "drop heuristics with edit /
+ * indel") exit(1) on.  plen/tlen < 0 skips the
  * per-pair ends-free bound check.  Returns WFAGPU_OK or WFAGPU_EINVAL (message
  * in err). */
 int wfagpu_config_check(const wfagpu_config_t* cfg, int64_t plen, int64_t tlen,
