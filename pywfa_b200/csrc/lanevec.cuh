@@ -70,6 +70,8 @@ __device__ __forceinline__ vu splat(uint32_t x) { return x; }
 __device__ __forceinline__ vi splati(int x) { return x; }
 
 __device__ __forceinline__ vi vclz(vu x) { return __clz((int)x); }
+/* 4-bit symbol codes, bit 0 of a nibble = "not the wildcard": 0xF in every nibble in which neither operand is the wildcard */
+__device__ __forceinline__ vu nib_both(vu a, vu b) { return (a & b & 0x11111111u) * 15u; }
 __device__ __forceinline__ vu vbrev(vu x) { return __brev(x); }
 
 /* ---- memory ---- */
@@ -126,3 +128,59 @@ __device__ __forceinline__ int hist_load(const histref& h, int off) {
 }  // namespace wfagpu
 
 #endif
+
+/* ---- scalar helpers shared by the device code and the host model ---- */
+#ifdef __CUDACC__
+#define WFA_LV_HD __host__ __device__ __forceinline__
+#else
+#define WFA_LV_HD inline
+#endif
+namespace wfagpu {
+namespace lv {
+
+/*
+ * Byte mode on the register tier: 4-bit symbol codes, 8 bases per word (base b of a word in bits 4b..4b+3).
+ * The wildcard (pywfa's wildcard= byte, pywfa/align.pyx:297-304) is code 0; A C G T N R Y K are 8..15 (bit 3 =
+ * "not the wildcard"); any other byte makes the pair ineligible (`bad`; it runs on the scalar tiers).
+ * w0 / w1: upper-cased bytes 0-3 / 4-7 of the word, nvalid: how many of them lie inside the sequence.
+ */
+WFA_LV_HD uint32_t nib_pack8(uint32_t w0, uint32_t w1, int nvalid, uint32_t wild, bool& bad) {
+  const unsigned long long LO = (8ull << 0) | (9ull << 8) | (10ull << 24) | (15ull << 40) | (12ull << 52);   /* A C G K N */
+  const unsigned long long HI = (13ull << 4) | (11ull << 12) | (14ull << 32);                                /* R T Y */
+  uint32_t out = 0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const uint32_t c = ((b < 4 ? w0 : w1) >> (8 * (b & 3))) & 0xffu;
+    const uint32_t idx = c - 'A';
+    const unsigned long long tb = (idx & 16u) ? HI : LO;
+    uint32_t code = idx < 26u ? (uint32_t)(tb >> ((idx & 15u) * 4u)) & 15u : 0u;
+    const bool is_wild = wild != 0u && c == wild;
+    if (b < nvalid) { if (is_wild) code = 0u; else if (code == 0u) bad = true; }
+    else code = 0u;
+    out |= code << (4 * b);
+  }
+  return out;
+}
+
+/* per lane: the 8 bases of one nibble word; `bad` collects "a byte outside the symbol set" */
+#if defined(__CUDACC__) && !defined(WFA_LANEVEC_HOST)
+__device__ __forceinline__ vu nib8(vu w0, vu w1, vi nvalid, uint32_t wild, vb& bad) {
+  bool b = false;
+  const vu r = nib_pack8(w0, w1, nvalid, wild, b);
+  bad = bad || b;
+  return r;
+}
+#elif defined(WFA_LANEVEC_HOST)
+inline vu nib8(const vu& w0, const vu& w1, const vi& nvalid, uint32_t wild, vb& bad) {
+  vu r;
+  for (int l = 0; l < 32; ++l) {
+    bool b = false;
+    r.v[l] = nib_pack8(w0.v[l], w1.v[l], nvalid.v[l], wild, b);
+    if (b) bad.m |= 1u << l;
+  }
+  return r;
+}
+#endif
+
+}  // namespace lv
+}  // namespace wfagpu

@@ -1022,6 +1022,8 @@ cudaError_t init_kernels(int smem_optin) {
         }
   const cudaError_t e = init_reg(smem_optin);
   if (e != cudaSuccess) return e;
+  const cudaError_t eb = init_regb(smem_optin);
+  if (eb != cudaSuccess) return eb;
   const cudaError_t e2 = init_vec(smem_optin);
   if (e2 != cudaSuccess) return e2;
   const cudaError_t e3 = init_pair(smem_optin);

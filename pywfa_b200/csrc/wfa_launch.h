@@ -60,6 +60,13 @@ bool reg_tier_supported(int dx, int doe, int de, int regs, bool full);
 cudaError_t launch_reg(const KParams& P, int regs, bool full, int grid, int block, size_t smem, cudaStream_t st);
 int reg_occupancy(const KParams& P, int regs, bool full, int block, size_t smem);
 
+/* byte mode on the register tier (wfa_reg_bytes.cu): pairs with non-ACGT bytes / the wildcard, 256-diagonal window */
+bool regb_tier_supported(int dx, int doe, int de, bool full);
+int regb_regs();
+cudaError_t launch_regb(const KParams& P, bool full, int grid, int block, size_t smem, cudaStream_t st);
+int regb_occupancy(const KParams& P, bool full, int block, size_t smem);
+cudaError_t init_regb(int smem_optin);
+
 /* packed-halfword tier (wfa_vec.cuh): nw = warps per pair (1, 8 or 16) */
 cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st);
 int vec_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t smem);

@@ -88,7 +88,7 @@ WFA_DEV int origin_code(const lv::histref& h, int row_bytes, int s, int d) {
 template <bool SH>
 WFA_DEV int backtrace_origin(const lv::histref& hist, int row_bytes, int kbase, int dx, int doe, int de,
                              int s_end, int k_end, int plen, int tlen, const uint32_t* pw, const uint32_t* tw,
-                             uint8_t* ops, int opcap, FwdEmitter& em) {
+                             uint8_t* ops, int opcap, FwdEmitter& em, int wild = -1) {
   int s = s_end, d = k_end - kbase, nops = 0;
   int mt = CM;
   while (s > 0) {
@@ -111,7 +111,7 @@ WFA_DEV int backtrace_origin(const lv::histref& hist, int row_bytes, int kbase, 
     }
   }
   if (nops > opcap) return -1;
-  replay_ops(ops, nops, kbase + d, plen, tlen, pw, tw, em);
+  replay_ops(ops, nops, kbase + d, plen, tlen, pw, tw, em, wild);
   return em.n;
 }
 
@@ -124,19 +124,46 @@ WFA_DEV int backtrace_origin(const lv::histref& hist, int row_bytes, int kbase, 
  * word past the end); bases beyond the sequence end are garbage and are clamped away by the
  * caller.  `len + 1` windows are written.
  */
+/* CB = bits per base of `words`: 2 (ACGT codes, 16 bases per window) or 4 (the symbol codes of byte mode,
+ * nibble_words below: 8 bases per window; the bit reversal also reverses every code, which equality does not mind) */
+template <int CB = 2>
 WFA_DEV void build_windows(const uint32_t* words, int len, uint32_t* win) {
   using namespace lv;
+  constexpr int LG = CB == 2 ? 4 : 3;              /* log2(bases per word) */
   const vi lane = lane_id();
   for (int i0 = 0; i0 <= len; i0 += 32) {
     const vi i = lane + i0;
     const vb in = i <= len;
-    const vi j = i >> 4;
-    const vu w = vfunnel_r(gather_u32(words, j, in), gather_u32(words, j + 1, in), (i & 15) << 1);
+    const vi j = i >> LG;
+    const vu w = vfunnel_r(gather_u32(words, j, in), gather_u32(words, j + 1, in), (i & ((1 << LG) - 1)) << (5 - LG));
     scatter_u32(win, i, vbrev(w), in);
   }
 }
 
-template <int P, int DX, int DOE, bool FULL, bool HS_ = reg_hist_in_smem(P, FULL)>
+/*
+ * Byte mode (non-ACGT input / the wildcard; the reference compares bytes:
+ * W/wavefront/wavefront_extend_kernels.c:167-203 through wildcard_match_fun, pywfa/align.pyx:297-304):
+ * the pair's upper-cased bytes (4 per word, wfa_pack.cu: pack_bytes_kernel) -> 4-bit symbol codes, 8 per word
+ * (lv::nib_pack8), (len >> 3) + 2 words written (the windows read one word past the last base).
+ * Returns false if the sequence holds a byte outside the symbol set (the pair then takes the scalar tiers).
+ */
+WFA_DEV bool nibble_words(const uint32_t* bytes, int len, uint32_t* out, int wild) {
+  using namespace lv;
+  const vi lane = lane_id();
+  const int nout = (len >> 3) + 2, nin = (len + 3) >> 2;
+  vb bad = vfalse();
+  for (int j0 = 0; j0 < nout; j0 += 32) {
+    const vi j = lane + j0;
+    const vb in = j < nout;
+    const vi b0 = j + j;
+    const vu w0 = gather_u32(bytes, b0, in & (b0 < nin)), w1 = gather_u32(bytes, b0 + 1, in & (b0 + 1 < nin));
+    const vi left = splati(len) - (j << 3);         /* bases of the sequence from this word on (<= 0: padding) */
+    scatter_u32(out, j, nib8(w0, w1, left, (uint32_t)wild, bad), in);
+  }
+  return !any(bad);
+}
+
+template <int P, int DX, int DOE, bool FULL, bool HS_ = reg_hist_in_smem(P, FULL), int CB = 2>
 struct RegAligner {
   static constexpr int RM = DX > DOE ? DX : DOE;   /* M ring: M[r] = wavefront of score s-1-r when score s is computed */
   static constexpr int DE = 1;
@@ -175,6 +202,21 @@ struct RegAligner {
   int status;                                      /* 0 running, 1 end reached, 3 max steps, 4 overflow */
   int cur_lo, cur_hi;                              /* window range [first, last] of the newest M wavefront */
 
+  /* pattern XOR text from the cells' positions on: the first set bit marks the first differing base.  Byte mode
+   * (CB = 4): 8 symbol codes per word, and a position where either side is the wildcard (code 0) never differs */
+  static constexpr int LGC = CB == 2 ? 1 : 2;      /* log2(bits per base) */
+  template <int B>
+  WFA_DEV lv::vu diff_at(const lv::vi& off, const lv::vb& p) {
+    using namespace lv;
+    if constexpr (CB == 2) {
+      return load_win_at<-32 * B>(pa, off, p, 0u) ^ load_win_at<0>(ta, off, p, 0x80000000u);
+    } else {
+      /* idle lanes see the codes 8 and 9 (bit-reversed in the window): "first base differs" */
+      const vu a = load_win_at<-32 * B>(pa, off, p, 0x10000000u), b = load_win_at<0>(ta, off, p, 0x90000000u);
+      return (a ^ b) & nib_both(a, b);
+    }
+  }
+
   /* ---- extension of one block of 32 diagonals (extend_kernels.c:64-110), in place in its half of
    * the packed register `mn`, followed by the edge / termination bookkeeping (termination.c:37-162) ---- */
   template <int B>
@@ -187,12 +229,12 @@ struct RegAligner {
     const vb valid = off0 >= 0;
     /* 16 bases per XOR; a null cell loads nothing and sees "first base differs", so it never moves;
      * min(offset + matches, ub) clamps the run at the end of the diagonal (VIADDMNMX) */
-    const vu x = load_win_at<-32 * B>(pa, off0, valid, 0u) ^ load_win_at<0>(ta, off0, valid, 0x80000000u);
-    vi off = vaddmin(off0, vclz(x) >> 1, ubk);
+    const vu x = diff_at<B>(off0, valid);
+    vi off = vaddmin(off0, vclz(x) >> LGC, ubk);
     vb more = (x == 0u) & (off < ubk);
     while (any(more)) {
-      const vu y = load_win_at<-32 * B>(pa, off, more, 0u) ^ load_win_at<0>(ta, off, more, 0x80000000u);
-      off = vaddmin(off, vclz(y) >> 1, ubk);
+      const vu y = diff_at<B>(off, more);
+      off = vaddmin(off, vclz(y) >> LGC, ubk);
       more = more & (y == 0u) & (off < ubk);
     }
     mn = HI ? put_hi(mn, off) : put_lo(mn, off);
@@ -466,17 +508,17 @@ struct RegAligner {
 
 /*
  * Align one pair on the register tier.  pw / tw: 2-bit packed words (any memory, readable one
- * word past the end; used by the backtrace); pwin / twin: the sequence windows of
- * build_windows in shared memory.  ops / runs_stage are per-warp scratch (scope=full).
+ * word past the end; used by the backtrace) -- byte mode (CB = 4): the pair's bytes, 4 per word, and
+ * wild = the wildcard byte or 0; pwin / twin: the sequence windows of build_windows<CB> in shared memory.  ops / runs_stage are per-warp scratch (scope=full).
  * is_leader: exactly one lane of the warp (device) or true (host model) -- it runs the
  * backtrace.  Returns PAIR_DONE (res filled by every lane except nruns / locs, which only the
  * leader knows and must be broadcast by the caller) or PAIR_OVERFLOW.
  */
-template <int P, int DX, int DOE, bool FULL, bool HS = reg_hist_in_smem(P, FULL)>
+template <int P, int DX, int DOE, bool FULL, bool HS = reg_hist_in_smem(P, FULL), int CB = 2>
 WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_t* tw, lv::seqref pwin, lv::seqref twin,
                            int plen, int tlen, const lv::histref& hist, uint8_t* ops, uint32_t* runs_stage, bool is_leader,
-                           PairResult& res) {
-  RegAligner<P, DX, DOE, FULL, HS> A;
+                           PairResult& res, int wild = -1) {
+  RegAligner<P, DX, DOE, FULL, HS, CB> A;
   A.init(R, pwin, twin, plen, tlen, hist);
   int end_k = 0, end_off = 0;
   if (A.run(end_k, end_off) == PAIR_OVERFLOW) return PAIR_OVERFLOW;
@@ -496,7 +538,7 @@ WFA_DEV int align_pair_reg(const RegParams& R, const uint32_t* pw, const uint32_
     lv::fence_warp();
     if (is_leader) {
       FwdEmitter em; em.init(runs_stage, R.runcap);
-      const int n = backtrace_origin<A.HS>(hist, 32 * P, A.kbase, DX, DOE, 1, A.s, end_k, plen, tlen, pw, tw, ops, R.opcap, em);
+      const int n = backtrace_origin<A.HS>(hist, 32 * P, A.kbase, DX, DOE, 1, A.s, end_k, plen, tlen, pw, tw, ops, R.opcap, em, wild);
       res.nruns = n;
       if (n >= 0) locations_from_runs(runs_stage, imin(n, R.runcap), plen, tlen, res.locs);
     }

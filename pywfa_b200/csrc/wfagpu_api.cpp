@@ -95,13 +95,14 @@ struct StageRing {
 
 /* test / tuning switches, read from the environment once per call (WFAGPU_* variables) */
 struct DebugKnobs {
-  bool trace = false, no_reg = false, no_vec = false, no_tier_skip = false, no_buckets = false, host_stage = false, no_metric_map = false;
+  bool trace = false, no_reg = false, no_regb = false, no_vec = false, no_tier_skip = false, no_buckets = false, host_stage = false, no_metric_map = false;
   int vec_nw = 0, block_threads = 0;
   long long chunk = 0;
 };
 
 struct Tier {
   int regs = 0;            /* > 0: register-resident tier (wfa_reg.cuh) with a window of 64*regs diagonals */
+  bool bytes = false;      /* ... in byte mode (wfa_reg_bytes.cu): takes the pairs with non-ACGT bytes / the wildcard */
   int vec_nw = 0;          /* > 0: packed-halfword tier (wfa_vec.cuh) with vec_nw warps per pair */
   bool vec_seqw = false;   /* ... with the sequences staged as per-base windows */
   int max_groups = 0;      /* > 0: at most this many pairs in flight (history arena per pair grows accordingly) */
@@ -289,6 +290,18 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
       B.tiers.push_back(t);
     }
   }
+  /* ... and the same tier in byte mode for the pairs the 2-bit tiers hand on untried (non-ACGT bytes, the wildcard):
+   * 4-bit symbol codes, 8 bases per window word; what it cannot take (other bytes than ACGTNRYK and the wildcard,
+   * wavefronts beyond 256 diagonals) goes on to the scalar tiers */
+  if (!no_reg && !dbg.no_regb && any_bytes && !B.two_p && !k.m_only && k.heuristic == 0 && std::max(B.maxp, B.maxt) <= REG_MAX_LEN &&
+      4 * winw <= 8192 && regb_tier_supported(k.dx, k.doe1, k.de1, B.full)) {
+    Tier t;
+    t.regs = regb_regs(); t.bytes = true; t.mode = 0; t.threads = 128; t.groups_per_block = 4; t.wcap = 64 * t.regs;
+    t.scap = 32 * t.regs + k.doe1 + 1;
+    t.seq_words_cap = winw + (B.maxp >> 3) + (B.maxt >> 3) + 4;       /* windows + the symbol codes they are built from */
+    t.group_bytes = (4 * t.seq_words_cap + 15) & ~15; t.smem = (size_t)t.group_bytes * 4;
+    B.tiers.push_back(t);
+  }
   /* packed-halfword tiers (wfa_vec.cuh): everything the register tier does not take, reads up to
    * VEC_MAX_LEN; warp per pair first, then 8 and 16 warps per pair with the widest rings that
    * leave two / one CTA per SM */
@@ -392,7 +405,8 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
     }
   }
   for (auto& t : B.tiers) {
-    int bps = t.regs ? reg_occupancy(k, t.regs, B.full, t.threads, t.smem)
+    int bps = t.bytes ? regb_occupancy(k, B.full, t.threads, t.smem)
+              : t.regs ? reg_occupancy(k, t.regs, B.full, t.threads, t.smem)
               : t.mode == 2 ? grid_occupancy(B.two_p, B.full, t.smem)
               : t.vec_nw ? vec_occupancy(B.two_p, B.full, t.vec_nw, k.heuristic, t.threads, t.smem)
                          : align_occupancy(B.two_p, B.full, t.mode, t.off16, t.threads, t.smem);
@@ -639,6 +653,7 @@ void read_knobs(wfagpu_ctx* ctx) {
   auto num = [](const char* name) { const char* e = getenv(name); return e ? atoll(e) : 0ll; };
   k.trace = flag("WFAGPU_TRACE");
   k.no_reg = flag("WFAGPU_NO_REG_TIER");
+  k.no_regb = flag("WFAGPU_NO_REG_BYTES");
   k.no_vec = flag("WFAGPU_NO_VEC_TIER");
   k.no_tier_skip = flag("WFAGPU_NO_TIER_SKIP");
   k.no_buckets = flag("WFAGPU_NO_BUCKETS");
@@ -1038,7 +1053,8 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         const bool probing = t.mode != 0 && ti + 1 < bk.tiers.size() && !ctx->knobs.no_tier_skip && nwork >= 3 * groups;
         k.work_limit = probing ? (int)groups : INT_MAX;
         auto launch_tier = [&]() -> int {
-          if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
+          if (t.bytes) CK(launch_regb(k, b->full, blocks, t.threads, t.smem, st));
+          else if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
           else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
           else if (t.mode == 2) {
             CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
@@ -1070,7 +1086,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         }
         if (trace)
           fprintf(stderr, "[wfagpu]   bucket %d (<= %d bp) tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d)%s\n",
-                  q, bk.max_len, ti, t.vec_nw ? "vec" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
+                  q, bk.max_len, ti, t.vec_nw ? "vec" : t.bytes ? "reg-bytes" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
                   chain_on ? " +" : "");
         cur_list = lists[li & 1];
         last_li = li;

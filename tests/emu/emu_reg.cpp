@@ -29,6 +29,22 @@ static int run_pair(bool full, const RegParams& R, const uint32_t* pw, const uin
   return align_pair_reg<P, DX, DOE, false>(R, pw, tw, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res);
 }
 
+/* byte mode (what wfa_regb_kernel does per pair): bytes -> 4-bit symbol codes -> windows of 8 bases; a pair holding
+ * a byte outside the symbol set is handed on like an overflow */
+template <int P, int DX, int DOE>
+static int run_pair_bytes(bool full, const RegParams& R, const uint32_t* pb, const uint32_t* tb, int plen, int tlen, int wild,
+                          uint8_t* hist, uint8_t* ops, uint32_t* stage, PairResult& res) {
+  std::vector<uint32_t> pn((size_t)(plen >> 3) + 2), tn((size_t)(tlen >> 3) + 2);
+  const bool okp = nibble_words(pb, plen, pn.data(), wild), okt = nibble_words(tb, tlen, tn.data(), wild);
+  if (!okp || !okt) return PAIR_OVERFLOW;
+  std::vector<uint32_t> pwin((size_t)plen + 1), twin((size_t)tlen + 1);
+  build_windows<4>(pn.data(), plen, pwin.data());
+  build_windows<4>(tn.data(), tlen, twin.data());
+  const lv::histref h = lv::make_histref(hist, false);
+  if (full) return align_pair_reg<P, DX, DOE, true, false, 4>(R, pb, tb, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res, wild);
+  return align_pair_reg<P, DX, DOE, false, false, 4>(R, pb, tb, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res, wild);
+}
+
 /* regs = packed registers per wavefront (window = 64 * regs diagonals); hrows = origin rows */
 extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
                                    const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,
@@ -56,8 +72,17 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
   for (int64_t i = 0; i < n; ++i) {
     const int plen = p_len[i], tlen = t_len[i];
     std::vector<uint32_t> pw((plen + 15) / 16 + 1, 0), tw((tlen + 15) / 16 + 1, 0);
-    if (!pack_sequence(seq + p_off[i], plen, pw.data())) return -2;
-    if (!pack_sequence(seq + t_off[i], tlen, tw.data())) return -2;
+    const int wc = cfg->wildcard & 0xff;
+    bool bytes = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
+    if (!bytes) bytes = !pack_sequence(seq + p_off[i], plen, pw.data()) || !pack_sequence(seq + t_off[i], tlen, tw.data());
+    if (bytes) {
+      /* byte mode of the library (wfa_pack.cu pack_bytes_kernel): upper-cased bytes, 4 per word */
+      pw.assign((plen + 3) / 4 + 1, 0); tw.assign((tlen + 3) / 4 + 1, 0);
+      auto put = [](const uint8_t* s8, int len, uint32_t* out) {
+        for (int j = 0; j < len; ++j) { uint8_t c = s8[j]; if (c >= 'a' && c <= 'z') c -= 32; out[j >> 2] |= (uint32_t)c << (8 * (j & 3)); }
+      };
+      put(seq + p_off[i], plen, pw.data()); put(seq + t_off[i], tlen, tw.data());
+    }
     std::vector<uint32_t> stage((size_t)plen + tlen + 2);
     std::vector<uint8_t> ops((size_t)plen + tlen + 8);
     R.runcap = (int)stage.size(); R.opcap = (int)ops.size();
@@ -65,7 +90,8 @@ extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* se
     memset(&res, 0, sizeof res);
     int rc;
     if (plen > REG_MAX_LEN || tlen > REG_MAX_LEN) rc = PAIR_OVERFLOW;
-#define RUN(PP, DX, DOE) rc = run_pair<PP, DX, DOE>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res)
+#define RUN(PP, DX, DOE) rc = bytes ? run_pair_bytes<PP, DX, DOE>(full, R, pw.data(), tw.data(), plen, tlen, wc, hist.data(), ops.data(), stage.data(), res) \
+                                   : run_pair<PP, DX, DOE>(full, R, pw.data(), tw.data(), plen, tlen, hist.data(), ops.data(), stage.data(), res)
 #define RUN_SHAPE(PP) do { if (shape == 0) RUN(PP, 2, 4); else if (shape == 1) RUN(PP, 1, 1); else if (shape == 2) RUN(PP, 2, 1); \
                            else if (shape == 3) RUN(PP, 4, 7); else if (shape == 4) RUN(PP, 1, 2); else RUN(PP, 1, 3); } while (0)
     else if (regs == 1) RUN_SHAPE(1);

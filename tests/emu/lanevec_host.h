@@ -113,6 +113,8 @@ inline vu vfunnel_r(const vu& lo, const vu& hi, const vi& sh) {
   vu r; LV_FOR { const uint64_t v = ((uint64_t)hi.v[l] << 32) | lo.v[l]; r.v[l] = (uint32_t)(v >> (sh.v[l] & 31)); }
   return r;
 }
+inline vu nib_both(const vu& a, const vu& b) { vu r; LV_FOR r.v[l] = (a.v[l] & b.v[l] & 0x11111111u) * 15u; return r; }
+inline vu operator&(const vu& a, const vu& b) { vu r; LV_FOR r.v[l] = a.v[l] & b.v[l]; return r; }
 inline vi vclz(const vu& x) { vi r; LV_FOR r.v[l] = x.v[l] ? __builtin_clz(x.v[l]) : 32; return r; }
 inline vu vbrev(const vu& x) {
   vu r;

@@ -189,3 +189,65 @@ def test_register_tier_origin_rows_overflow(emu_reg, oracle):
     got = emu_reg(cfg, batch, 4, hrows=20)
     novf = compare(got, want, True)
     assert 0 < novf < 200
+
+
+def _pairs_with_symbols(seed, n, lo, hi, extra="N", p_x=0.03, t_x=0.04, odd=0.0):
+    """Mutated pairs sprinkled with `extra` symbols (and, with probability `odd` per pair, one byte outside the
+    register tier's symbol set)."""
+    rng = np.random.default_rng(seed)
+    rnd = lambda m, alpha="ACGT": "".join(alpha[i] for i in rng.integers(0, len(alpha), m))
+    pairs = []
+    for _ in range(n):
+        p = list(rnd(int(rng.integers(lo, hi))))
+        t = list(p)
+        for j in range(len(t)):
+            r = rng.random()
+            if r < 0.03: t[j] = rnd(1)
+            elif r < 0.045: t[j] = ""
+            elif r < 0.06: t[j] += rnd(2)
+            elif r < 0.06 + t_x: t[j] = rnd(1, extra)
+            elif r < 0.06 + 1.1 * t_x: t[j] = t[j].lower()
+        for j in range(len(p)):
+            if rng.random() < p_x: p[j] = rnd(1, extra)
+        if rng.random() < odd and p:
+            p[int(rng.integers(0, len(p)))] = "S"
+        pairs.append(("".join(p), "".join(t)))
+    return pairs
+
+
+REG_BYTE_KW = [
+    dict(span="end-to-end"),                                   # N equals N, differs from every base
+    dict(span="end-to-end", wildcard="N"),                     # pywfa's wildcard: N matches everything
+    dict(span="end-to-end", wildcard="N", scope="score"),
+    dict(wildcard="N", pattern_begin_free=3, text_end_free=5),
+    dict(span="end-to-end", wildcard="A"),                     # a base as the wildcard: every pair is a byte pair
+    dict(span="end-to-end", wildcard="X"),                     # a wildcard outside the symbol set
+    dict(span="end-to-end", gap_extension=1, wildcard="N"),    # shape (4, 7, 1)
+    dict(span="end-to-end", mismatch=1, gap_opening=0, gap_extension=1, scope="score", wildcard="N"),   # edit-like, score-only
+]
+
+
+@pytest.mark.parametrize("kw", REG_BYTE_KW, ids=[str(i) for i in range(len(REG_BYTE_KW))])
+def test_register_tier_byte_mode(emu_reg, oracle, kw):
+    """Byte mode on the register tier (4-bit symbol codes, 8 bases per window word; wfa_reg.cuh CB = 4): pairs with
+    N / IUPAC bytes, lower case and pywfa's wildcard= must equal the checker (which is pinned against the reference's
+    wavefront_align_lambda path in test_oracle.py); a pair with a byte outside the symbol set is handed on."""
+    extra = "NRYKX" if kw.get("wildcard") == "X" else "NRYK"
+    pairs = _pairs_with_symbols(7, 500, 20, 240, extra=extra, odd=0.05)
+    pairs += [("N", "N"), ("N", "A"), ("NNNN", "ACGT"), ("ACGTNNNNACGT", "ACGTACGT"), ("n" * 40, "N" * 40), ("", "N"), ("N", "")]
+    if kw.get("span") != "end-to-end":
+        pairs = [pt for pt in pairs if min(len(pt[0]), len(pt[1])) >= 10]
+    batch = pairs_from_strings(pairs)
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind="port")
+    got = emu_reg(cfg, batch, 4)
+    novf = compare(got, want, kw.get("scope", "full") == "full")
+    # handed on: the ~5 % of the pairs holding an 'S', and window overflows
+    odd = sum(("S" in p.upper() or "S" in t.upper()) for p, t in pairs)
+    if kw.get("wildcard") == "X":
+        odd = len(pairs)       # 'X' itself is fine (the wildcard), but count loosely: X-rich pairs may also overflow
+    assert novf <= odd + 0.05 * len(pairs), (novf, odd)
+    done = np.flatnonzero(got["ovf"] == 0)
+    assert len(done) > 0.8 * len(pairs) or kw.get("wildcard") == "X"
+    for i in done:
+        assert "S" not in pairs[i][0].upper() and "S" not in pairs[i][1].upper(), "a pair outside the symbol set was aligned"

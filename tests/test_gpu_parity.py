@@ -2,6 +2,7 @@
 seeded inputs (bit-exact score, status, CIGAR incl. tie-breaks, start/end coordinates).  The
 checker is the unmodified reference (oracle/_ref, compiled from /root/reference in the build
 container and shipped with the snapshot) whenever it is present, else the restatement."""
+import re
 import zlib
 
 import numpy as np
@@ -273,6 +274,39 @@ def test_byte_mode_non_acgt_and_wildcard(gpu_ctx, oracle):
     a = gpu_ctx.align_batch(oracle.make_config(span="end-to-end"), *plain)
     b = gpu_ctx.align_batch(oracle.make_config(span="end-to-end", wildcard="N"), *plain)
     assert_same(b, a, what="wildcard N on ACGT-only input")
+
+
+def test_byte_pairs_run_on_the_register_tier(gpu_ctx, oracle, monkeypatch, capfd):
+    """Pairs with N / IUPAC bytes (and the wildcard) are taken by the byte-mode register tier (wfa_reg_bytes.cu:
+    4-bit symbol codes, 8 bases per window word) instead of the scalar tiers: same results with the tier on and off,
+    and the tier's trace line shows that only the pairs outside its symbol set / window are handed on."""
+    from test_emu_reg import _pairs_with_symbols, REG_BYTE_KW
+    pairs = _pairs_with_symbols(31, 4000, 40, 260, extra="NRYK", odd=0.03)
+    n_odd = sum(1 for p, t in pairs if "S" in p.upper() or "S" in t.upper())
+    batch = pairs_from_strings(pairs)
+    for kw in REG_BYTE_KW:
+        if kw.get("span") != "end-to-end":
+            continue
+        cfg = oracle.make_config(**kw)
+        want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
+        monkeypatch.setenv("WFAGPU_TRACE", "1")
+        monkeypatch.setenv("WFAGPU_NO_BUCKETS", "1")        # one bucket: launch index = tier index in the trace
+        capfd.readouterr()
+        got = gpu_ctx.align_batch(cfg, *batch)
+        trace = capfd.readouterr().err
+        monkeypatch.delenv("WFAGPU_TRACE")
+        monkeypatch.delenv("WFAGPU_NO_BUCKETS")
+        assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"byte-mode register tier {kw}")
+        m = re.search(r"tier (\d+) \(reg-bytes", trace)
+        assert m, trace[-2000:]
+        # "<n> pairs in -> a b c overflowed": the pairs each tier of a chain of launches handed on, in tier order
+        handed = [int(x) for ln in trace.splitlines() if "pairs in ->" in ln
+                  for x in ln.split("->")[1].split("overflowed")[0].split()]
+        assert handed[int(m.group(1))] <= n_odd + 0.05 * len(pairs), (handed, n_odd)
+        monkeypatch.setenv("WFAGPU_NO_REG_BYTES", "1")
+        off = gpu_ctx.align_batch(cfg, *batch)
+        monkeypatch.delenv("WFAGPU_NO_REG_BYTES")
+        assert_same(off, got, scope_full=kw.get("scope", "full") == "full", what=f"scalar tiers {kw}")
 
 
 def _check_cigar(runs, pattern, text, x, o1, e1, o2, e2):
