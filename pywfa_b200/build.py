@@ -47,6 +47,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
         ("wfa_kernels.cu", [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])),
         ("wfa_pack.cu", [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])),
         ("wfa_reg_bytes.cu", [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])),
+        ("wfa_vec_bytes.cu", [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])),
         ("wfagpu_api.cpp", ["g++"] + CXX_FLAGS + ["-I" + os.path.join(cuda, "include")]),
         ("pack.cpp", ["g++"] + CXX_FLAGS),
     ]

@@ -1026,6 +1026,8 @@ cudaError_t init_kernels(int smem_optin) {
   if (eb != cudaSuccess) return eb;
   const cudaError_t e2 = init_vec(smem_optin);
   if (e2 != cudaSuccess) return e2;
+  const cudaError_t e2b = init_vecb(smem_optin);
+  if (e2b != cudaSuccess) return e2b;
   const cudaError_t e3 = init_pair(smem_optin);
   if (e3 != cudaSuccess) return e3;
   return init_grid(smem_optin);

@@ -71,6 +71,11 @@ cudaError_t init_regb(int smem_optin);
 cudaError_t launch_vec(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st);
 int vec_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t smem);
 
+/* ... in byte mode (wfa_vec_bytes.cu): pairs with non-ACGT bytes / the wildcard */
+cudaError_t launch_vecb(const KParams& P, bool two_p, bool full, int nw, int heur, int grid, int block, size_t smem, cudaStream_t st);
+int vecb_occupancy(bool two_p, bool full, int nw, int heur, int block, size_t smem);
+cudaError_t init_vecb(int smem_optin);
+
 /* several CTAs per pair (long reads): groups * ncta co-resident CTAs of 512 threads; `scratch` holds
  * grid_scratch_bytes(groups) bytes of device memory */
 size_t grid_scratch_bytes(int groups);

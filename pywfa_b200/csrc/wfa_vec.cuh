@@ -58,9 +58,16 @@ constexpr uint32_t ONE2 = 0x00010001u;
 #ifndef WFA_VEC_PAD
 #define WFA_VEC_PAD 1
 #endif
+/* WFA_VEC_BYTES (defined by wfa_vec_bytes.cu only): byte mode.  The sequence windows hold 8 four-bit symbol codes
+ * per word (lv::nib_pack8: wildcard 0, A C G T N R Y K 8..15) instead of 16 two-bit codes, every group size uses the
+ * windows, and the replay of the backtrace compares the pair's bytes (bpw / btw: 4 per word). */
+#ifndef WFA_VEC_BYTES
+#define WFA_VEC_BYTES 0
+#endif
 #ifndef WFA_VEC_EXT2
 #define WFA_VEC_EXT2 0      /* interleaving the two extensions of a lane measured slower (r01: -6 % on cfg3) */
 #endif
+#define VEC_WIN(NW) ((NW) > 1 || WFA_VEC_BYTES != 0)   /* the window variant of the extension is compiled in */
 constexpr int RENORM_MASK = 4095;          /* I/D nulls drift by one per step: re-based every 4096 scores */
 
 /* per-step reduction cells in shared memory (three rotating sets) */
@@ -133,12 +140,22 @@ template <bool WIN>
 __device__ __forceinline__ int vext(const uint32_t* pw, const uint32_t* tw, int seqw, int v, int h, int rem) {
   int n = 0;
   if (WIN && seqw) {
+#if WFA_VEC_BYTES
+    /* 8 symbol codes per window; a position where either side is the wildcard (code 0) never differs */
+    while (n < rem) {
+      const uint32_t a = pw[v + n], b = tw[h + n];
+      const int c = __clz((int)((a ^ b) & ((a & b & 0x11111111u) * 15u))) >> 2;
+      n += c;
+      if (c < 8) break;
+    }
+#else
     /* per-base windows: 16 bases = LDS, LDS, XOR, CLZ */
     while (n < rem) {
       const int a = __clz((int)(pw[v + n] ^ tw[h + n])) >> 1;
       n += a;
       if (a < 16) break;
     }
+#endif
     return imin(n, rem);
   }
   while (n < rem) {
@@ -319,7 +336,7 @@ __device__ inline int backtrace_vcodes(const KParams& P, const uint8_t* h_code, 
     if (is_ins) --k; else ++k;
   }
   if (nops > opcap) return -1;
-  replay_ops(ops, nops, k, plen, tlen, pw, tw, em);
+  replay_ops(ops, nops, k, plen, tlen, pw, tw, em, WFA_VEC_BYTES ? P.wildcard : -1);
   return em.n;
 }
 
@@ -602,7 +619,7 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
       const int u0 = imax(imin(tlen, plen + k0), UB_MIN), u1 = imax(imin(tlen, plen + k0 + 1), UB_MIN);
       const int s0 = (k0 >= lo0 && k0 <= hi0) ? imax(k0, 0) : NULL16;
       const int s1 = (k0 + 1 >= lo0 && k0 + 1 <= hi0) ? imax(k0 + 1, 0) : NULL16;
-      finish_m<(NW > 1)>(cx, rM, vm.flags, false, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
+      finish_m<VEC_WIN(NW)>(cx, rM, vm.flags, false, lv::pack2(s0, s1), pos, k0, u0, u1, kblock, lane);
     }
     for (int c = 0; c < 5; ++c) { clo[c] = 1; chi[c] = -1; }
     clo[CM] = lo0; chi[CM] = hi0;
@@ -847,8 +864,8 @@ __device__ int align_pair_vec(const KParams& P, const VMem& vm, int plen, int tl
               if (pl.oI2 >= 0) vm.ring[pl.oI2 + posb + lane] = NULL2;
               if (pl.oD2 >= 0) vm.ring[pl.oD2 + posb + lane] = NULL2;
             }
-          } else if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false, (NW > 1)>(cx, pl, Fn, exact, b, posb, lane);
-          else vec_block<TWO_P, FULL, true, (NW > 1)>(cx, pl, Fn, exact, b, posb, lane);
+          } else if (b >= pl.fl && b <= pl.fh) vec_block<TWO_P, FULL, false, VEC_WIN(NW)>(cx, pl, Fn, exact, b, posb, lane);
+          else vec_block<TWO_P, FULL, true, VEC_WIN(NW)>(cx, pl, Fn, exact, b, posb, lane);
         }
       }
       WFA_TM(2)

@@ -308,21 +308,21 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
   const bool no_vec = dbg.no_vec;
   bool vec_covers_smem = false;
   const bool use_vec = !no_vec && !B.byte_mode && !k.m_only && std::max(B.maxp, B.maxt) <= VEC_MAX_LEN;   /* byte mode, gap-linear / edit / indel: scalar tiers */
-  if (use_vec) {
-    const int nslots = k.rm + 2 * k.r1 + (B.two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
-    const long long nblk_max = (wmax + 63) / 64 + 1;
-    long long last_nblk = 0;
-    auto add_vec = [&](int nw, long long budget, long long hcap, long long scap) {
+  const int nslots = k.rm + 2 * k.r1 + (B.two_p ? 2 * k.r2 : 0) + 1;      /* + the all-null slot */
+  const long long nblk_max = (wmax + 63) / 64 + 1;
+  long long last_nblk = 0;
+  /* bytes: the byte-mode kernels (wfa_vec_bytes.cu): always windows (8 symbol codes per word), plus the codes they are built from */
+  auto add_vec = [&](int nw, long long budget, long long hcap, long long scap, bool bytes) {
       /* per-base sequence windows (one word per base: 16 bases = LDS, LDS, XOR, CLZ) where they are small
        * next to the rings, 2-bit packed words otherwise */
-      const long long winw = (long long)B.maxp + B.maxt + 2;
-      const bool seqw_t = nw > 1 && 4 * winw <= 16384;          /* (the one-warp kernel is compiled without the window variant) */
+      const long long winw = (long long)B.maxp + B.maxt + 2 + (bytes ? (B.maxp >> 3) + (B.maxt >> 3) + 4 : 0);
+      const bool seqw_t = bytes || (nw > 1 && 4 * winw <= 16384);          /* (the one-warp kernel is compiled without the window variant) */
       const long long fixed = (long long)k.mr * 48 + 256 + 4 * (seqw_t ? winw : seqw2) + 512;   /* + two step plans */
       long long nblk = (budget - fixed) / ((long long)nslots * 128);
       nblk = std::min(nblk, nblk_max);
       if (nblk < 2 || nblk <= last_nblk) return;
       Tier t;
-      t.vec_nw = nw; t.mode = nw == 1 ? 0 : 1;
+      t.vec_nw = nw; t.mode = nw == 1 ? 0 : 1; t.bytes = bytes;
       t.threads = nw == 1 ? 128 : nw * 32; t.groups_per_block = nw == 1 ? 4 : 1;
       t.wcap = (int)(64 * nblk); t.seq_words_cap = (int)(seqw_t ? winw : seqw2); t.vec_seqw = seqw_t;
       t.group_bytes = (int)((fixed + nblk * nslots * 128 + 15) & ~15ll);
@@ -332,16 +332,22 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
       t.hcap = (t.hcap + 63) & ~63ll;
       B.tiers.push_back(t);
       last_nblk = nblk;
-      if (nblk == nblk_max) vec_covers_smem = true;
-    };
+      if (nblk == nblk_max && !bytes) vec_covers_smem = true;
+  };
+  auto add_vecs = [&](bool bytes) {
+    last_nblk = 0;
     const int only = dbg.vec_nw;                          /* tests: push everything through one group size */
     if (!only || only == 1) {
-      add_vec(1, 11264 + 512, 2ll << 20, 16384);
-      if (last_nblk == 0) add_vec(1, 22528 + 512, 2ll << 20, 16384);
+      add_vec(1, 11264 + 512, 2ll << 20, 16384, bytes);
+      if (last_nblk == 0) add_vec(1, 22528 + 512, 2ll << 20, 16384, bytes);
     }
-    if (!only || only == 8) add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768);
-    if (!only || only == 16) add_vec(16, smem_max - 1024, 64ll << 20, 65536);
-  }
+    if (!only || only == 8) add_vec(8, (smem_max - 2048) / 2, 16ll << 20, 32768, bytes);
+    if (!only || only == 16) add_vec(16, smem_max - 1024, 64ll << 20, 65536, bytes);
+  };
+  if (use_vec) add_vecs(false);
+  /* ... and in byte mode, for the pairs the 2-bit tiers hand on untried; what these cannot take (other bytes than
+   * ACGTNRYK and the wildcard, wavefronts beyond the rings) ends on the scalar tiers below */
+  if (!no_vec && !dbg.no_regb && any_bytes && !k.m_only && std::max(B.maxp, B.maxt) <= VEC_MAX_LEN) add_vecs(true);
   int last_wcap = 0;
   auto add_warp = [&](int wcap, long long hcap, int scap) {
     if ((vec_covers_smem || use_vec) && !any_bytes) return;   /* the vec tiers replace the scalar shared-memory tiers (byte-mode pairs still need them) */
@@ -405,8 +411,9 @@ void plan_tiers(wfagpu_ctx* ctx, wfagpu_batch* b, Bucket& bk) {
     }
   }
   for (auto& t : B.tiers) {
-    int bps = t.bytes ? regb_occupancy(k, B.full, t.threads, t.smem)
+    int bps = t.regs && t.bytes ? regb_occupancy(k, B.full, t.threads, t.smem)
               : t.regs ? reg_occupancy(k, t.regs, B.full, t.threads, t.smem)
+              : t.vec_nw && t.bytes ? vecb_occupancy(B.two_p, B.full, t.vec_nw, k.heuristic, t.threads, t.smem)
               : t.mode == 2 ? grid_occupancy(B.two_p, B.full, t.smem)
               : t.vec_nw ? vec_occupancy(B.two_p, B.full, t.vec_nw, k.heuristic, t.threads, t.smem)
                          : align_occupancy(B.two_p, B.full, t.mode, t.off16, t.threads, t.smem);
@@ -1053,8 +1060,9 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         const bool probing = t.mode != 0 && ti + 1 < bk.tiers.size() && !ctx->knobs.no_tier_skip && nwork >= 3 * groups;
         k.work_limit = probing ? (int)groups : INT_MAX;
         auto launch_tier = [&]() -> int {
-          if (t.bytes) CK(launch_regb(k, b->full, blocks, t.threads, t.smem, st));
+          if (t.regs && t.bytes) CK(launch_regb(k, b->full, blocks, t.threads, t.smem, st));
           else if (t.regs) CK(launch_reg(k, t.regs, b->full, blocks, t.threads, t.smem, st));
+          else if (t.vec_nw && t.bytes) CK(launch_vecb(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
           else if (t.vec_nw) CK(launch_vec(k, b->two_p, b->full, t.vec_nw, k.heuristic, blocks, t.threads, t.smem, st));
           else if (t.mode == 2) {
             CK(ctx->gscratch.ensure(grid_scratch_bytes((int)groups)));
@@ -1086,7 +1094,7 @@ int batch_run(wfagpu_ctx* ctx, wfagpu_batch* b, cudaStream_t st, DevCounters* hc
         }
         if (trace)
           fprintf(stderr, "[wfagpu]   bucket %d (<= %d bp) tier %zu (%s nw=%d regs=%d mode=%d wcap=%d smem=%zu B x %d CTA/SM, grid %d x %d)%s\n",
-                  q, bk.max_len, ti, t.vec_nw ? "vec" : t.bytes ? "reg-bytes" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
+                  q, bk.max_len, ti, t.vec_nw ? (t.bytes ? "vec-bytes" : "vec") : t.bytes ? "reg-bytes" : t.regs ? "reg" : "scalar", t.vec_nw, t.regs, t.mode, t.wcap, t.smem, t.blocks_per_sm, blocks * grid_ctas, t.threads,
                   chain_on ? " +" : "");
         cur_list = lists[li & 1];
         last_li = li;

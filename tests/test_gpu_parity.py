@@ -276,37 +276,56 @@ def test_byte_mode_non_acgt_and_wildcard(gpu_ctx, oracle):
     assert_same(b, a, what="wildcard N on ACGT-only input")
 
 
-def test_byte_pairs_run_on_the_register_tier(gpu_ctx, oracle, monkeypatch, capfd):
-    """Pairs with N / IUPAC bytes (and the wildcard) are taken by the byte-mode register tier (wfa_reg_bytes.cu:
-    4-bit symbol codes, 8 bases per window word) instead of the scalar tiers: same results with the tier on and off,
-    and the tier's trace line shows that only the pairs outside its symbol set / window are handed on."""
-    from test_emu_reg import _pairs_with_symbols, REG_BYTE_KW
-    pairs = _pairs_with_symbols(31, 4000, 40, 260, extra="NRYK", odd=0.03)
+BYTE_TIER_CASES = [
+    # config, lengths, pairs, byte-mode tier(s) expected in the plan
+    (dict(span="end-to-end"), (40, 260), 4000, ("reg-bytes",)),
+    (dict(span="end-to-end", wildcard="N"), (40, 260), 4000, ("reg-bytes",)),
+    (dict(span="end-to-end", wildcard="N", scope="score"), (40, 260), 4000, ("reg-bytes",)),
+    (dict(span="end-to-end", wildcard="A"), (40, 260), 3000, ("reg-bytes",)),
+    (dict(span="end-to-end", gap_extension=1, wildcard="N"), (40, 260), 3000, ("reg-bytes",)),
+    (dict(span="end-to-end", wildcard="N"), (500, 1200), 400, ("reg-bytes", "vec-bytes")),
+    (dict(distance="affine2p", wildcard="N"), (40, 300), 3000, ("vec-bytes",)),
+    (dict(distance="affine2p", span="end-to-end"), (600, 1100), 300, ("vec-bytes",)),
+    (dict(distance="affine2p", wildcard="N", pattern_begin_free=5, text_end_free=9, scope="score"), (300, 700), 500, ("vec-bytes",)),
+    (dict(heuristic="adaptive", span="end-to-end", wildcard="N"), (1500, 2500), 120, ("vec-bytes",)),
+    (dict(heuristic="X-drop", span="end-to-end", wildcard="N"), (300, 600), 300, ("vec-bytes",)),
+    (dict(match=-1, span="end-to-end", wildcard="N"), (100, 400), 1000, ("vec-bytes",)),
+]
+
+
+@pytest.mark.parametrize("kw,lens,n,tiers", BYTE_TIER_CASES, ids=[str(i) for i in range(len(BYTE_TIER_CASES))])
+def test_byte_pairs_run_on_the_fast_tiers(gpu_ctx, oracle, monkeypatch, capfd, kw, lens, n, tiers):
+    """Pairs with N / IUPAC bytes (and the wildcard) are taken by the byte-mode register tier (wfa_reg_bytes.cu) and
+    the byte-mode packed-halfword tiers (wfa_vec_bytes.cu) -- 4-bit symbol codes, 8 bases per window word -- instead
+    of the scalar tiers: bit-exact against the checker, same results with these tiers switched off, and the trace
+    shows that only the pairs outside their symbol set / capacity are handed on to the scalar tiers."""
+    from test_emu_reg import _pairs_with_symbols
+    div = 1.0 if lens[1] <= 400 else 0.4            # longer reads: fewer odd symbols, so that cut-offs keep their shape
+    pairs = _pairs_with_symbols(31 + n, n, lens[0], lens[1], extra="NRYK", p_x=0.03 * div, t_x=0.04 * div, odd=0.03)
     n_odd = sum(1 for p, t in pairs if "S" in p.upper() or "S" in t.upper())
     batch = pairs_from_strings(pairs)
-    for kw in REG_BYTE_KW:
-        if kw.get("span") != "end-to-end":
-            continue
-        cfg = oracle.make_config(**kw)
-        want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
-        monkeypatch.setenv("WFAGPU_TRACE", "1")
-        monkeypatch.setenv("WFAGPU_NO_BUCKETS", "1")        # one bucket: launch index = tier index in the trace
-        capfd.readouterr()
-        got = gpu_ctx.align_batch(cfg, *batch)
-        trace = capfd.readouterr().err
-        monkeypatch.delenv("WFAGPU_TRACE")
-        monkeypatch.delenv("WFAGPU_NO_BUCKETS")
-        assert_same(got, want, scope_full=kw.get("scope", "full") == "full", what=f"byte-mode register tier {kw}")
-        m = re.search(r"tier (\d+) \(reg-bytes", trace)
-        assert m, trace[-2000:]
-        # "<n> pairs in -> a b c overflowed": the pairs each tier of a chain of launches handed on, in tier order
-        handed = [int(x) for ln in trace.splitlines() if "pairs in ->" in ln
-                  for x in ln.split("->")[1].split("overflowed")[0].split()]
-        assert handed[int(m.group(1))] <= n_odd + 0.05 * len(pairs), (handed, n_odd)
-        monkeypatch.setenv("WFAGPU_NO_REG_BYTES", "1")
-        off = gpu_ctx.align_batch(cfg, *batch)
-        monkeypatch.delenv("WFAGPU_NO_REG_BYTES")
-        assert_same(off, got, scope_full=kw.get("scope", "full") == "full", what=f"scalar tiers {kw}")
+    full = kw.get("scope", "full") == "full"
+    cfg = oracle.make_config(**kw)
+    want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
+    monkeypatch.setenv("WFAGPU_TRACE", "1")
+    monkeypatch.setenv("WFAGPU_NO_BUCKETS", "1")        # one bucket: launch index = tier index in the trace
+    capfd.readouterr()
+    got = gpu_ctx.align_batch(cfg, *batch)
+    trace = capfd.readouterr().err
+    monkeypatch.delenv("WFAGPU_TRACE")
+    monkeypatch.delenv("WFAGPU_NO_BUCKETS")
+    assert_same(got, want, scope_full=full, what=f"byte-mode fast tiers {kw}")
+    idx = [int(m.group(1)) for name in tiers for m in re.finditer(r"tier (\d+) \(%s" % name, trace)]
+    assert idx, trace[-3000:]
+    # "<n> pairs in -> a b c overflowed": the pairs each tier of a chain of launches handed on, in tier order
+    handed = [int(x) for ln in trace.splitlines() if "pairs in ->" in ln
+              for x in ln.split("->")[1].split("overflowed")[0].split()]
+    last = max(i for i in idx if i < len(handed))
+    assert handed[last] <= n_odd + 0.1 * len(pairs), (handed, idx, n_odd)    # + pairs beyond the tiers' capacity
+    monkeypatch.setenv("WFAGPU_NO_REG_BYTES", "1")
+    off = gpu_ctx.align_batch(cfg, *batch)
+    monkeypatch.delenv("WFAGPU_NO_REG_BYTES")
+    assert_same(off, got, scope_full=full, what=f"scalar tiers {kw}")
 
 
 def _check_cigar(runs, pattern, text, x, o1, e1, o2, e2):
