@@ -12,11 +12,13 @@ import pywfa_b200
 from pywfa_b200 import _ffi
 from pywfa_b200.synth import generate_pairs
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+n0 = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 ctx = _ffi.Context(0)
-for length, div in ((150, 0.05), (250, 0.10)):
+for length, div, base_kw, fracs in ((150, 0.05, dict(span="end-to-end"), (0.0, 0.02, 0.2, 1.0)), (250, 0.10, dict(span="end-to-end"), (0.0, 0.02, 0.2, 1.0)),
+                                    (1000, 0.10, dict(distance="affine2p"), (0.0, 0.05, 1.0)), (1000, 0.10, dict(span="end-to-end"), (0.0, 0.05, 1.0))):
+    n = n0 if length < 1000 else max(1000, n0 // 20)
     seq, po, pl, to, tl = generate_pairs(n, length, div, seed=11)
-    for frac in (0.0, 0.02, 0.2, 1.0):
+    for frac in fracs:
         s = seq.copy()
         rng = np.random.default_rng(5)
         dirty = np.flatnonzero(rng.random(n) < frac)
@@ -25,7 +27,7 @@ for length, div in ((150, 0.05), (250, 0.10)):
         s[to[dirty] + rng.integers(0, np.maximum(tl[dirty], 1))] = ord("N")
         for kw in (dict(), dict(wildcard="N")):
             for scope in ("score", "full"):
-                cfg = pywfa_b200.WavefrontAligner(span="end-to-end", scope=scope, **kw)._cfg
+                cfg = pywfa_b200.WavefrontAligner(scope=scope, **base_kw, **kw)._cfg
                 rates = []
                 for off in (False, True):
                     if off:
@@ -40,6 +42,6 @@ for length, div in ((150, 0.05), (250, 0.10)):
                         b.run()
                     rates.append(n / ((time.perf_counter() - t0) / 3) / 1e6)
                     b.free()
-                print(f"{length} bp, {100 * frac:5.1f} % of the pairs with N, {str(kw):20s} scope={scope:5s}: "
-                      f"{rates[0]:7.1f} M pairs/s with the byte-mode register tier, {rates[1]:7.1f} without", flush=True)
+                print(f"{n} x {length} bp {base_kw}, {100 * frac:5.1f} % of the pairs with N, {str(kw):20s} scope={scope:5s}: "
+                      f"{rates[0]:7.1f} M pairs/s with the byte-mode fast tiers, {rates[1]:7.1f} without", flush=True)
 os.environ.pop("WFAGPU_NO_REG_BYTES", None)

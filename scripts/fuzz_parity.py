@@ -1,6 +1,7 @@
 """Randomised differential check of the CUDA path against the CPU checker: random penalties, spans,
 free ends, cut-offs, lengths and divergences (incl. unequal lengths and N-holding pairs).
-    python scripts/fuzz_parity.py [rounds] [seed]
+    python scripts/fuzz_parity.py [rounds] [seed] [bytes]
+(third argument "bytes": every round draws N / IUPAC-holding pairs, half of them with the wildcard -- the byte-mode tiers)
 Prints one line per round; exits non-zero on the first mismatch (with the offending configuration)."""
 import sys
 import time
@@ -19,6 +20,7 @@ from test_emu import _pairs_with_n
 
 rounds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+only_bytes = len(sys.argv) > 3 and sys.argv[3] == "bytes"
 rng = np.random.default_rng(seed)
 build_library()
 oracle_py.build(ref=None if not oracle_py.have_ref() else False)
@@ -49,7 +51,7 @@ for r in range(rounds):
         kw.update(heuristic="X-drop", xdrop=int(rng.integers(5, 300)), steps_between_cutoffs=int(rng.integers(1, 5)))
     if rng.random() < 0.15:
         kw["max_steps"] = int(rng.integers(5, 400))
-    shape = rng.random()
+    shape = 1.0 if only_bytes else rng.random()
     if shape < 0.4:
         length, div = int(rng.integers(20, 600)), float(rng.choice([0.01, 0.05, 0.1, 0.2, 0.4]))
         batch = generate_pairs(int(rng.integers(200, 3000)), length, div, seed=int(rng.integers(1 << 30)))
@@ -69,8 +71,9 @@ for r in range(rounds):
         batch = pairs_from_strings(_ragged_pairs(int(rng.integers(1 << 30)), int(rng.integers(100, 800)), lo, int(rng.integers(lo + 10, 500))))
         minlen = 0
     else:
-        batch = pairs_from_strings(_pairs_with_n(int(rng.integers(1 << 30)), int(rng.integers(100, 1500)), 20, int(rng.integers(60, 400)),
-                                                 p_n=float(rng.choice([0.0005, 0.01])), t_n=float(rng.choice([0.0005, 0.02]))))
+        hi = int(rng.integers(60, 400)) if rng.random() < 0.7 else int(rng.integers(400, 3000))
+        batch = pairs_from_strings(_pairs_with_n(int(rng.integers(1 << 30)), int(rng.integers(100, 1500)) if hi < 400 else int(rng.integers(20, 200)),
+                                                 20, hi, p_n=float(rng.choice([0.0005, 0.01])), t_n=float(rng.choice([0.0005, 0.02]))))
         if rng.random() < 0.6:
             kw["wildcard"] = "N"
         minlen = 0
