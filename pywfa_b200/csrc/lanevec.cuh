@@ -97,6 +97,16 @@ __device__ __forceinline__ vu load_win_at(lanead a, vi idx, vb p, uint32_t dflt)
                : "=r"(r) : "r"(a + 4u * (uint32_t)idx), "r"((uint32_t)p), "n"(4 * IMM), "r"(dflt) : "memory");
   return r;
 }
+/* idx >= 0 ? a[idx + IA] ^ b[idx + IB] : 0x80000000 -- the first compare of an extension: one SETP on the offset itself,
+ * two predicated LDS and a predicated XOR (a null cell loads nothing and sees "first base differs") */
+template <int IA, int IB>
+__device__ __forceinline__ vu diff_win_nonneg(lanead a, lanead b, vi idx) {
+  vu r;
+  asm volatile("{\n\t.reg .pred q;\n\t.reg .u32 x, y;\n\tsetp.ge.s32 q, %3, 0;\n\tmov.u32 %0, 0x80000000;\n\t"
+               "@q ld.shared.u32 x, [%1+%4];\n\t@q ld.shared.u32 y, [%2+%5];\n\t@q xor.b32 %0, x, y;\n\t}"
+               : "=r"(r) : "r"(a + 4u * (uint32_t)idx), "r"(b + 4u * (uint32_t)idx), "r"(idx), "n"(4 * IA), "n"(4 * IB) : "memory");
+  return r;
+}
 /* min(a + b, c): VIADDMNMX */
 __device__ __forceinline__ vi vaddmin(vi a, vi b, vi c) { return __viaddmin_s32(a, b, c); }
 /* orders the warp's shared-memory accesses: what other lanes stored before is visible to the lane that reads after */

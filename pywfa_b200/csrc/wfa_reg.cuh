@@ -54,6 +54,9 @@
 
 namespace wfagpu {
 
+#ifndef WFA_REG_LEAN_EXT
+#define WFA_REG_LEAN_EXT 1     /* extension of a block: first compare with the predicate taken from the offset, one vote for the common visit */
+#endif
 constexpr uint32_t REG_NULL2 = 0xC000C000u;     /* two int16 nulls (-16384) */
 constexpr int REG_NULL16 = -16384;
 constexpr int REG_UB_MIN = -8192;              /* floor of ub[k] for diagonals left of the matrix */
@@ -229,6 +232,31 @@ struct RegAligner {
     const vb valid = off0 >= 0;
     /* 16 bases per XOR; a null cell loads nothing and sees "first base differs", so it never moves;
      * min(offset + matches, ub) clamps the run at the end of the diagonal (VIADDMNMX) */
+#if WFA_REG_LEAN_EXT
+    vi off;
+    if constexpr (CB == 2) {
+      /* the common visit -- every run ends within 16 bases and no cell touches the edge of the matrix -- costs one
+       * vote: "a cell needs a second look" = 16 bases matched and there is room left, or the offset reached ub */
+      const vu x = diff_win_nonneg<-32 * B, 0>(pa, ta, off0);
+      off = vaddmin(off0, vclz(x) >> 1, ubk);
+      vb more = (x == 0u) & (off < ubk);
+      if (!any(more | (off >= ubk))) { mn = HI ? put_hi(mn, off) : put_lo(mn, off); return; }
+      while (any(more)) {
+        const vu y = diff_at<B>(off, more);
+        off = vaddmin(off, vclz(y) >> 1, ubk);
+        more = more & (y == 0u) & (off < ubk);
+      }
+    } else {
+      const vu x = diff_at<B>(off0, valid);
+      off = vaddmin(off0, vclz(x) >> LGC, ubk);
+      vb more = (x == 0u) & (off < ubk);
+      while (any(more)) {
+        const vu y = diff_at<B>(off, more);
+        off = vaddmin(off, vclz(y) >> LGC, ubk);
+        more = more & (y == 0u) & (off < ubk);
+      }
+    }
+#else
     const vu x = diff_at<B>(off0, valid);
     vi off = vaddmin(off0, vclz(x) >> LGC, ubk);
     vb more = (x == 0u) & (off < ubk);
@@ -237,6 +265,7 @@ struct RegAligner {
       off = vaddmin(off, vclz(y) >> LGC, ubk);
       more = more & (y == 0u) & (off < ubk);
     }
+#endif
     mn = HI ? put_hi(mn, off) : put_lo(mn, off);
     /* a cell on the edge of the matrix (null offsets are far below every ub) */
     const vb edge = off >= ubk;

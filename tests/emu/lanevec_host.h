@@ -130,6 +130,12 @@ template <int IMM>
 inline vu load_win_at(const lanead& a, const vi& idx, const vb& p, uint32_t dflt) {
   vu r; LV_FOR r.v[l] = (p.m >> l & 1) ? a.base[a.idx0.v[l] + idx.v[l] + IMM] : dflt; return r;
 }
+template <int IA, int IB>
+inline vu diff_win_nonneg(const lanead& a, const lanead& b, const vi& idx) {
+  vu r;
+  LV_FOR r.v[l] = idx.v[l] >= 0 ? (a.base[a.idx0.v[l] + idx.v[l] + IA] ^ b.base[b.idx0.v[l] + idx.v[l] + IB]) : 0x80000000u;
+  return r;
+}
 inline vi vaddmin(const vi& a, const vi& b, const vi& c) { vi r; LV_FOR { const int t = a.v[l] + b.v[l]; r.v[l] = t < c.v[l] ? t : c.v[l]; } return r; }
 inline vb operator==(const vu& a, uint32_t b) { vb r{0}; LV_FOR if (a.v[l] == b) r.m |= 1u << l; return r; }
 inline void fence_warp() {}          /* one host thread models the whole warp: nothing to order */
