@@ -387,17 +387,25 @@ __global__ void __launch_bounds__(512, 2) wfa_grid_kernel(const __grid_constant_
                                the 192-diagonal window on cfg2 / cfg1: 6 -> 46.1 / 115.2, 7 -> 46.5 / 117.1, 8 -> 40.6 / 111.1
                                M pairs/s; with the 256-diagonal window only: 5 -> 41.6, 6 -> 42.8, 7 -> 37.3) */
 #endif
+/* r02, after the leaner extension (67 registers at 7 CTAs): 8 CTAs per SM (64 registers, no spills) for the 128- and
+ * 192-diagonal windows: cfg1 150.6 -> 165.0, cfg2 68.0 -> 69.8 M pairs/s */
 #ifndef WFA_REG_MINB2
-#define WFA_REG_MINB2 WFA_REG_MINB     /* ... for the 128-diagonal window */
+#define WFA_REG_MINB2 8                /* ... for the 128-diagonal window */
 #endif
 #ifndef WFA_REG_MINB3
-#define WFA_REG_MINB3 WFA_REG_MINB     /* ... for the 192-diagonal window */
+#define WFA_REG_MINB3 8                /* ... for the 192-diagonal window */
 #endif
-__host__ __device__ constexpr int reg_min_blocks(int regs) { return regs == 2 ? WFA_REG_MINB2 : regs == 3 ? WFA_REG_MINB3 : WFA_REG_MINB; }
+#ifndef WFA_REG_MINB4
+#define WFA_REG_MINB4 6                /* ... for the 256-diagonal window (80 registers: no spills; r01: 6 -> 42.8, 7 -> 37.3 M pairs/s on that window alone) */
+#endif
+/* (shapes with a deep M ring -- (4, 7, 1): seven slots per packed register -- keep the 72-register budget) */
+__host__ __device__ constexpr int reg_min_blocks(int regs, int ring) {
+  return regs >= 4 ? WFA_REG_MINB4 : ring > 4 ? WFA_REG_MINB : regs == 2 ? WFA_REG_MINB2 : WFA_REG_MINB3;
+}
 /* ---- the register-resident tier (wfa_reg.cuh): warp-per-pair, wavefronts in registers ---- */
 /* shared memory of one warp: the sequence windows of the pair (seq_words_cap words, one per base + 2) */
 template <int P, int DX, int DOE, bool FULL>
-__global__ void __launch_bounds__(128, reg_min_blocks(P)) wfa_reg_kernel(const __grid_constant__ KParams K) {
+__global__ void __launch_bounds__(128, reg_min_blocks(P, DX > DOE ? DX : DOE)) wfa_reg_kernel(const __grid_constant__ KParams K) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool HS = reg_hist_in_smem(P, FULL);        /* origin arena, edit-operation stack and run staging in shared memory */
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

@@ -57,6 +57,11 @@ namespace wfagpu {
 #ifndef WFA_REG_LEAN_EXT
 #define WFA_REG_LEAN_EXT 1     /* extension of a block: first compare with the predicate taken from the offset, one vote for the common visit */
 #endif
+#ifndef WFA_REG_NARROW
+#define WFA_REG_NARROW 0       /* 1: recurrence and ring rotation on the middle register(s) only while the wavefront stays inside them.
+                                  Measured r02 with the lean extension: cfg2 68.0 M pairs/s with it, 72.0 without (the two push variants
+                                  cost more register moves in the step's tail than the narrow recurrence saves) */
+#endif
 constexpr uint32_t REG_NULL2 = 0xC000C000u;     /* two int16 nulls (-16384) */
 constexpr int REG_NULL16 = -16384;
 constexpr int REG_UB_MIN = -8192;              /* floor of ub[k] for diagonals left of the matrix */
@@ -475,7 +480,7 @@ struct RegAligner {
       /* phases A + B on the packed registers the wavefront can occupy: while it stays inside the middle
        * register(s) (about half the scores of a typical pair on the 192- and 256-diagonal windows) the
        * outer ones hold nothing but nulls in every ring slot and are neither computed nor rotated */
-      narrow = NLO > 0 && dlo >= 64 * NLO && dhi < 64 * (NHI + 1);
+      narrow = WFA_REG_NARROW && NLO > 0 && dlo >= 64 * NLO && dhi < 64 * (NHI + 1);
       if (narrow) {
         recurrence<NLO, NHI>(Mn);
 #pragma unroll
