@@ -66,7 +66,7 @@ struct PinBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-constexpr int MAX_LAUNCH = 64;      /* tier launches of one batch run, over all length buckets */
+constexpr int MAX_LAUNCH = 160;     /* tier launches of one batch run, over all length buckets (up to ~15 tiers per bucket when byte pairs exist) */
 struct DevCounters {       /* one per batch, in HBM */
   int work[MAX_LAUNCH];
   int retry[MAX_LAUNCH];
