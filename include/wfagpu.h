@@ -89,7 +89,9 @@ typedef struct wfagpu_config {
   int32_t max_steps;               /* <= 0 means unlimited (align.pyx:415)   */
   int32_t wildcard;                /* 0: none; else the (upper-case) byte that matches every base --
                                       pywfa's wildcard= kwarg, wavefront_align_lambda with
-                                      wildcard_match_fun (pywfa/align.pyx:297-304,438-442)          */
+                                      wildcard_match_fun (pywfa/align.pyx:297-304,438-442).  Pairs
+                                      whose bytes are among ACGTNRYK and this byte stay on the fast
+                                      kernels (4-bit symbol codes); any other byte: scalar kernels   */
 } wfagpu_config_t;
 
 typedef struct wfagpu_ctx wfagpu_ctx;       /* one per CUDA device            */
