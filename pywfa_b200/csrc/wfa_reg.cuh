@@ -60,7 +60,10 @@ namespace wfagpu {
 #ifndef WFA_REG_NARROW
 #define WFA_REG_NARROW 0       /* 1: recurrence and ring rotation on the middle register(s) only while the wavefront stays inside them.
                                   Measured r02 with the lean extension: cfg2 68.0 M pairs/s with it, 72.0 without (the two push variants
-                                  cost more register moves in the step's tail than the narrow recurrence saves) */
+                                  cost more register moves in the step's tail than the narrow recurrence saves).
+                                  2: narrow recurrence, but one rotation of the whole ring: measured last in r02, cfg2 73.8 against 72.1 M
+                                  pairs/s (+2.4 %); not the default because the round's GPU budget did not cover a second pass of the GPU
+                                  suite and a fresh ncu capture on it (CPU suite green with it) */
 #endif
 constexpr uint32_t REG_NULL2 = 0xC000C000u;     /* two int16 nulls (-16384) */
 constexpr int REG_NULL16 = -16384;
@@ -515,7 +518,7 @@ struct RegAligner {
       wprev = cur_hi - cur_lo + 1;                    /* 0 when nothing is valid (cur_lo = cur_hi + 1) */
     }
     /* (far from the matrix edges the outermost diagonals are reached by one gap of `reach` bases and are valid) */
-    if (narrow) push<NLO, NHI>(Mn, wprev > 0);
+    if (narrow && WFA_REG_NARROW == 1) push<NLO, NHI>(Mn, wprev > 0);      /* (2: narrow recurrence, one rotation of the whole ring) */
     else push<0, P - 1>(Mn, wprev > 0);
     /* step limit first, then termination (unialign.c:241-273 order); score 0 has no limit check */
     if (!seeding && s >= s_limit) {
