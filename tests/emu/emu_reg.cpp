@@ -45,6 +45,14 @@ static int run_pair_bytes(bool full, const RegParams& R, const uint32_t* pb, con
   return align_pair_reg<P, DX, DOE, false, false, 4>(R, pb, tb, pwin.data(), twin.data(), plen, tlen, h, ops, stage, true, res, wild);
 }
 
+/* the symbol table of byte mode: code of one byte (in the low byte of a word, 1 valid base); *bad = outside the set */
+extern "C" int emu_nib_code(int byte, int wild, int* bad) {
+  bool b = false;
+  const uint32_t w = lv::nib_pack8((uint32_t)byte & 0xffu, 0u, 1, (uint32_t)wild, b);
+  *bad = b ? 1 : 0;
+  return (int)(w & 15u) | (int)((w >> 4) != 0u ? 0x100 : 0);      /* (nothing may leak into the padding codes) */
+}
+
 /* regs = packed registers per wavefront (window = 64 * regs diagonals); hrows = origin rows */
 extern "C" int emu_reg_align_batch(const wfagpu_config_t* cfg, const uint8_t* seq, const int64_t* p_off,
                                    const int32_t* p_len, const int64_t* t_off, const int32_t* t_len, int64_t n,

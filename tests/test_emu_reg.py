@@ -251,3 +251,26 @@ def test_register_tier_byte_mode(emu_reg, oracle, kw):
     assert len(done) > 0.8 * len(pairs) or kw.get("wildcard") == "X"
     for i in done:
         assert "S" not in pairs[i][0].upper() and "S" not in pairs[i][1].upper(), "a pair outside the symbol set was aligned"
+
+
+def test_byte_mode_symbol_table(emu_reg):
+    """lv::nib_pack8 (lanevec.cuh): the wildcard is code 0, A C G T N R Y K get eight distinct codes with bit 3 set
+    (= "not the wildcard", what the extension's mask tests), every other byte is refused -- for every byte value."""
+    lib = C.CDLL(os.path.join(HERE, "emu", "libwfaemu_reg.so"))
+    lib.emu_nib_code.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+    lib.emu_nib_code.restype = C.c_int
+    for wild in (0, ord("N"), ord("A"), ord("X"), ord("n"), 255):
+        codes = {}
+        for byte in range(256):
+            bad = C.c_int(0)
+            code = lib.emu_nib_code(byte, wild, C.byref(bad))
+            assert code < 0x100, "a valid base leaked into the padding"
+            if wild and byte == wild:
+                assert (code, bad.value) == (0, 0)
+            elif chr(byte) in "ACGTNRYK":
+                assert bad.value == 0 and 8 <= code <= 15
+                codes[chr(byte)] = code
+            else:
+                assert bad.value == 1, (byte, wild)
+        expect = set("ACGTNRYK") - ({chr(wild)} if wild else set())
+        assert set(codes) == expect and len(set(codes.values())) == len(expect)
