@@ -1591,7 +1591,11 @@ extern "C" int wfagpu_align_pair(wfagpu_ctx* ctx, const wfagpu_config_t* cfg, co
   KParams k;
   memset(&k, 0, sizeof k);
   fill_kparams(*cfg, k);
-  const bool fast = cfg->distance == WFAGPU_DISTANCE_AFFINE && cfg->heuristic == WFAGPU_HEURISTIC_NONE && cfg->wildcard == 0 &&
+  /* a wildcard other than A, C, G, T changes nothing for a pair of pure ACGT reads, and the kernel hands every other
+   * pair back (rc = 1): loops like pywfa's a(text, pattern) with wildcard="N" keep the one-launch path */
+  const int wc = cfg->wildcard & 0xff;
+  const bool wc_is_base = wc == 'A' || wc == 'C' || wc == 'G' || wc == 'T';
+  const bool fast = cfg->distance == WFAGPU_DISTANCE_AFFINE && cfg->heuristic == WFAGPU_HEURISTIC_NONE && !wc_is_base &&
                     plen <= PAIR_MAX_LEN && tlen <= PAIR_MAX_LEN && k.dx == 2 && k.doe1 == 4 && k.de1 == 1;   /* the shape wfa_pair_kernel is compiled for */
   if (fast) {
     std::lock_guard<std::mutex> call(ctx->call_mu);

@@ -222,7 +222,7 @@ def test_single_pair_entry_point(gpu_ctx, oracle):
     for kw in (dict(span="end-to-end"), dict(), dict(span="end-to-end", scope="score"),
                dict(pattern_begin_free=0, pattern_end_free=0, text_begin_free=0, text_end_free=0, match=-1, span="end-to-end"),
                dict(distance="affine2p"), dict(heuristic="adaptive", span="end-to-end"),
-               dict(span="end-to-end", max_steps=30)):
+               dict(span="end-to-end", max_steps=30), dict(span="end-to-end", wildcard="N"), dict(span="end-to-end", wildcard="A")):
         cfg = oracle.make_config(**kw)
         want = oracle.align_batch(cfg, *batch, kind=oracle.checker_kind())
         full = kw.get("scope", "full") == "full"
@@ -234,6 +234,10 @@ def test_single_pair_entry_point(gpu_ctx, oracle):
                 assert locs == want["locs"][i].tolist(), (kw, i)
             else:
                 assert runs == []
+    # a wildcard that is not a base leaves clean pairs on the one-launch path; a pair holding it takes the batch path
+    cfg = oracle.make_config(span="end-to-end", wildcard="N")
+    assert gpu_ctx.align_pair(cfg, b"ACGTTACGTTTGA", b"ACGTAACGTTTGA")[0] == -4 and gpu_ctx.last_launches() == 1
+    assert gpu_ctx.align_pair(cfg, b"ACGTNACGTTTGA", b"ACGTAACGTTTGA")[0] == 0 and gpu_ctx.last_launches() > 1
     # the pywfa surface rides on it
     import pywfa_b200
     a = pywfa_b200.WavefrontAligner("TCTTTACTCGCGCGTTGGAGAAATACAATAGT")
