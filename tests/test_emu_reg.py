@@ -222,6 +222,8 @@ REG_BYTE_KW = [
     dict(wildcard="N", pattern_begin_free=3, text_end_free=5),
     dict(span="end-to-end", wildcard="A"),                     # a base as the wildcard: every pair is a byte pair
     dict(span="end-to-end", wildcard="X"),                     # a wildcard outside the symbol set
+    dict(span="end-to-end", wildcard="K"),                     # one of the eight symbols as the wildcard
+    dict(span="end-to-end", wildcard="n"),                     # lower case: never equals an (upper-cased) base, like in the reference
     dict(span="end-to-end", gap_extension=1, wildcard="N"),    # shape (4, 7, 1)
     dict(span="end-to-end", mismatch=1, gap_opening=0, gap_extension=1, scope="score", wildcard="N"),   # edit-like, score-only
 ]
